@@ -1,0 +1,307 @@
+"""render / batchify_rays / render_rays / render_path with the reference's signatures and return
+structure (DS_NeRF/run_nerf.py:74-307, 593-737), executed by the fused CUDA chunk pipeline
+(spn_render_rays_fwd / spn_render_rays_bwd): sample -> encode -> MLP -> composite -> resample ->
+encode -> MLP -> composite in one C call per ray chunk, with its own autograd node.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import check, f32, lib, ptr, stream
+from .nerf import NeRF, NeRF_RGB
+
+_DIFF = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0")
+
+
+def _flags(lindisp, white_bkgd, detach_weights, perturb, need_alpha):
+    return ((L.F_LINDISP if lindisp else 0) | (L.F_WHITE_BKGD if white_bkgd else 0) |
+            (L.F_DETACH_WEIGHTS if detach_weights else 0) | (L.F_PERTURB if perturb else 0) |
+            (L.F_NEED_ALPHA if need_alpha else 0))
+
+
+class RenderChunk(torch.autograd.Function):
+    """One ray chunk through spn_render_rays_fwd; backward = spn_render_rays_bwd into flat grads."""
+
+    @staticmethod
+    def forward(ctx, opts, rays, net_c, net_f, t_rand, u, noise0, noise1, *params):
+        rays = f32(rays)
+        n, ncols = rays.shape
+        S, NI = opts["N_samples"], opts["N_importance"]
+        S2 = S + NI
+        prec = net_c.precision
+        dev = rays.device
+        E = lambda *sh: torch.empty(sh, device=dev, dtype=torch.float32)
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        flat_c, packed_c = net_c._sync()
+        flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
+        cfg = L.RenderCfg(n, ncols, S, NI, _flags(opts["lindisp"], opts["white_bkgd"], opts["detach_weights"],
+                                                 opts["perturb"], opts["need_alpha"]), prec, float(opts["raw_noise_std"]))
+        io = L.RenderIO()
+        keep = dict(rays=rays, t_rand=t_rand, u=u, noise0=noise0, noise1=noise1,
+                    rgb_map=E(n, 3), disp_map=E(n), acc_map=E(n), depth_map=E(n), weights=E(n, S2), z_vals=E(n, S2),
+                    raw=E(n, S2, 4))
+        if NI > 0:
+            keep.update(rgb0=E(n, 3), disp0=E(n), acc0=E(n), z_std=E(n), z_coarse=E(n, S), raw_coarse=E(n, S, 4))
+        if opts["need_alpha"]:
+            keep.update(alpha=E(n, S2), alpha0=E(n, S))
+        need_stash = train or prec == L.PREC_FP32
+        if need_stash:
+            keep["stash_coarse"] = ops.mlp_stash(n * S, prec, dev)
+            if NI > 0:
+                keep["stash_fine"] = ops.mlp_stash(n * S2, prec, dev)
+        for k, v in keep.items():
+            setattr(io, k, ptr(v))
+        io.params_coarse, io.packed_coarse = ptr(flat_c), ptr(packed_c)
+        io.params_fine, io.packed_fine = ptr(flat_f), ptr(packed_f)
+        check(lib().spn_render_rays_fwd(C.byref(cfg), C.byref(io), stream()), "spn_render_rays_fwd")
+        ctx.state = (cfg, keep, net_c, net_f, train)
+        names = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "raw"]
+        if NI > 0:
+            names += ["rgb0", "disp0", "acc0", "z_std"]
+        if opts["need_alpha"]:
+            names += ["alpha", "alpha0"]
+        ctx.names = names
+        outs = tuple(keep[k] for k in names)
+        ctx.mark_non_differentiable(*[keep[k] for k in names if k not in _DIFF])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg, keep, net_c, net_f, train = ctx.state
+        if not train:
+            raise RuntimeError("RenderChunk.backward without a training forward")
+        g = dict(zip(ctx.names, gouts))
+        dev = keep["rays"].device
+        n, S, NI = cfg.n_rays, cfg.n_samples, cfg.n_importance
+        flat_c, packed_c = net_c._sync()
+        flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
+        io = L.RenderIO()
+        for k, v in keep.items():
+            setattr(io, k, ptr(v))
+        io.params_coarse, io.packed_coarse = ptr(flat_c), ptr(packed_c)
+        io.params_fine, io.packed_fine = ptr(flat_f), ptr(packed_f)
+        gc = torch.zeros(L.MLP_NPARAMS, device=dev)
+        gf = torch.zeros(L.MLP_NPARAMS, device=dev) if net_f is not None else None
+        gr = L.RenderGrads()
+        hold = []
+        for cname, k in (("g_rgb", "rgb_map"), ("g_disp", "disp_map"), ("g_acc", "acc_map"), ("g_depth", "depth_map"),
+                         ("g_weights", "weights"), ("g_rgb0", "rgb0"), ("g_disp0", "disp0"), ("g_acc0", "acc0")):
+            t = g.get(k)
+            if t is not None:
+                t = f32(t); hold.append(t)
+                setattr(gr, cname, ptr(t))
+        scratch = torch.empty(n * (S + NI) * 4, device=dev)
+        ws = ops.mlp_bwd_workspace(n * (S + NI), cfg.precision, dev)
+        gr.grads_coarse, gr.grads_fine = ptr(gc), ptr(gf)
+        gr.d_raw_scratch, gr.workspace = ptr(scratch), ptr(ws)
+        check(lib().spn_render_rays_bwd(C.byref(cfg), C.byref(io), C.byref(gr), stream()), "spn_render_rays_bwd")
+        ctx.state = None
+        grads = [gc[o:o + p.numel()].view(p.shape) for o, p in zip(net_c._offsets, net_c._flat_params())]
+        if net_f is not None:
+            grads += [gf[o:o + p.numel()].view(p.shape) for o, p in zip(net_f._offsets, net_f._flat_params())]
+        return (None,) * 8 + tuple(grads)
+
+
+def _np_rand(*shape, device):
+    """The reference's pytest=True stream: re-seeded before every draw (run_nerf.py:662-666)."""
+    np.random.seed(0)
+    return torch.as_tensor(np.random.rand(*shape), dtype=torch.float32, device=device)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., pytest=False, sigma_loss=None,
+                verbose=False, need_alpha=False, detach_weights=False):
+    """Volumetric rendering of one chunk — same arguments and returned dict as run_nerf.py:593-737.
+    `network_query_fn` is not called: encoding + MLP run inside the fused kernels."""
+    if sigma_loss is not None:
+        raise NotImplementedError("sigma_loss (DS_NeRF/loss.py) is outside the B200 hot path")
+    fused = type(network_fn) is NeRF and (network_fine is None or type(network_fine) is NeRF)
+    if not fused:
+        return render_rays_composed(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb,
+                                    N_importance, network_fine, white_bkgd, raw_noise_std, pytest, need_alpha,
+                                    detach_weights)
+    if ray_batch.shape[-1] <= 9:
+        raise NotImplementedError("spinnerf_b200 renders with use_viewdirs=True ray batches (11|12 columns)")
+    n = ray_batch.shape[0]
+    dev = ray_batch.device
+    S2 = N_samples + N_importance
+    t_rand = u = noise0 = noise1 = None
+    if perturb > 0.:
+        t_rand = _np_rand(n, N_samples, device=dev) if pytest else torch.rand(n, N_samples, device=dev)
+        if N_importance > 0:
+            u = _np_rand(n, N_importance, device=dev) if pytest else torch.rand(n, N_importance, device=dev)
+    if raw_noise_std > 0.:
+        noise0 = _np_rand(n, N_samples, device=dev) if pytest else torch.randn(n, N_samples, device=dev)
+        if N_importance > 0:
+            noise1 = _np_rand(n, S2, device=dev) if pytest else torch.randn(n, S2, device=dev)
+    opts = dict(N_samples=int(N_samples), N_importance=int(N_importance), lindisp=bool(lindisp),
+                white_bkgd=bool(white_bkgd), detach_weights=bool(detach_weights), perturb=perturb > 0.,
+                need_alpha=bool(need_alpha), raw_noise_std=float(raw_noise_std))
+    params = network_fn._flat_params() + (network_fine._flat_params() if network_fine is not None else [])
+    outs = RenderChunk.apply(opts, ray_batch, network_fn, network_fine, t_rand, u, noise0, noise1, *params)
+    names = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "raw"]
+    if N_importance > 0:
+        names += ["rgb0", "disp0", "acc0", "z_std"]
+    if need_alpha:
+        names += ["alpha", "alpha0"]
+    ret = dict(zip(names, outs))
+    if not retraw:
+        ret.pop("raw")
+    return ret
+
+
+def render_rays_composed(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb, N_importance,
+                         network_fine, white_bkgd, raw_noise_std, pytest, need_alpha, detach_weights):
+    """Operator-level composition for the variants the fused chunk does not cover (NeRF_RGB /
+    --no_coarse / alpha_model, run_nerf.py:680-692): same CUDA ops, Python control flow."""
+    n = ray_batch.shape[0]
+    dev = ray_batch.device
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 9 else None
+    t_rand = None
+    if perturb > 0.:
+        t_rand = _np_rand(n, N_samples, device=dev) if pytest else torch.rand(n, N_samples, device=dev)
+    z_vals = ops.sample_z(ray_batch, N_samples, lindisp, t_rand)
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+    if network_fn is not None:
+        coarse = network_fn
+    else:
+        coarse = network_fine.alpha_model if getattr(network_fine, "alpha_model", None) is not None else network_fine
+    raw = network_query_fn(pts, viewdirs, coarse)
+    rgb_map, disp_map, acc_map, weights, depth_map, alpha = ops.raw2outputs(
+        raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest, need_alpha=need_alpha, detach_weights=detach_weights)
+    ret = {}
+    if N_importance > 0:
+        rgb0, disp0, acc0, alpha0 = rgb_map, disp_map, acc_map, alpha
+        u = None
+        if perturb > 0.:
+            u = _np_rand(n, N_importance, device=dev) if pytest else torch.rand(n, N_importance, device=dev)
+        z_vals, z_std, _, _ = ops.resample(z_vals, weights, N_importance, u)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = network_query_fn(pts, viewdirs, run_fn)
+        rgb_map, disp_map, acc_map, weights, depth_map, alpha = ops.raw2outputs(
+            raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest, need_alpha=need_alpha,
+            detach_weights=detach_weights)
+        ret.update(rgb0=rgb0, disp0=disp0, acc0=acc0, z_std=z_std)
+        if need_alpha:
+            ret["alpha0"] = alpha0
+    ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map, weights=weights, z_vals=z_vals)
+    if retraw:
+        ret["raw"] = raw
+    if need_alpha:
+        ret["alpha"] = alpha
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, need_alpha=False, detach_weights=False, **kwargs):
+    """run_nerf.py:74-87."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, depths=None, need_alpha=False, detach_weights=False, patch=None, **kwargs):
+    """run_nerf.py:90-165 — same arguments, same [rgb, disp, acc, depth, extras] return."""
+    if not use_viewdirs:
+        raise NotImplementedError("spinnerf_b200 implements the use_viewdirs=True path")
+    if c2w is not None:
+        rays_o, rays_d = ops.get_rays(H, W, focal, c2w, patch)
+    else:
+        rays_o, rays_d = rays
+    view_src = rays_d
+    if c2w_staticcam is not None:
+        rays_o, rays_d = ops.get_rays(H, W, focal, c2w_staticcam)
+    sh = rays_d.shape
+    if c2w_staticcam is None and depths is None and not torch.is_tensor(near) and not torch.is_tensor(far):
+        ray_mat = ops.build_ray_batch(rays_o, rays_d, near, far, ndc, H, W, focal)
+    else:   # general form (run_nerf.py:128-153)
+        viewdirs = f32(view_src).reshape(-1, 3)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        if ndc:
+            rays_o, rays_d = ops.ndc_rays(H, W, focal, 1., rays_o, rays_d)
+        rays_o = f32(rays_o).reshape(-1, 3); rays_d = f32(rays_d).reshape(-1, 3)
+        cols = [rays_o, rays_d, near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])]
+        if depths is not None:
+            cols.append(depths.reshape(-1, 1).float())
+        ray_mat = torch.cat(cols + [viewdirs], -1)
+    all_ret = batchify_rays(ray_mat, chunk, need_alpha=need_alpha, detach_weights=detach_weights, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def to8b(x):
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                disp_require_grad=False, need_alpha=False, rgb_require_grad=False, detach_weights=False,
+                patch_len=None, masks=None):
+    """run_nerf.py:168-307: per-pose render loop (rays generated on the device from c2w), optional
+    LPIPS patch sampling inside the mask bbox (:197-211), optional per-frame dumps (:231-295)."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H = H // render_factor; W = W // render_factor; focal = focal / render_factor
+    H, W = int(H), int(W)
+    if savedir is not None:
+        np.savetxt(os.path.join(savedir, 'intrinsics.txt'), np.array([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1]]))
+    rgbs, disps, Xs, Ys = [], [], [], []
+    for i, c2w in enumerate(render_poses):
+        c2w = torch.as_tensor(c2w)
+        if disp_require_grad or rgb_require_grad:
+            patch = None
+            if patch_len is not None:
+                masked = np.where(masks[i] != 0)
+                masked = (masked[0] // render_factor, masked[1] // render_factor)
+                Xs.append(random.randint(masked[0].min(), max(masked[0].max() - patch_len[0], masked[0].min())))
+                Ys.append(random.randint(masked[1].min(), max(masked[1].max() - patch_len[1], masked[1].min())))
+                patch = (Xs[-1], Ys[-1], patch_len[0], patch_len[1])
+            rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
+                                                   need_alpha=need_alpha, detach_weights=detach_weights, patch=patch,
+                                                   **render_kwargs)
+        else:
+            with torch.no_grad():
+                rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
+                                                       need_alpha=need_alpha, **render_kwargs)
+        disps.append(disp if disp_require_grad else disp.detach().cpu().numpy())
+        rgbs.append(rgb if rgb_require_grad else rgb.detach().cpu().numpy())
+        if savedir is not None:
+            _dump_frame(savedir, i, rgbs[-1], gt_imgs, depth, disp, extras, need_alpha, c2w)
+    disps = torch.stack(disps, 0) if disp_require_grad else np.stack(disps, 0)
+    rgbs = torch.stack(rgbs, 0) if rgb_require_grad else np.stack(rgbs, 0)
+    return rgbs, disps, (Xs, Ys)
+
+
+def _dump_frame(savedir, i, rgb, gt_imgs, depth, disp, extras, need_alpha, c2w):
+    import cv2
+    sub = lambda d: os.path.join(savedir, d)
+    for d in ['rgb', 'depth', 'disp', 'weight', 'images', 'z', 'pose'] + (['alpha'] if need_alpha else []):
+        os.makedirs(sub(d), exist_ok=True)
+    rgb_np = rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb
+    rgb8 = to8b(np.nan_to_num(rgb_np))
+    cv2.imwrite(os.path.join(sub('rgb'), '{:06d}.png'.format(i)), rgb8[..., ::-1])
+    if gt_imgs is not None:
+        gt = gt_imgs[i]
+        gt = gt.detach().cpu().numpy() if torch.is_tensor(gt) else gt
+        cv2.imwrite(os.path.join(sub('images'), '{:06d}.png'.format(i)), to8b(gt)[..., ::-1])
+    np.save(os.path.join(sub('depth'), '{:06d}.npy'.format(i)), depth.detach().cpu().numpy())
+    np.save(os.path.join(sub('disp'), '{:06d}.npy'.format(i)), disp.detach().cpu().numpy())
+    np.save(os.path.join(sub('weight'), '{:06d}.npy'.format(i)), extras['weights'].detach().cpu().numpy())
+    np.save(os.path.join(sub('z'), '{:06d}.npy'.format(i)), extras['z_vals'].detach().cpu().numpy())
+    if need_alpha:
+        np.save(os.path.join(sub('alpha'), '{:06d}.npy'.format(i)), extras['alpha'].detach().cpu().numpy())
+    pose = np.concatenate([c2w[:3, :4].detach().cpu().numpy(), np.array([[0, 0, 0, 1]])], axis=0)
+    np.savetxt(os.path.join(sub('pose'), '{:06d}.txt'.format(i)), pose)

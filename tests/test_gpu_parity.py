@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (called through the C ABI) against the CPU oracle and the golden
+fixtures produced by the unmodified reference.  Needs a B200:  pytest -m gpu
+
+Tolerances (fp32 mode): weights/rgb/acc abs 1e-5..2e-4 through the MLP,
+depth/z rel 1e-5, disp rel 1e-4, sample_pdf indices bit-exact given identical cdf and u.
+bf16 (tcgen05) mode: raw abs 2e-2 * max|raw| (bf16 operands, fp32 accumulation over 9 layers).
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+spn = importlib.import_module("spin-nerf_b200")
+ops = spn.ops
+DEV = "cuda"
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(N(a) if torch.is_tensor(a) else a, b, rtol=rtol, atol=atol)
+
+
+def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
+    a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
+    err = np.abs(a - b); tol = atol + rtol * np.abs(b)
+    assert np.mean(err > tol) <= max_frac, (np.mean(err > tol), err.max())
+    assert err.max() <= hard * max(1.0, np.abs(b).max()), err.max()
+
+
+def make_net(seed, precision, bias_sigma=0.0):
+    p = O.init_params(seed)
+    p["alpha_linear.bias"] = p["alpha_linear.bias"] + np.float32(bias_sigma)
+    net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+    net = net.to(DEV)
+    net.precision = precision
+    return net, p
+
+
+def test_library_is_the_native_one():
+    assert spn._lib.lib().spn_version() == 100
+    sms = __import__("ctypes").c_int()
+    spn._lib.check(spn._lib.lib().spn_device_info(sms, None, None))
+    assert sms.value >= 100
+
+
+# ---- small ops --------------------------------------------------------------------------------
+def test_embed():
+    g = load_golden("embed")
+    close(ops.embed(T(g["x"]), 10), g["e10"], rtol=0, atol=2e-6)
+    close(ops.embed(T(g["x"]), 4), g["e4"], rtol=0, atol=2e-6)
+
+
+def test_rays_and_ndc():
+    g = load_golden("rays")
+    ro, rd = ops.get_rays(12, 16, 14.4, T(g["c2w"]))
+    close(ro, g["ro"]); close(rd, g["rd"])
+    no, nd = ops.ndc_rays(12, 16, 14.4, 1.0, ro, rd)
+    close(no, g["ndc_o"], rtol=1e-5, atol=1e-6); close(nd, g["ndc_d"], rtol=1e-5, atol=1e-6)
+    # patch window == python slicing of the full grid (run_nerf.py:120-123)
+    po, pd = ops.get_rays(12, 16, 14.4, T(g["c2w"]), patch=(3, 5, 4, 7))
+    close(pd, g["rd"][3:7, 5:12])
+    rb = ops.build_ray_batch(ro, rd, 0.0, 1.0, ndc=True, H=12, W=16, focal=14.4)
+    close(rb, O.make_ray_batch(g["ro"], g["rd"], 0.0, 1.0, ndc=True, H=12, W=16, focal=14.4), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("lindisp", [False, True])
+@pytest.mark.parametrize("perturb", [False, True])
+def test_sample_z(lindisp, perturb):
+    rng = np.random.default_rng(3)
+    n, S = 77, 64
+    rays = np.zeros((n, 11), np.float32)
+    rays[:, 6] = rng.uniform(0.5, 2.0, n); rays[:, 7] = rays[:, 6] + rng.uniform(1, 8, n)
+    t_rand = rng.uniform(0, 1, (n, S)).astype(np.float32) if perturb else None
+    z = ops.sample_z(T(rays), S, lindisp, None if t_rand is None else T(t_rand))
+    ref = O.sample_z(rays[:, 6], rays[:, 7], S, lindisp, t_rand)
+    assert np.array_equal(N(z), ref) or np.abs(N(z) - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert (np.diff(N(z), axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("tag,white,detach", [("plain", False, False), ("white", True, False),
+                                              ("noise_detach", True, True)])
+def test_raw2outputs_forward_backward(tag, white, detach):
+    g = {k.split("__", 1)[1]: v for k, v in load_golden("raw2outputs").items() if k.startswith(tag + "__")}
+    raw = T(g["raw"]).requires_grad_(True)
+    noise = T(g["noise"]) if g["noise"].any() else None
+    outs = spn.ops._Raw2Outputs.apply(raw, T(g["z"]), T(g["rd"]), noise, white, True, detach)
+    rgb, disp, acc, w, depth, alpha = outs
+    close(w, g["w"], atol=2e-6); close(alpha, g["alpha"], atol=2e-6)
+    close(rgb, g["rgb"], atol=3e-6); close(acc, g["acc"], atol=3e-6)
+    close(depth, g["depth"], rtol=1e-5); close(disp, g["disp"], rtol=1e-4)
+    loss = sum((o * T(g[k])).sum() for o, k in zip((rgb, disp, acc, w, depth), ("g_rgb", "g_disp", "g_acc", "g_w", "g_depth")))
+    loss.backward()
+    close(raw.grad, g["d_raw"], rtol=2e-3, atol=2e-4 * np.abs(g["d_raw"]).max())
+
+
+def test_raw2outputs_edge_cases():
+    # ragged sample counts (not a multiple of 32), single sample, empty batch, zero density
+    rng = np.random.default_rng(5)
+    for S in (1, 7, 33, 100, 200):
+        raw = (rng.standard_normal((9, S, 4))).astype(np.float32)
+        z = np.sort(rng.uniform(1, 5, (9, S)).astype(np.float32), -1)
+        rd = rng.standard_normal((9, 3)).astype(np.float32)
+        got = ops.raw2outputs(T(raw), T(z), T(rd), need_alpha=True)
+        ref = O.raw2outputs(raw, z, rd, need_alpha=True)
+        for a, b in zip(got, ref):
+            close(a, b, rtol=2e-5, atol=3e-6)
+    e = ops.raw2outputs(torch.empty(0, 64, 4, device=DEV), torch.empty(0, 64, device=DEV), torch.empty(0, 3, device=DEV))
+    assert e[0].shape == (0, 3) and e[3].shape == (0, 64)
+    raw = np.zeros((2, 8, 4), np.float32); raw[..., 3] = -1.0       # sigma<=0 everywhere -> acc=0, disp NaN like torch
+    out = ops.raw2outputs(T(raw), T(np.tile(np.arange(1, 9, dtype=np.float32), (2, 1))), T(np.ones((2, 3), np.float32)))
+    assert float(out[2].abs().max()) == 0.0 and torch.isnan(out[1]).all()
+    with pytest.raises(RuntimeError):
+        ops.raw2outputs(torch.zeros(2, 300, 4, device=DEV, requires_grad=True), torch.zeros(2, 300, device=DEV),
+                        torch.ones(2, 3, device=DEV))[0].sum().backward()       # S > 256 unsupported in bwd
+
+
+def test_sample_pdf_indices_bit_exact():
+    g = load_golden("sample_pdf")
+    for u, ref_s in ((g["u_det"], g["det"]), (g["u_sto"], g["sto"])):
+        s, inds, cdf = ops.sample_pdf(T(g["bins"]), T(g["weights"]), 64, u=T(u), return_inds=True, return_cdf=True)
+        assert np.abs(N(cdf) - g["cdf"]).max() <= 4e-7          # fp32 row total may round 1 ulp differently
+        # bit-exact GIVEN identical cdf and u: the oracle search/lerp on the GPU's own cdf
+        s_o, i_o = O.sample_pdf_from_cdf(g["bins"], N(cdf), u)
+        assert np.array_equal(N(inds), i_o)
+        assert np.array_equal(N(s), s_o)
+        # and against the reference's samples: equal except where a ~1e-5 cdf step amplifies 1 ulp
+        err = np.abs(N(s) - ref_s)
+        assert np.mean(err > 1e-5) < 0.01 and err.max() < 2e-2
+    # weights whose fp32 sums are exact in any order -> cdf identical to the reference -> indices identical
+    rng = np.random.default_rng(9)
+    w = (rng.integers(0, 64, (50, 62)) / 64.0).astype(np.float32) - np.float32(1e-5)
+    bins = np.sort(rng.uniform(1, 8, (50, 63)).astype(np.float32), -1)
+    uu = rng.uniform(0, 1, (50, 64)).astype(np.float32)
+    s, inds, cdf = ops.sample_pdf(T(bins), T(w), 64, u=T(uu), return_inds=True, return_cdf=True)
+    ref_cdf = O.pdf_to_cdf(w)
+    s_o, i_o = O.sample_pdf_from_cdf(bins, ref_cdf, uu)
+    same = np.all(N(cdf) == ref_cdf, axis=1)
+    assert same.mean() > 0.5 and np.array_equal(N(inds)[same], i_o[same])
+    g2 = load_golden("searchsorted_kat")          # torch.searchsorted(right=True) KAT
+    cdf_k = g2["cdf"][0]
+    wk = np.diff(cdf_k).astype(np.float32)        # build weights that reproduce the KAT cdf
+    _, inds_k, cdf_g = ops.sample_pdf(T(np.zeros((1, 5), np.float32)), T(wk[None] - np.float32(1e-5)), 6, u=T(g2["u"]),
+                                      return_inds=True, return_cdf=True)
+    if np.array_equal(N(cdf_g)[0], cdf_k):
+        assert N(inds_k).tolist() == g2["inds"].tolist()
+
+
+def test_merge_and_resample():
+    rng = np.random.default_rng(11)
+    a = np.sort(rng.uniform(1, 8, (33, 64)).astype(np.float32), -1)
+    b = rng.uniform(1, 8, (33, 64)).astype(np.float32)                 # unsorted, like stochastic z_samples
+    close(ops.merge_sorted(T(a), T(b)), O.merge_sorted(a, b), rtol=0, atol=0)
+    close(ops.merge_sorted(T(a[:, :5]), T(b[:, :3])), O.merge_sorted(a[:, :5], b[:, :3]), rtol=0, atol=0)
+    w = (rng.uniform(0, 1, (33, 64)) ** 3).astype(np.float32)
+    u = rng.uniform(0, 1, (33, 64)).astype(np.float32)
+    zm, zstd, zs, inds = ops.resample(T(a), T(w), 64, T(u), want_samples=True, want_inds=True)
+    mid = np.float32(0.5) * (a[:, 1:] + a[:, :-1])
+    s_o, i_o = O.sample_pdf(mid, w[:, 1:-1], 64, det=False, u=u)
+    assert (N(inds) == i_o).mean() > 0.999
+    close_mostly(zs, s_o, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(N(zm), np.sort(np.concatenate([a, N(zs)], -1), -1))       # sortedness + multiset
+    close(zstd, N(zs).std(-1), rtol=1e-4, atol=1e-5)
+
+
+# ---- MLP ----------------------------------------------------------------------------------------
+def _mlp_case():
+    g = load_golden("mlp")
+    x90 = g["x90"]
+    x6 = np.concatenate([x90[:, 0:3], x90[:, 63:66]], -1)
+    return g, x90, x6
+
+
+def test_mlp_fp32_forward_backward():
+    g, x90, x6 = _mlp_case()
+    net, p = make_net(11, spn.PREC_FP32)
+    raw = net(T(x6))
+    close(raw, g["raw"], rtol=1e-4, atol=3e-5)
+    close(net(T(x90)), g["raw"], rtol=1e-4, atol=3e-5)        # pre-embedded input (non-lazy embedder) path
+    raw.backward(T(g["draw"]))
+    for k, v in net.named_parameters():
+        gv = N(v.grad)
+        close(gv.reshape(-1)[::97], g["g_sub__" + k], rtol=2e-3, atol=2e-4)
+        assert abs(np.abs(gv).sum(dtype=np.float64) - g["g_abs__" + k]) <= 1e-3 * g["g_abs__" + k] + 1e-4
+
+
+def test_mlp_ragged_sizes_fp32():
+    net, p = make_net(11, spn.PREC_FP32)
+    rng = np.random.default_rng(2)
+    for m in (1, 127, 129, 1000):
+        x6 = np.concatenate([rng.standard_normal((m, 3)) * 2, O.embed(rng.standard_normal((m, 3)), 0)], -1).astype(np.float32)
+        x6[:, 3:] /= np.linalg.norm(x6[:, 3:], axis=1, keepdims=True)
+        ref = O.mlp_forward(p, np.concatenate([O.embed(x6[:, :3], 10), O.embed(x6[:, 3:], 4)], -1))
+        with torch.no_grad():
+            close(net(T(x6)), ref, rtol=1e-4, atol=3e-5)
+    with torch.no_grad():
+        assert net(torch.empty(0, 6, device=DEV)).shape == (0, 4)
+
+
+# ---- render end to end ----------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["det_lindisp_white", "det_ndc", "sto_lindisp_white", "coarse_only"])
+def test_render_matches_reference_fp32(tag):
+    g = load_golden("render")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    netc, _ = make_net(11, spn.PREC_FP32, 1.0)
+    netf, _ = make_net(12, spn.PREC_FP32, 1.0)
+    ndc = tag == "det_ndc"
+    near, far = (0.0, 1.0) if ndc else (1.2, 8.0)
+    n_imp = 0 if tag == "coarse_only" else 64
+    sto = tag.startswith("sto")
+    kw = dict(network_query_fn=None, network_fn=netc, network_fine=netf if n_imp else None, N_samples=64,
+              N_importance=n_imp, lindisp="lindisp" in tag, white_bkgd="white" in tag, perturb=1. if sto else 0.,
+              raw_noise_std=1. if sto else 0., pytest=sto)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=32768, rays=T(g["rays"]), retraw=True, use_viewdirs=True,
+                                               ndc=ndc, near=near, far=far, need_alpha=bool(n_imp), **kw)
+    G = lambda k: g[f"{tag}__{k}"]
+    cm = (lambda a, b, rtol=1e-5, atol=1e-6: close(a, b, rtol, atol)) if n_imp == 0 else close_mostly
+    cm(ex["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
+    cm(ex["raw"], G("raw"), rtol=1e-3, atol=1e-3)
+    cm(ex["weights"], G("weights"), rtol=0, atol=2e-4)
+    cm(rgb, G("rgb"), rtol=0, atol=2e-4); cm(acc, G("acc"), rtol=0, atol=2e-4)
+    cm(depth, G("depth"), rtol=2e-4, atol=2e-4); cm(disp, G("disp"), rtol=5e-4, atol=0)
+    if n_imp:
+        close(ex["rgb0"], G("rgb0"), atol=2e-4); close(ex["disp0"], G("disp0"), rtol=5e-4)
+        cm(ex["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
+        cm(ex["alpha"], G("alpha"), rtol=0, atol=2e-4); close(ex["alpha0"], G("alpha0"), atol=2e-4)
+        mse = float(((rgb - T(G("rgb"))) ** 2).mean())
+        assert -10 * np.log10(max(mse, 1e-20)) > 60.0          # PSNR of our render vs the reference's render
+
+
+def test_train_step_matches_reference_fp32():
+    """loss, gradients and two Adam steps through render() (golden: tests/golden/make_golden.py train_step)."""
+    g = load_golden("render"); tr = load_golden("train_step")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    netc, _ = make_net(11, spn.PREC_FP32, 1.0)
+    netf, _ = make_net(12, spn.PREC_FP32, 1.0)
+    opt = torch.optim.Adam(list(netc.parameters()) + list(netf.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    target, tdisp = T(tr["target"]), T(tr["tdisp"])
+    mse = lambda a, b: torch.mean((a - b) ** 2)
+    for it in range(2):
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=32768, rays=T(g["rays"]), retraw=True, use_viewdirs=True,
+                                               network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64,
+                                               N_importance=64, ndc=False, lindisp=True, white_bkgd=True, perturb=0.,
+                                               raw_noise_std=0., near=1.2, far=8.0)
+        opt.zero_grad()
+        loss = mse(rgb, target) + mse(ex["rgb0"], target) + mse(disp, tdisp) + mse(ex["disp0"], tdisp)
+        loss.backward()
+        assert abs(loss.item() - float(tr[f"loss{it}"])) <= 2e-4 * abs(float(tr[f"loss{it}"])), (it, loss.item())
+        if it == 0:
+            for nm, net in (("c", netc), ("f", netf)):
+                for k, v in net.named_parameters():
+                    gv = N(v.grad)
+                    ref_abs = float(tr[f"g_abs__{nm}__{k}"])
+                    assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-6, (nm, k)
+                    close_mostly(gv.reshape(-1)[::997], tr[f"g_sub__{nm}__{k}"], rtol=1e-2, atol=1e-3 * np.abs(gv).max() + 1e-9,
+                                 max_frac=0.03, hard=1.0)
+        opt.step()
+    for nm, net in (("c", netc), ("f", netf)):
+        for k, v in net.named_parameters():
+            close_mostly(N(v).reshape(-1)[::997], tr[f"p_sub__{nm}__{k}"], rtol=0, atol=2e-4, max_frac=0.03, hard=1.0)
+
+
+def test_adam_flat_matches_torch():
+    rng = np.random.default_rng(4)
+    p = rng.standard_normal(10007).astype(np.float32); gr = rng.standard_normal(10007).astype(np.float32)
+    tp = torch.nn.Parameter(T(p.copy())); opt = torch.optim.Adam([tp], lr=3e-3)
+    mp, m, v = T(p.copy()), torch.zeros(10007, device=DEV), torch.zeros(10007, device=DEV)
+    for step in range(1, 4):
+        tp.grad = T(gr * step); opt.step()
+        ops.adam_step(mp, T(gr * step), m, v, step, 3e-3)
+    close(mp, N(tp), rtol=1e-5, atol=1e-6)
+    po, m0, v0 = O.adam_step(p, gr, np.zeros_like(p), np.zeros_like(p), 1, 3e-3)
+    mp2, m2, v2 = T(p.copy()), torch.zeros(10007, device=DEV), torch.zeros(10007, device=DEV)
+    ops.adam_step(mp2, T(gr), m2, v2, 1, 3e-3)
+    close(mp2, po, rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        ops.embed(torch.zeros(4, 3), 10)                      # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ops.sample_pdf(torch.zeros(2, 300, device=DEV), torch.zeros(2, 299, device=DEV), 8, det=True)   # nb > 256
+    with pytest.raises(NotImplementedError):
+        spn.NeRF(D=4, W=128, input_ch=63, input_ch_views=27, use_viewdirs=True)
