@@ -53,6 +53,14 @@ const char* spn_last_error(void);
 /* SM count / arch of the current device (0 on failure). */
 int spn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Measurement hooks (bench.py).  spn_profile_enable(1) brackets every MLP kernel launch with a cudaEvent pair
+ * on the launching stream; spn_profile_read(kind, ...) synchronises them and returns the launch count and the
+ * summed device time in ms (kind 0 = fused MLP forward, 1 = MLP dgrad, 2 = MLP wgrad).
+ * spn_launch_count returns the number of kernels this library has launched (reset != 0 zeroes it). */
+int spn_profile_enable(int on);
+int spn_profile_read(int kind, int* launches, float* total_ms);
+long long spn_launch_count(int reset);
+
 /* ---- a9  rays ------------------------------------------------------------------------- */
 /* get_rays (helpers:249-260) for the pixel window [i0,i0+h) x [j0,j0+w) of an H x W image
  * (render()'s `patch`, run_nerf.py:120-123).  c2w: [3,4] row-major. rays_o/rays_d: [h,w,3]. */
@@ -130,6 +138,10 @@ int spn_mlp_fwd_rays(const float* params_flat, const void* packed, const float* 
 /* grads_flat [SPN_MLP_NPARAMS] += dL/dparams (accumulates: zero it first if needed). */
 int spn_mlp_bwd(const float* params_flat, const void* packed, const void* stash, const float* d_raw,
                 int64_t m, float* grads_flat, void* workspace, int precision, void* stream);
+
+/* Diagnostic: a single tcgen05 GEMM D[128,N] = A[128,K] B[N,K]^T (fp32 in/out, bf16 operands on the tensor
+ * cores) with exactly the shared-memory/TMEM conventions of the MLP kernels. N in {128,256}, K in {64,128,192,256}. */
+int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
 
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */
 int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

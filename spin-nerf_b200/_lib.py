@@ -45,6 +45,9 @@ _SIGS = {
     "spn_version": (C.c_int, []),
     "spn_last_error": (C.c_char_p, []),
     "spn_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "spn_profile_enable": (C.c_int, [C.c_int]),
+    "spn_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "spn_launch_count": (C.c_longlong, [C.c_int]),
     "spn_get_rays": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
     "spn_ndc_rays": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "spn_build_ray_batch": (C.c_int, [C.c_int, c_fp, c_fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp]),
@@ -64,6 +67,7 @@ _SIGS = {
     "spn_mlp_fwd_points": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, c_fp, c_fp, C.c_int, c_fp]),
     "spn_mlp_fwd_rays": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int, C.c_int, c_fp, c_fp, C.c_int, c_fp]),
     "spn_mlp_bwd": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, c_fp, C.c_int, c_fp]),
+    "spn_tc_selftest_gemm": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp]),
     "spn_adam_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, c_fp]),
     "spn_render_rays_fwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), c_fp]),
     "spn_render_rays_bwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), C.POINTER(RenderGrads), c_fp]),
@@ -108,7 +112,9 @@ def ptr(t):
         raise RuntimeError("spinnerf_b200: expected a CUDA tensor (this path has no CPU implementation)")
     if not t.is_contiguous():
         raise RuntimeError("spinnerf_b200: expected a contiguous tensor")
-    return t.data_ptr()
+    # empty tensors have data_ptr() == 0; the C side rejects NULL for required buffers but never
+    # dereferences anything when the element count is 0, so hand it an aligned non-null token
+    return t.data_ptr() if t.numel() else 256
 
 
 def f32(t):

@@ -33,9 +33,64 @@ int sm_count() {
   return n;
 }
 
+long long g_launches = 0;
+
+// ---- in-library kernel timing (bench.py's roofline leg): cudaEvent pairs on the launching stream ----
+namespace {
+constexpr int kProfMax = 4096;
+struct ProfState {
+  bool on = false;
+  int n[PROF_KINDS] = {0, 0, 0};
+  cudaEvent_t ev[PROF_KINDS][kProfMax][2];
+  int created[PROF_KINDS] = {0, 0, 0};
+} g_prof;
+}  // namespace
+
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n[kind] >= kProfMax) return;
+  int i = g_prof.n[kind];
+  if (i >= g_prof.created[kind]) {
+    cudaEventCreate(&g_prof.ev[kind][i][0]);
+    cudaEventCreate(&g_prof.ev[kind][i][1]);
+    g_prof.created[kind] = i + 1;
+  }
+  cudaEventRecord(g_prof.ev[kind][i][0], st);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n[kind] >= kProfMax) return;
+  cudaEventRecord(g_prof.ev[kind][g_prof.n[kind]][1], st);
+  ++g_prof.n[kind];
+}
+
 }  // namespace spn
 
 using namespace spn;
+
+extern "C" int spn_profile_enable(int on) {
+  g_prof.on = on != 0;
+  for (int k = 0; k < PROF_KINDS; ++k) g_prof.n[k] = 0;
+  return SPN_OK;
+}
+
+extern "C" int spn_profile_read(int kind, int* launches, float* total_ms) {
+  SPN_CHECK_ARG(kind >= 0 && kind < PROF_KINDS && launches && total_ms, "spn_profile_read: bad arguments");
+  float tot = 0.f;
+  for (int i = 0; i < g_prof.n[kind]; ++i) {
+    float ms = 0.f;
+    SPN_CUDA(cudaEventSynchronize(g_prof.ev[kind][i][1]));
+    SPN_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[kind][i][0], g_prof.ev[kind][i][1]));
+    tot += ms;
+  }
+  *launches = g_prof.n[kind];
+  *total_ms = tot;
+  return SPN_OK;
+}
+
+extern "C" long long spn_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
 
 extern "C" int spn_version(void) { return SPN_VERSION; }
 extern "C" const char* spn_last_error(void) { return g_err; }
@@ -67,6 +122,10 @@ extern "C" int spn_mlp_pack_weights(const float* params_flat, void* packed, void
   return mlp_tc_pack(params_flat, packed, as_stream(stream));
 }
 
+extern "C" int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, void* stream) {
+  return tc_selftest_gemm(A, B, D, N, K, as_stream(stream));
+}
+
 extern "C" size_t spn_mlp_stash_bytes(int64_t m, int precision) {
   return precision == SPN_PREC_FP32 ? mlp_fp32_stash_bytes(m) : mlp_tc_stash_bytes(m);
 }
@@ -87,6 +146,7 @@ static int mlp_fwd(const float* params, const void* packed, const SampleSource& 
 
 extern "C" int spn_mlp_fwd_points(const float* params_flat, const void* packed, const float* x6, int64_t m,
                                   float* raw, void* stash, int precision, void* stream) {
+  if (m == 0) return SPN_OK;
   SPN_CHECK_ARG(x6, "spn_mlp_fwd_points: null x6");
   SampleSource src{x6, nullptr, nullptr, 0, 1};
   return mlp_fwd(params_flat, packed, src, m, raw, stash, precision, as_stream(stream));

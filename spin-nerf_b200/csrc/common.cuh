@@ -29,9 +29,17 @@ int cuda_fail(cudaError_t e, const char* what);
 
 #define SPN_LAUNCH_CHECK(name)                                       \
   do {                                                               \
+    ++spn::g_launches;                                               \
     cudaError_t e__ = cudaGetLastError();                            \
     if (e__ != cudaSuccess) return spn::cuda_fail(e__, name);        \
   } while (0)
+
+extern long long g_launches;   // kernels launched by this library (spn_launch_count)
+
+// optional in-library CUDA-event timing of the dominant kernels, on the launching stream
+enum ProfKind : int { PROF_MLP_FWD = 0, PROF_MLP_DGRAD = 1, PROF_MLP_WGRAD = 2, PROF_KINDS = 3 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
@@ -122,6 +130,7 @@ size_t mlp_tc_bwd_ws_bytes(int64_t m);
 int mlp_tc_pack(const float* params, void* packed, cudaStream_t st);
 int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* raw, void* stash,
                cudaStream_t st);
+int tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_t m, float* grads,
                void* ws, cudaStream_t st);
 

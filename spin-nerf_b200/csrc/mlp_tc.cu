@@ -1,10 +1,556 @@
-// placeholder — replaced by the tcgen05 implementation
+// NeRF MLP (DS_NeRF/run_nerf_helpers.py:74-127) fused with sampling-point generation and positional
+// encoding (run_nerf.py:56-71, 670; helpers:22-70) on the 5th-generation tensor cores (tcgen05).
+//
+// One persistent CTA per SM, 320 threads:
+//   warp 0      weight producer: streams pre-swizzled bf16 weight chunks (32 KB = [256 out x 64 in]) from
+//               L2/HBM into a 3-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarrier tx counts
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256|128, K=16), accumulators in TMEM
+//   warps 2-5   epilogue / prologue of tile A (rows 0..127 -> TMEM lanes 0..127)
+//   warps 6-9   epilogue / prologue of tile B
+// Two 128-sample tiles are in flight per CTA and ping-pong on the tensor pipe: while tile A's epilogue turns
+// its fp32 accumulator (TMEM, 256 columns) into the next layer's bf16 A-operand (bias, ReLU, cast, 128B-swizzled
+// store to shared memory, in place), tile B's layer runs on the tensor cores, and vice versa.  Activations
+// never leave the SM; HBM sees 24 B in + 16 B out per sample (plus the bf16 stash in training).
+//
+// The 63-wide skip input of layer 5 and the 27-wide view encoding of the views layer are applied as a
+// second accumulating pass (K=64 / K=32) after the 256-wide pass, so the 128x256 activation tile can be
+// updated in place; the encodings stay packed in registers in between.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace spn {
-size_t mlp_tc_packed_bytes() { return 16; }
-size_t mlp_tc_stash_bytes(int64_t) { return 16; }
-size_t mlp_tc_bwd_ws_bytes(int64_t) { return 16; }
-int mlp_tc_pack(const float*, void*, cudaStream_t) { set_error("tcgen05 path not built"); return SPN_E_ARG; }
-int mlp_tc_fwd(const void*, const SampleSource&, int64_t, float*, void*, cudaStream_t) { set_error("tcgen05 path not built"); return SPN_E_ARG; }
-int mlp_tc_bwd(const void*, const void*, const float*, int64_t, float*, void*, cudaStream_t) { set_error("tcgen05 path not built"); return SPN_E_ARG; }
+using namespace tc;
+
+// ---- packed weight image -----------------------------------------------------------------------
+constexpr int kChunkBig = 256 * 128;   // [256 rows x 64 bf16] = 32 KB
+constexpr int kChunkV = 128 * 128;     // [128 rows x 64 bf16] = 16 KB
+constexpr int kFwdChunks = 39;
+constexpr int kBwdChunks = 34;
+constexpr size_t kFwdBytes = 34 * (size_t)kChunkBig + 5 * (size_t)kChunkV;
+constexpr size_t kBwdBytes = (size_t)kBwdChunks * kChunkBig;
+// fp32 constants that the epilogues read (floats)
+constexpr int C_B = 0;          // b0..b7 [8][256]
+constexpr int C_BF = 2048;      // feature bias [256]
+constexpr int C_BV = 2304;      // views bias [128]
+constexpr int C_WA = 2432;      // alpha weight [256]
+constexpr int C_BA = 2688;      // alpha bias (padded to 4)
+constexpr int C_WR = 2692;      // rgb weight [3][128]
+constexpr int C_BR = 3076;      // rgb bias (padded to 4)
+constexpr int kConstFloats = 3080;
+constexpr size_t kPackedBytes = kFwdBytes + kBwdBytes + kConstFloats * sizeof(float);
+
+size_t mlp_tc_packed_bytes() { return kPackedBytes; }
+
+struct ChunkDesc {
+  int src_off;   // float offset of the tensor inside the flat parameter vector (+ n0 for transposed chunks)
+  int ld;        // row stride of the source matrix
+  int trans;     // 0: val(n,k) = W[n*ld + k0+k]   1: val(n,k) = W[(k0+k)*ld + n]
+  int nrows;     // N rows of the chunk (256 | 128)
+  int k0;
+  int kvalid;    // columns >= kvalid are zero padding
+  int dst_off;   // byte offset inside the packed image
+};
+struct PackTable {
+  ChunkDesc c[kFwdChunks + kBwdChunks];
+};
+
+static PackTable build_pack_table() {
+  PackTable t;
+  ParamOffsets po = param_offsets();
+  int n = 0, dst = 0;
+  auto add = [&](int src, int ld, int trans, int nrows, int k0, int kvalid) {
+    t.c[n++] = ChunkDesc{src, ld, trans, nrows, k0, kvalid, dst};
+    dst += nrows * 128;
+  };
+  auto W = [&](int i) { return (int)po.off[2 * i]; };
+  // ---- forward, in consumption order
+  add(W(0), kEncP, 0, 256, 0, kEncP);
+  for (int i = 1; i <= 4; ++i) for (int k = 0; k < 4; ++k) add(W(i), kW, 0, 256, 64 * k, 64);
+  for (int k = 0; k < 4; ++k) add(W(5), kW + kEncP, 0, 256, kEncP + 64 * k, 64);
+  add(W(5), kW + kEncP, 0, 256, 0, kEncP);
+  for (int i = 6; i <= 7; ++i) for (int k = 0; k < 4; ++k) add(W(i), kW, 0, 256, 64 * k, 64);
+  for (int k = 0; k < 4; ++k) add((int)po.off[T_WF], kW, 0, 256, 64 * k, 64);
+  for (int k = 0; k < 4; ++k) add((int)po.off[T_WV], kW + kEncD, 0, 128, 64 * k, 64);
+  add((int)po.off[T_WV], kW + kEncD, 0, 128, kW, kEncD);
+  // ---- backward (dgrad): B[n = input feature][k = output feature] = W[k][n]
+  for (int k = 0; k < 2; ++k) add((int)po.off[T_WV], kW + kEncD, 1, 256, 64 * k, 64);
+  for (int k = 0; k < 4; ++k) add((int)po.off[T_WF], kW, 1, 256, 64 * k, 64);
+  for (int i = 7; i >= 1; --i)
+    for (int k = 0; k < 4; ++k) add(W(i) + (i == 5 ? kEncP : 0), i == 5 ? kW + kEncP : kW, 1, 256, 64 * k, 64);
+  return t;
 }
+
+__global__ void pack_kernel(const float* __restrict__ P, uint8_t* __restrict__ out, PackTable tab, int total16) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte (8 x bf16) piece per thread
+  if (idx >= total16) return;
+  // locate the chunk: pieces per chunk = nrows*8
+  int c = 0, base = 0;
+  while (true) {
+    int pieces = tab.c[c].nrows * 8;
+    if (idx < base + pieces) break;
+    base += pieces; ++c;
+  }
+  const ChunkDesc d = tab.c[c];
+  int local = idx - base;
+  int n = local >> 3, j = local & 7;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int k = j * 8 + e;
+    float x = 0.0f;
+    if (k < d.kvalid) x = d.trans ? P[d.src_off + (int64_t)(d.k0 + k) * d.ld + n] : P[d.src_off + (int64_t)n * d.ld + d.k0 + k];
+    v[e] = x;
+  }
+  uint4 q;
+  q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + d.dst_off + sw128_off(n, j)) = q;
+}
+
+__global__ void pack_consts_kernel(const float* __restrict__ P, float* __restrict__ cst, ParamOffsets po) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kConstFloats) return;
+  float v = 0.0f;
+  if (i < C_BF) v = P[po.off[2 * (i / 256) + 1] + (i % 256)];
+  else if (i < C_BV) v = P[po.off[T_BF] + (i - C_BF)];
+  else if (i < C_WA) v = P[po.off[T_BV] + (i - C_BV)];
+  else if (i < C_BA) v = P[po.off[T_WA] + (i - C_WA)];
+  else if (i == C_BA) v = P[po.off[T_BA]];
+  else if (i >= C_WR && i < C_BR) v = P[po.off[T_WR] + (i - C_WR)];
+  else if (i >= C_BR && i < C_BR + 3) v = P[po.off[T_BR] + (i - C_BR)];
+  cst[i] = v;
+}
+
+int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
+  static const PackTable tab = build_pack_table();
+  SPN_CHECK_ARG(((uintptr_t)packed & 15) == 0, "spn_mlp_pack_weights: packed image must be 16-byte aligned");
+  int total16 = (int)((kFwdBytes + kBwdBytes) / 16);
+  pack_kernel<<<(total16 + 255) / 256, 256, 0, st>>>(params, (uint8_t*)packed, tab, total16);
+  SPN_LAUNCH_CHECK("pack_kernel");
+  pack_consts_kernel<<<(kConstFloats + 255) / 256, 256, 0, st>>>(
+      params, (float*)((uint8_t*)packed + kFwdBytes + kBwdBytes), param_offsets());
+  SPN_LAUNCH_CHECK("pack_consts_kernel");
+  return SPN_OK;
+}
+
+// ---- kernel geometry ------------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kAtomBytes = kTileM * 128;        // [128 rows x 64 bf16] swizzle atom = 16 KB
+constexpr int kActBytes = 4 * kAtomBytes;       // 256-wide activation tile = 64 KB
+constexpr int kStages = 3;
+constexpr int kThreads = 320;
+constexpr int kNumSteps = 12;
+constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
+constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
+constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers + tmem pointer
+constexpr int kSmemBytes = SM_BAR + 256 + 1024;            // + slack for 1024-byte alignment
+
+// step tables (forward).  A step = one accumulation pass on the tensor cores followed by an epilogue action.
+enum EpiAction : int { EPI_RELU = 0, EPI_WRITE_ENC = 1, EPI_LINEAR = 2, EPI_WRITE_DENC = 3, EPI_FINAL = 4, EPI_RELU_ALPHA = 5 };
+__constant__ int c_step_chunks[kNumSteps] = {1, 4, 4, 4, 4, 4, 1, 4, 4, 4, 4, 1};
+__constant__ int c_step_n[kNumSteps] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 128, 128};
+__constant__ int c_step_acc[kNumSteps] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+__constant__ int c_step_ksteps[kNumSteps] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2};
+__constant__ int c_step_epi[kNumSteps] = {EPI_RELU, EPI_RELU, EPI_RELU, EPI_RELU, EPI_RELU, EPI_WRITE_ENC, EPI_RELU,
+                                          EPI_RELU, EPI_RELU_ALPHA, EPI_LINEAR, EPI_WRITE_DENC, EPI_FINAL};
+__constant__ int c_step_bias[kNumSteps] = {C_B + 0, C_B + 256, C_B + 512, C_B + 768, C_B + 1024, 0, C_B + 1280,
+                                           C_B + 1536, C_B + 1792, C_BF, 0, C_BV};
+// stash slot written after the step's epilogue (-1: none).  Slots are 16 KB atoms inside the per-tile stash.
+__constant__ int c_step_stash_atom[kNumSteps] = {1, 5, 9, 13, 17, -1, 21, 25, 29, 33, -1, 37};
+__constant__ int c_step_mask_slot[kNumSteps] = {0, 1, 2, 3, 4, -1, 5, 6, 7, -1, -1, 8};
+
+// per-tile stash (training): bf16 SWIZZLE_128B images, 16 KB atoms:
+//   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)
+//   atoms 33-36 feature                          atoms 37-38   hv (128 wide)
+//   atom 39     gamma(viewdir) (27 + pad)
+// followed by ReLU masks: 9 slots x 128 rows x 8 words (h0..h7, hv)
+constexpr int kStashAtoms = 40;
+constexpr size_t kStashTileBytes = (size_t)kStashAtoms * kAtomBytes + 9 * 128 * 32;   // 692224 B per 128 samples
+
+size_t mlp_tc_stash_bytes(int64_t m) {
+  int64_t tiles = (m + 2 * kTileM - 1) / (2 * kTileM) * 2;   // tiles are processed in pairs
+  return (size_t)tiles * kStashTileBytes + 256;
+}
+
+struct FwdParams {
+  const uint8_t* packed;
+  SampleSource src;
+  int64_t m;
+  float* raw;
+  uint8_t* stash;   // nullable
+  int num_pairs;
+};
+
+// packs [v, sin(2^k v), cos(2^k v)]_k (helpers:28-52 order) as bf16 pairs; unused tail = 0
+template <int NFREQ, int NWORDS>
+__device__ __forceinline__ void encode_point(const float v[3], uint32_t (&out)[NWORDS]) {
+  float vals[2 * NWORDS];
+#pragma unroll
+  for (int i = 0; i < 2 * NWORDS; ++i) vals[i] = 0.0f;
+  vals[0] = v[0]; vals[1] = v[1]; vals[2] = v[2];
+#pragma unroll
+  for (int k = 0; k < NFREQ; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(__fmul_rn(v[a], (float)(1 << k)), &s, &c);
+      vals[3 + 6 * k + a] = s;
+      vals[3 + 6 * k + 3 + a] = c;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NWORDS; ++i) out[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // barriers: full[3] empty[3] acc_full[2] act_ready[2]; tmem pointer after them
+  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
+  const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_pairs; ++it) {
+        const uint8_t* src = p.packed;
+        for (int s = 0; s < kNumSteps; ++s) {
+          const uint32_t bytes = (uint32_t)c_step_n[s] * 128u;
+          for (int t = 0; t < 2; ++t) {
+            const uint8_t* sp = src;
+            for (int c = 0; c < c_step_chunks[s]; ++c) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
+              bulk_g2s(sbase + SM_RING + stage * kChunkBig, sp, bytes, bar_full + 8 * stage);
+              sp += bytes;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          src += (size_t)c_step_chunks[s] * bytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t act_phase[2] = {0, 0};
+      for (int it = 0; it < my_pairs; ++it) {
+        for (int s = 0; s < kNumSteps; ++s) {
+          const int nch = c_step_chunks[s], n = c_step_n[s], ksteps = c_step_ksteps[s];
+          const uint32_t idesc = make_idesc(kTileM, n, 0, 0);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(bar_act + 8 * t, act_phase[t]);   // A operand written, accumulator drained
+            act_phase[t] ^= 1;
+            tcgen05_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+            uint32_t accumulate = (uint32_t)c_step_acc[s];
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tcgen05_fence_after_sync();
+              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + (nch == 1 ? 0 : c) * kAtomBytes;
+              const uint32_t b_addr = sbase + SM_RING + stage * kChunkBig;
+              const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
+              const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024);
+              for (int k = 0; k < ksteps; ++k) {
+                // +32 bytes (16 bf16) along K inside the 128-byte swizzle atom: start-address field += 2
+                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(bar_empty + 8 * stage);      // ring slot free once these MMAs have read it
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_acc + 8 * t);              // accumulator complete -> epilogue of tile t
+          }
+        }
+      }
+    }
+  } else {
+    // ================= prologue + epilogue warps =================
+    const int t = (warp - 2) >> 2;                       // tile slot 0/1
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                         // row inside the tile
+    uint8_t* act = smem + SM_ACT + t * kActBytes;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    uint32_t acc_phase = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + t;
+      const int64_t row = tile * kTileM + r;
+      const bool live = row < p.m;
+      uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
+      // ---- prologue: sample point -> encodings (kept packed in registers), gamma(pts) -> A atom 0
+      uint32_t encp[32], encd[16];
+      {
+        float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+        if (live) fetch_sample(p.src, row, pt, dir);
+        encode_point<10, 32>(pt, encp);
+        encode_point<4, 16>(dir, encd);
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) encp[i] = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) encd[i] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = make_uint4(encp[4 * j], encp[4 * j + 1], encp[4 * j + 2], encp[4 * j + 3]);
+          *reinterpret_cast<uint4*>(act + sw128_off(r, j)) = v;
+          if (kTrain) {
+            *reinterpret_cast<uint4*>(stash_tile + sw128_off(r, j)) = v;
+            uint4 dv = j < 4 ? make_uint4(encd[4 * j], encd[4 * j + 1], encd[4 * j + 2], encd[4 * j + 3]) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(stash_tile + (size_t)39 * kAtomBytes + sw128_off(r, j)) = dv;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_act + 8 * t);
+      }
+      float alpha = 0.0f;
+      for (int s = 0; s < kNumSteps; ++s) {
+        mbar_wait(bar_acc + 8 * t, acc_phase);
+        acc_phase ^= 1;
+        tcgen05_fence_after_sync();
+        const int epi = c_step_epi[s];
+        if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
+          // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 v;
+            if (epi == EPI_WRITE_ENC) v = make_uint4(encp[4 * j], encp[4 * j + 1], encp[4 * j + 2], encp[4 * j + 3]);
+            else v = j < 4 ? make_uint4(encd[4 * j], encd[4 * j + 1], encd[4 * j + 2], encd[4 * j + 3]) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(act + sw128_off(r, j)) = v;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(bar_act + 8 * t);
+          continue;
+        }
+        const float* bias = cst + c_step_bias[s];
+        if (epi == EPI_FINAL) {
+          // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123)
+          float rgb[3] = {cst[C_BR], cst[C_BR + 1], cst[C_BR + 2]};
+          uint32_t mask[4];
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(tmem_lane + cb * 32, v);
+            tmem_ld_wait();
+            uint32_t mb = 0, pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb * 32 + j;
+              float h = fmaxf(__uint_as_float(v[j]) + __ldg(bias + col), 0.0f);
+              mb |= (h > 0.0f ? 1u : 0u) << j;
+              rgb[0] = fmaf(h, __ldg(cst + C_WR + col), rgb[0]);
+              rgb[1] = fmaf(h, __ldg(cst + C_WR + 128 + col), rgb[1]);
+              rgb[2] = fmaf(h, __ldg(cst + C_WR + 256 + col), rgb[2]);
+              v[j] = __float_as_uint(h);
+            }
+            mask[cb] = mb;
+            if (kTrain) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = cb * 32 + g * 8;
+                *reinterpret_cast<uint4*>(stash_tile + (size_t)(37 + col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) =
+                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+              }
+            }
+          }
+          if (kTrain) {
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + (size_t)kStashAtoms * kAtomBytes) + (8 * 128 + r) * 8;
+            *reinterpret_cast<uint4*>(mrow) = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+          }
+          if (live) *reinterpret_cast<float4*>(p.raw + row * 4) = make_float4(rgb[0], rgb[1], rgb[2], alpha + cst[C_BA]);
+          tcgen05_fence_before_sync();
+          continue;   // next arrival on act_ready comes from the next tile's prologue
+        }
+        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
+        const bool relu = epi != EPI_LINEAR;
+        const int stash_atom = c_step_stash_atom[s];
+        uint32_t maskw[8];
+#pragma unroll 1
+        for (int cb = 0; cb < 8; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_lane + cb * 32, v);
+          tmem_ld_wait();
+          uint32_t mb = 0, pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + j));
+            float h0 = __uint_as_float(v[j]) + b4.x, h1 = __uint_as_float(v[j + 1]) + b4.y;
+            float h2 = __uint_as_float(v[j + 2]) + b4.z, h3 = __uint_as_float(v[j + 3]) + b4.w;
+            if (relu) { h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f); }
+            mb |= (h0 > 0.f ? 1u : 0u) << j | (h1 > 0.f ? 1u : 0u) << (j + 1) | (h2 > 0.f ? 1u : 0u) << (j + 2) |
+                  (h3 > 0.f ? 1u : 0u) << (j + 3);
+            if (epi == EPI_RELU_ALPHA) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + cb * 32 + j));
+              alpha = fmaf(h0, w4.x, fmaf(h1, w4.y, fmaf(h2, w4.z, fmaf(h3, w4.w, alpha))));
+            }
+            pk[j / 2] = pack_bf16(h0, h1);
+            pk[j / 2 + 1] = pack_bf16(h2, h3);
+          }
+          maskw[cb] = mb;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = cb * 32 + g * 8;
+            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
+            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            *reinterpret_cast<uint4*>(act + off) = v4;
+            if (kTrain) *reinterpret_cast<uint4*>(stash_tile + (size_t)stash_atom * kAtomBytes + off) = v4;
+          }
+        }
+        if (kTrain && c_step_mask_slot[s] >= 0) {
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + (size_t)kStashAtoms * kAtomBytes) +
+                           (c_step_mask_slot[s] * 128 + r) * 8;
+          *reinterpret_cast<uint4*>(mrow) = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
+          *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(maskw[4], maskw[5], maskw[6], maskw[7]);
+        }
+        if (s == 0) alpha = 0.0f;
+        tcgen05_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(bar_act + 8 * t);
+      }
+    }
+  }
+
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int check_arch() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      major = 0;
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) {
+    set_error("the tcgen05 MLP kernels need an sm_100 device (B200)");
+    return SPN_E_ARCH;
+  }
+  return SPN_OK;
+}
+
+int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* raw, void* stash, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != SPN_OK) return rc;
+  SPN_CHECK_ARG(((uintptr_t)packed & 15) == 0 && (!stash || ((uintptr_t)stash & 15) == 0), "mlp_tc_fwd: unaligned buffer");
+  FwdParams p;
+  p.packed = (const uint8_t*)packed; p.src = src; p.m = m; p.raw = raw; p.stash = (uint8_t*)stash;
+  int64_t tiles = (m + kTileM - 1) / kTileM;
+  p.num_pairs = (int)((tiles + 1) / 2);
+  int grid = p.num_pairs < sm_count() ? p.num_pairs : sm_count();
+  auto kern = stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[stash ? 1 : 0]) {
+    SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set[stash ? 1 : 0] = true;
+  }
+  prof_begin(PROF_MLP_FWD, st);
+  kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+  prof_end(PROF_MLP_FWD, st);
+  SPN_LAUNCH_CHECK("mlp_fwd_kernel");
+  return SPN_OK;
+}
+
+// ---- diagnostic: one UMMA GEMM  D[128,N] = A[128,K] * B[N,K]^T  (bf16 operands, fp32 accumulate) -------------
+// Exercises exactly the descriptor / swizzle / TMEM conventions the MLP kernels rely on, in isolation.
+__global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                float* __restrict__ D, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  uint8_t* sA = smem;                         // K/64 atoms of [128 x 64]
+  uint8_t* sB = smem + 4 * kAtomBytes;        // K/64 chunks of [N x 64]
+  const uint32_t bar = sbase + 4 * kAtomBytes + 4 * kChunkBig;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 4 * kAtomBytes + 4 * kChunkBig + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int katoms = K / 64;
+  for (int i = threadIdx.x; i < 128 * katoms * 8; i += 128) {      // A pieces
+    int j = i & 7, rr = (i >> 3) & 127, at = i >> 10;
+    const float* s = A + (size_t)rr * K + at * 64 + j * 8;
+    *reinterpret_cast<uint4*>(sA + at * kAtomBytes + sw128_off(rr, j)) =
+        make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+  }
+  for (int i = threadIdx.x; i < N * katoms * 8; i += 128) {        // B pieces
+    int j = i & 7, rr = (i >> 3) % N, at = (i >> 3) / N;
+    const float* s = B + (size_t)rr * K + at * 64 + j * 8;
+    *reinterpret_cast<uint4*>(sB + at * (N * 128) + sw128_off(rr, j)) =
+        make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(tptr), 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    uint32_t acc = 0;
+    for (int at = 0; at < katoms; ++at) {
+      const uint64_t a_desc = make_smem_desc(sbase + at * kAtomBytes, 16, 1024);
+      const uint64_t b_desc = make_smem_desc(sbase + 4 * kAtomBytes + at * (N * 128), 16, 1024);
+      for (int k = 0; k < 4; ++k) { umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc); acc = 1; }
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tcgen05_fence_after_sync();
+  for (int cb = 0; cb < N / 32; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * N + cb * 32 + j] = __uint_as_float(v[j]);
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
+}
+
+int tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != SPN_OK) return rc;
+  SPN_CHECK_ARG(A && B && D && (N == 128 || N == 256) && K >= 64 && K <= 256 && K % 64 == 0, "spn_tc_selftest_gemm: N in {128,256}, K in {64..256}");
+  const int smem_bytes = 4 * kAtomBytes + 4 * kChunkBig + 128 + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  selftest_gemm_kernel<<<1, 128, smem_bytes, st>>>(A, B, D, N, K);
+  SPN_LAUNCH_CHECK("selftest_gemm_kernel");
+  return SPN_OK;
+}
+
+size_t mlp_tc_bwd_ws_bytes(int64_t) { return 256; }
+int mlp_tc_bwd(const void*, const void*, const float*, int64_t, float*, void*, cudaStream_t) {
+  set_error("tcgen05 backward not built yet");
+  return SPN_E_ARG;
+}
+
+}  // namespace spn

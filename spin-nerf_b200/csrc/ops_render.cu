@@ -538,6 +538,7 @@ extern "C" int spn_raw2outputs_fwd(const float* raw, const float* z, const float
 int spn::composite_fwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise,
                        float noise_scale, int n, int S, int white_bkgd, float* rgb_map, float* disp_map,
                        float* acc_map, float* weights, float* depth_map, float* alpha, cudaStream_t stream) {
+  if (n == 0) return SPN_OK;   // empty batches carry null data pointers
   SPN_CHECK_ARG(raw && z && rays_d && rgb_map && disp_map && acc_map && weights && depth_map,
                 "spn_raw2outputs_fwd: null pointer");
   SPN_CHECK_ARG(n >= 0 && S >= 1 && ld_d >= 3, "spn_raw2outputs_fwd: bad shape n=%d S=%d", n, S);
@@ -562,6 +563,7 @@ int spn::composite_bwd(const float* raw, const float* z, const float* rays_d, in
                        float noise_scale, int n, int S, int white_bkgd, int detach_weights, const float* g_rgb,
                        const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
                        float* d_raw, cudaStream_t stream) {
+  if (n == 0) return SPN_OK;
   SPN_CHECK_ARG(raw && z && rays_d && d_raw, "spn_raw2outputs_bwd: null pointer");
   SPN_CHECK_ARG(n >= 0 && S >= 1 && S <= kMaxChunks * 32 && ld_d >= 3,
                 "spn_raw2outputs_bwd: S=%d outside [1,%d]", S, kMaxChunks * 32);

@@ -32,8 +32,8 @@ class _MLPFunction(torch.autograd.Function):
     z_samples are detached, run_nerf.py:700)."""
 
     @staticmethod
-    def forward(ctx, net, x6, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, net, need_grad, x6, *params):
+        # (grad mode is always off inside Function.forward, so the caller decides whether to stash)
         flat, packed = net._sync()
         stash = ops.mlp_stash(x6.shape[0], net.precision, x6.device) if need_grad else None
         raw, stash = ops.mlp_forward_points(flat, packed, x6, net.precision, stash)
@@ -48,7 +48,7 @@ class _MLPFunction(torch.autograd.Function):
         ops.mlp_backward(flat, packed, ctx.stash, d_raw.contiguous(), g, net.precision)
         ctx.stash = None
         grads = [g[o:o + p.numel()].view(p.shape) for o, p in zip(net._offsets, net._flat_params())]
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class NeRF(nn.Module):
@@ -142,7 +142,9 @@ class NeRF(nn.Module):
     def forward(self, x):
         sh = x.shape
         x6 = self._as_points(x).reshape(-1, 6).float().contiguous()
-        raw = _MLPFunction.apply(self, x6, *self._flat_params())
+        params = self._flat_params()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        raw = _MLPFunction.apply(self, need_grad, x6, *params)
         return raw.reshape(*sh[:-1], 4)
 
     def load_weights_from_keras(self, weights):

@@ -38,7 +38,7 @@ class RenderChunk(torch.autograd.Function):
         prec = net_c.precision
         dev = rays.device
         E = lambda *sh: torch.empty(sh, device=dev, dtype=torch.float32)
-        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        train = opts["train"]       # decided by the caller: grad mode is off inside Function.forward
         flat_c, packed_c = net_c._sync()
         flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
         cfg = L.RenderCfg(n, ncols, S, NI, _flags(opts["lindisp"], opts["white_bkgd"], opts["detach_weights"],
@@ -145,6 +145,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 white_bkgd=bool(white_bkgd), detach_weights=bool(detach_weights), perturb=perturb > 0.,
                 need_alpha=bool(need_alpha), raw_noise_std=float(raw_noise_std))
     params = network_fn._flat_params() + (network_fine._flat_params() if network_fine is not None else [])
+    opts["train"] = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     outs = RenderChunk.apply(opts, ray_batch, network_fn, network_fine, t_rand, u, noise0, noise1, *params)
     names = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "raw"]
     if N_importance > 0:

@@ -274,6 +274,88 @@ def test_train_step_matches_reference_fp32():
             close_mostly(N(v).reshape(-1)[::997], tr[f"p_sub__{nm}__{k}"], rtol=0, atol=2e-4, max_frac=0.03, hard=1.0)
 
 
+# ---- tcgen05 (bf16) path ----------------------------------------------------------------------------
+def bf16r(a):
+    """round-to-nearest-even to bfloat16, returned as float32 (what cvt.rn.bf16x2.f32 does)."""
+    return N(torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).float())
+
+
+def mlp_forward_bf16(p, x6):
+    """The kernel's arithmetic restated on the CPU: bf16 operands (weights, encodings, activations), fp32
+    accumulation, fp32 bias/ReLU, sigma from the fp32 h7, rgb from the fp32 hv."""
+    W = lambda k: bf16r(p[k])
+    xp = bf16r(O.embed(x6[:, :3], 10)); xd = bf16r(O.embed(x6[:, 3:], 4))
+    acts = {"xp": xp, "xd": xd}
+    h = xp
+    for i in range(8):
+        w = W(f"pts_linears.{i}.weight")
+        pre = (h @ w[:, 63:].T + xp @ w[:, :63].T) if i == 5 else h @ w.T
+        hf = np.maximum(pre + p[f"pts_linears.{i}.bias"], 0).astype(np.float32)
+        h = bf16r(hf); acts[f"h{i}"] = h
+    alpha = hf @ p["alpha_linear.weight"].T + p["alpha_linear.bias"]
+    feat = bf16r(h @ W("feature_linear.weight").T + p["feature_linear.bias"]); acts["feat"] = feat
+    wv = W("views_linears.0.weight")
+    hv = np.maximum(feat @ wv[:, :256].T + xd @ wv[:, 256:].T + p["views_linears.0.bias"], 0).astype(np.float32)
+    acts["hv"] = bf16r(hv)
+    rgb = hv @ p["rgb_linear.weight"].T + p["rgb_linear.bias"]
+    return np.concatenate([rgb, alpha], -1).astype(np.float32), acts
+
+
+@pytest.mark.parametrize("N_,K", [(256, 64), (256, 256), (128, 128), (128, 64)])
+def test_tc_selftest_gemm(N_, K):
+    rng = np.random.default_rng(N_ + K)
+    A = rng.standard_normal((128, K)).astype(np.float32); B = rng.standard_normal((N_, K)).astype(np.float32)
+    D = torch.full((128, N_), float("nan"), device=DEV)
+    spn._lib.check(spn._lib.lib().spn_tc_selftest_gemm(spn._lib.ptr(T(A)), spn._lib.ptr(T(B)), spn._lib.ptr(D), N_, K,
+                                                       spn._lib.stream()), "selftest")
+    torch.cuda.synchronize()
+    ref = bf16r(A).astype(np.float64) @ bf16r(B).astype(np.float64).T
+    np.save("gpurun_out/selftest_D_%d_%d.npy" % (N_, K), N(D)) if __import__("os").path.isdir("gpurun_out") else None
+    close(D, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_mlp_bf16_forward_matches_emulation_and_oracle():
+    g, x90, x6 = _mlp_case()
+    net, p = make_net(11, spn.PREC_BF16)
+    with torch.no_grad():
+        raw = N(net(T(x6)))
+    emu, _ = mlp_forward_bf16(p, x6)
+    scale = np.abs(g["raw"]).max()
+    if __import__("os").path.isdir("gpurun_out"):
+        np.savez("gpurun_out/mlp_bf16_dbg.npz", raw=raw, emu=emu, ref=g["raw"])
+    assert np.abs(raw - emu).max() <= 2e-3 * scale, np.abs(raw - emu).max() / scale      # same arithmetic, other sum order
+    assert np.abs(raw - g["raw"]).max() <= 2e-2 * scale                                  # vs the fp32 reference
+
+
+@pytest.mark.parametrize("m", [1, 127, 128, 129, 257, 1000, 40000])
+def test_mlp_bf16_ragged_and_multi_tile(m):
+    net, p = make_net(11, spn.PREC_BF16)
+    rng = np.random.default_rng(m)
+    x6 = np.concatenate([rng.standard_normal((m, 3)) * 2, rng.standard_normal((m, 3))], -1).astype(np.float32)
+    x6[:, 3:] /= np.linalg.norm(x6[:, 3:], axis=1, keepdims=True)
+    with torch.no_grad():
+        raw = N(net(T(x6)))
+    sel = rng.choice(m, min(m, 512), replace=False)
+    emu, _ = mlp_forward_bf16(p, x6[sel])
+    assert np.abs(raw[sel] - emu).max() <= 3e-3 * max(1.0, np.abs(emu).max())
+
+
+def test_render_bf16_psnr_vs_reference():
+    g = load_golden("render")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    netc, _ = make_net(11, spn.PREC_BF16, 1.0)
+    netf, _ = make_net(12, spn.PREC_BF16, 1.0)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=32768, rays=T(g["rays"]), retraw=True, use_viewdirs=True,
+                                               ndc=False, near=1.2, far=8.0, network_query_fn=None, network_fn=netc,
+                                               network_fine=netf, N_samples=64, N_importance=64, lindisp=True,
+                                               white_bkgd=True, perturb=0., raw_noise_std=0.)
+    ref = g["det_lindisp_white__rgb"]
+    mse = float(((N(rgb) - ref) ** 2).mean())
+    assert -10 * np.log10(mse) > 35.0, -10 * np.log10(mse)          # bf16 render vs the fp32 reference render
+    assert np.abs(N(ex["rgb0"]) - g["det_lindisp_white__rgb0"]).max() < 3e-2
+
+
 def test_adam_flat_matches_torch():
     rng = np.random.default_rng(4)
     p = rng.standard_normal(10007).astype(np.float32); gr = rng.standard_normal(10007).astype(np.float32)

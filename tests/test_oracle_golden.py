@@ -133,3 +133,29 @@ def test_render_end_to_end(tag):
         close(out["rgb0"], G("rgb0"), atol=2e-4)
         cm(out["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
         cm(out["alpha"], G("alpha"), rtol=0, atol=2e-4); close(out["alpha0"], G("alpha0"), atol=2e-4)
+
+
+def test_train_step_oracle_matches_reference_autograd():
+    """oracle/train_oracle.py (loss, both nets' gradients, two Adam steps) vs autograd + torch.optim.Adam run
+    through the reference's render() (golden train_step)."""
+    from oracle import train_oracle as TO
+    g = load_golden("render"); tr = load_golden("train_step")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    pc = O.init_params(11); pc["alpha_linear.bias"] = pc["alpha_linear.bias"] + 1.0
+    pf = O.init_params(12); pf["alpha_linear.bias"] = pf["alpha_linear.bias"] + 1.0
+    rb = O.make_ray_batch(g["rays"][0], g["rays"][1], 1.2, 8.0)
+    sc, sf = TO.AdamState(pc), TO.AdamState(pf)
+    u = np.broadcast_to(g["lin64"], (48, 64))
+    for it in range(2):
+        loss, gc, gf = TO.train_step(rb, tr["target"], tr["tdisp"], pc, pf, sc, sf, 5e-4, t_vals=g["lin64"], u=u)
+        assert abs(loss - float(tr[f"loss{it}"])) <= 1e-4 * abs(float(tr[f"loss{it}"]))
+        if it == 0:
+            for nm, gr in (("c", gc), ("f", gf)):
+                for k, gv in gr.items():
+                    ref_abs = float(tr[f"g_abs__{nm}__{k}"])
+                    assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
+                    close_mostly(gv.reshape(-1)[::997], tr[f"g_sub__{nm}__{k}"], rtol=1e-2,
+                                 atol=1e-3 * np.abs(gv).max() + 1e-9, max_frac=0.03, hard=1.0)
+    for nm, p in (("c", pc), ("f", pf)):
+        for k, v in p.items():
+            close_mostly(v.reshape(-1)[::997], tr[f"p_sub__{nm}__{k}"], rtol=0, atol=2e-4, max_frac=0.03, hard=1.0)
