@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — rays/sec of the SPIn-NeRF train step (3 render calls -> losses -> backward -> Adam) on B200.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5          # our arm (one JSON line)
+  python bench.py --impl reference --steps 3 --warmup 1   # the reference algorithm on the host CPUs (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...       # ray-sharded data parallel, NCCL grad all-reduce
+
+Workload (BASELINE.json configs[1]): statue-shaped synthetic LLFF scene, 1008x756 (factor 2), 30 views,
+coarse+fine N_samples=64 N_importance=64, N_rand=1024 rays per render call per GPU, no_ndc, lindisp,
+white_bkgd, use_viewdirs, perturb=1, raw_noise_std=1, random-init weights (seed 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 756, 1008
+FOCAL = 0.9 * W
+N_VIEWS = 30
+NEAR, FAR = 1.2, 8.0
+FLOP_FWD, FLOP_BWD = 1186816, 2302208            # per MLP evaluation
+EVALS_PER_RAY = 192                              # 64 coarse + 128 fine
+RENDERS_PER_STEP = 3
+
+
+def poses(n, seed=0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        z = np.array([0.1, -0.05, 1.0]) + rng.standard_normal(3) * 0.05
+        z /= np.linalg.norm(z)
+        x = np.cross([0, 1, 0], z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        pos = np.array([rng.uniform(-.5, .5), rng.uniform(-.5, .5), 0.0])
+        out.append(np.stack([x, y, z, pos], 1).astype(np.float32))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the train step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(n_rays, steps, warmup, seed=0):
+    from oracle import nerf_oracle as O
+    from oracle import train_oracle as TO
+    rng = np.random.default_rng(seed)
+    pc, pf = O.init_params(1), O.init_params(2)
+    sc, sf = TO.AdamState(pc), TO.AdamState(pf)
+    ps = poses(4)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for call in range(RENDERS_PER_STEP):
+            ro, rd = O.get_rays(H, W, FOCAL, ps[(it + call) % len(ps)])
+            sel = rng.choice(H * W, n_rays, replace=False)
+            rb = O.make_ray_batch(ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], NEAR, FAR)
+            tgt = rng.uniform(0, 1, (n_rays, 3)).astype(np.float32); td = rng.uniform(0, 1, n_rays).astype(np.float32)
+            t_rand = rng.uniform(0, 1, (n_rays, 64)).astype(np.float32); u = rng.uniform(0, 1, (n_rays, 64)).astype(np.float32)
+
+            def g_out(o, call=call):
+                if call < 2:
+                    return dict(rgb_map=TO.mse_grad(o["rgb_map"], tgt)[1], rgb0=TO.mse_grad(o["rgb0"], tgt)[1])
+                return dict(disp_map=TO.mse_grad(o["disp_map"], td)[1], disp0=TO.mse_grad(o["disp0"], td)[1])
+            _, gc, gf = TO.render_with_grads(rb, pc, pf, 64, 64, True, True, g_out, detach_weights=(call == 1), u=u,
+                                             t_rand=t_rand, noise0=rng.standard_normal((n_rays, 64)).astype(np.float32),
+                                             noise1=rng.standard_normal((n_rays, 128)).astype(np.float32))
+            if call == 0:
+                acc_c, acc_f = gc, gf
+            else:
+                acc_c = {k: acc_c[k] + gc[k] for k in gc}; acc_f = {k: acc_f[k] + gf[k] for k in gf}
+        for p, g, st in ((pc, acc_c, sc), (pf, acc_f, sf)):
+            st.step += 1
+            for k in p:
+                p[k], st.m[k], st.v[k] = O.adam_step(p[k], g[k], st.m[k], st.v[k], st.step, 5e-4)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return RENDERS_PER_STEP * n_rays * len(times) / sum(times), float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_rays
+    rps, sec = cpu_train_steps(n, args.steps, args.warmup)
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "rays/sec (train-step)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, n),
+            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{RENDERS_PER_STEP}x{n} rays per step (same scene/config), numpy+BLAS oracle port of the reference train step"},
+            "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, n_rand):
+    return {"workload": "statue-shaped synthetic LLFF 1008x756 (factor 2), 30 views, coarse+fine N_samples=64 N_importance=64, "
+                        f"N_rand={n_rand} rays per render call per GPU, {RENDERS_PER_STEP} render calls per step, "
+                        "no_ndc lindisp white_bkgd use_viewdirs perturb=1 raw_noise_std=1 (BASELINE configs[1])",
+            "n_rand_per_gpu": n_rand, "renders_per_step": RENDERS_PER_STEP, "parallelism": f"ray-dp{n_gpus}",
+            "l2": "ray pool 548 MB + per-step activation stash > 126 MB L2; L2 flushed (256 MB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n_rand", type=int, default=1024)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--cpu_rays", type=int, default=64, help="rays per render call in the CPU sample")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    spn = importlib.import_module("spin-nerf_b200")
+    from oracle import nerf_oracle as O            # weights init + cpu_baseline leg only
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    prec = spn.PREC_BF16 if args.precision == "bf16" else spn.PREC_FP32
+
+    # ---- model: reference-shaped coarse + fine networks, seeded init (identical on every rank)
+    nets = []
+    for seed in (1, 2):
+        net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.init_params(seed).items()})
+        net = net.to(dev); net.precision = prec
+        nets.append(net)
+    n_rand = args.n_rand
+    sharder = trainer_mod.RaySharder(rank, world)
+    tr = trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                             perturb=1.0, raw_noise_std=1.0, near=NEAR, far=FAR, ndc=False, hwf=(H, W, FOCAL),
+                             sharder=sharder)
+
+    # ---- synthetic scene resident in HBM: all rays of all views (548 MB), targets, inpainted disparities
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    ro_all, rd_all = [], []
+    for c2w in poses(N_VIEWS):
+        ro, rd = spn.ops.get_rays(H, W, FOCAL, torch.from_numpy(c2w).to(dev))
+        ro_all.append(ro.reshape(-1, 3)); rd_all.append(rd.reshape(-1, 3))
+    pool = torch.stack([torch.cat(ro_all), torch.cat(rd_all)], 0)            # [2, M, 3]
+    M = pool.shape[1]
+    rgb_pool = torch.rand(M, 3, device=dev, generator=g); disp_pool = torch.rand(M, device=dev, generator=g)
+    global_n = n_rand * world
+
+    def device_batches():
+        idx = torch.randint(0, M, (3, global_n), device=dev, generator=g)
+        return (pool[:, idx[0]], rgb_pool[idx[0]], pool[:, idx[1]], rgb_pool[idx[1]], pool[:, idx[2]], disp_pool[idx[2]])
+
+    flush = torch.empty(64 * 1024 * 1024, device=dev)                         # 256 MB > 126 MB L2
+
+    def run_steps(k, batch_fn, timed):
+        ms, evs = 0.0, []
+        for _ in range(k):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss, psnr = tr.step(*batch_fn())
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs], loss
+
+    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    run_steps(args.warmup, device_batches, False)
+    barrier(); torch.cuda.synchronize()
+    L = spn._lib.lib()
+    L.spn_profile_enable(1); L.spn_launch_count(1)
+    clocks = ClockSampler(local); clocks.start()
+    t_wall = time.perf_counter()
+    times, loss = run_steps(args.steps, device_batches, True)
+    torch.cuda.synchronize(); barrier()
+    wall = time.perf_counter() - t_wall
+    clk = clocks.stop()
+    launches = int(L.spn_launch_count(0))
+    import ctypes
+    prof = {}
+    for kind, name in ((0, "mlp_fwd"), (1, "mlp_dgrad"), (2, "mlp_wgrad")):
+        n_l, ms_l = ctypes.c_int(), ctypes.c_float()
+        L.spn_profile_read(kind, ctypes.byref(n_l), ctypes.byref(ms_l))
+        prof[name] = (n_l.value, ms_l.value)
+    L.spn_profile_enable(0)
+    step_ms = float(np.sum(times))
+    if world > 1:
+        t = torch.tensor([step_ms], device=dev); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        step_ms = float(t.item())
+    rays_per_step = RENDERS_PER_STEP * global_n
+    value = rays_per_step * args.steps / (step_ms * 1e-3)
+
+    # ---- e2e: the public train-step API fed from pinned HOST memory, loss read back each step
+    host = [tuple(t.cpu().pin_memory() for t in device_batches()) for _ in range(args.warmup + args.steps)]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    it = iter(host)
+
+    def host_batches():
+        return tuple(t.to(dev, non_blocking=True) for t in next(it))
+
+    def e2e_steps(k):
+        evs = []
+        for _ in range(k):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss, psnr = tr.step(*host_batches())
+            _ = float(loss)                      # D2H of the step's result (synchronises)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+    e2e_steps(args.warmup)
+    barrier()
+    e2e_ms = float(np.sum(e2e_steps(args.steps)))
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = rays_per_step * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (fused MLP forward, tcgen05): MLP FLOPs / CUDA-event time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    evals_per_rank_step = RENDERS_PER_STEP * n_rand * EVALS_PER_RAY
+    fwd_n, fwd_ms = prof["mlp_fwd"]
+    kern = {}
+    for name, flop in (("mlp_fwd", FLOP_FWD), ("mlp_dgrad", 2 * 557696), ("mlp_wgrad", 2 * 593408)):
+        n_l, ms_l = prof[name]
+        if n_l and ms_l > 0:
+            kern[name] = {"launches_per_step": n_l / args.steps, "ms_per_step": ms_l / args.steps,
+                          "tflops": evals_per_rank_step * flop * args.steps / (ms_l * 1e-3) / 1e12}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                    "frac": kern[dom]["tflops"] / peak, "traffic": traffic, "peak_source": peak_src, "kernels": kern,
+                    "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
+    cpu = None
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        rps, sec = cpu_train_steps(args.cpu_rays, 2, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"3 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, numpy+BLAS oracle port "
+                         f"of the reference train step ({time.perf_counter() - t0:.1f} s)"}
+    line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
+            "config": workload_config(world, n_rand), "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "roofline": roofline, "cpu_baseline": cpu, "n_rand_per_sec": value / RENDERS_PER_STEP,
+            "wall_s_timed_region": wall, "final_loss": float(loss)}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -6,14 +6,17 @@ OUT="$HERE/../libspinnerf_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH=(-gencode arch=compute_100a,code=sm_100a)
 FLAGS=(-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v)
+SRCS=(api ops_render mlp_fp32 mlp_tc mlp_tc_bwd)
 mkdir -p "$HERE/obj"
 pids=()
-for f in api ops_render mlp_fp32 mlp_tc; do
+for f in "${SRCS[@]}"; do
   ( "$NVCC" "${ARCH[@]}" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" > "$HERE/obj/$f.log" 2>&1 ) &
   pids+=($!)
 done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "$HERE"/obj/*.log; exit 1; fi
-"$NVCC" "${ARCH[@]}" --shared -o "$OUT" "$HERE"/obj/{api,ops_render,mlp_fp32,mlp_tc}.o
+OBJS=()
+for f in "${SRCS[@]}"; do OBJS+=("$HERE/obj/$f.o"); done
+"$NVCC" "${ARCH[@]}" --shared -o "$OUT" "${OBJS[@]}"
 echo "built $OUT"

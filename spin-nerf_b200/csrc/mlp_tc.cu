@@ -17,27 +17,10 @@
 // updated in place; the encodings stay packed in registers in between.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "mlp_tc.cuh"
 
 namespace spn {
 using namespace tc;
-
-// ---- packed weight image -----------------------------------------------------------------------
-constexpr int kChunkBig = 256 * 128;   // [256 rows x 64 bf16] = 32 KB
-constexpr int kChunkV = 128 * 128;     // [128 rows x 64 bf16] = 16 KB
-constexpr int kFwdChunks = 39;
-constexpr int kBwdChunks = 34;
-constexpr size_t kFwdBytes = 34 * (size_t)kChunkBig + 5 * (size_t)kChunkV;
-constexpr size_t kBwdBytes = (size_t)kBwdChunks * kChunkBig;
-// fp32 constants that the epilogues read (floats)
-constexpr int C_B = 0;          // b0..b7 [8][256]
-constexpr int C_BF = 2048;      // feature bias [256]
-constexpr int C_BV = 2304;      // views bias [128]
-constexpr int C_WA = 2432;      // alpha weight [256]
-constexpr int C_BA = 2688;      // alpha bias (padded to 4)
-constexpr int C_WR = 2692;      // rgb weight [3][128]
-constexpr int C_BR = 3076;      // rgb bias (padded to 4)
-constexpr int kConstFloats = 3080;
-constexpr size_t kPackedBytes = kFwdBytes + kBwdBytes + kConstFloats * sizeof(float);
 
 size_t mlp_tc_packed_bytes() { return kPackedBytes; }
 
@@ -132,17 +115,8 @@ int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
   return SPN_OK;
 }
 
-// ---- kernel geometry ------------------------------------------------------------------------------
-constexpr int kTileM = 128;
-constexpr int kAtomBytes = kTileM * 128;        // [128 rows x 64 bf16] swizzle atom = 16 KB
-constexpr int kActBytes = 4 * kAtomBytes;       // 256-wide activation tile = 64 KB
-constexpr int kStages = 3;
-constexpr int kThreads = 320;
+// ---- kernel geometry: see mlp_tc.cuh ---------------------------------------------------------------
 constexpr int kNumSteps = 12;
-constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
-constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
-constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers + tmem pointer
-constexpr int kSmemBytes = SM_BAR + 256 + 1024;            // + slack for 1024-byte alignment
 
 // step tables (forward).  A step = one accumulation pass on the tensor cores followed by an epilogue action.
 enum EpiAction : int { EPI_RELU = 0, EPI_WRITE_ENC = 1, EPI_LINEAR = 2, EPI_WRITE_DENC = 3, EPI_FINAL = 4, EPI_RELU_ALPHA = 5 };
@@ -157,14 +131,6 @@ __constant__ int c_step_bias[kNumSteps] = {C_B + 0, C_B + 256, C_B + 512, C_B + 
 // stash slot written after the step's epilogue (-1: none).  Slots are 16 KB atoms inside the per-tile stash.
 __constant__ int c_step_stash_atom[kNumSteps] = {1, 5, 9, 13, 17, -1, 21, 25, 29, 33, -1, 37};
 __constant__ int c_step_mask_slot[kNumSteps] = {0, 1, 2, 3, 4, -1, 5, 6, 7, -1, -1, 8};
-
-// per-tile stash (training): bf16 SWIZZLE_128B images, 16 KB atoms:
-//   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)
-//   atoms 33-36 feature                          atoms 37-38   hv (128 wide)
-//   atom 39     gamma(viewdir) (27 + pad)
-// followed by ReLU masks: 9 slots x 128 rows x 8 words (h0..h7, hv)
-constexpr int kStashAtoms = 40;
-constexpr size_t kStashTileBytes = (size_t)kStashAtoms * kAtomBytes + 9 * 128 * 32;   // 692224 B per 128 samples
 
 size_t mlp_tc_stash_bytes(int64_t m) {
   int64_t tiles = (m + 2 * kTileM - 1) / (2 * kTileM) * 2;   // tiles are processed in pairs
@@ -545,12 +511,6 @@ int tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, cud
   selftest_gemm_kernel<<<1, 128, smem_bytes, st>>>(A, B, D, N, K);
   SPN_LAUNCH_CHECK("selftest_gemm_kernel");
   return SPN_OK;
-}
-
-size_t mlp_tc_bwd_ws_bytes(int64_t) { return 256; }
-int mlp_tc_bwd(const void*, const void*, const float*, int64_t, float*, void*, cudaStream_t) {
-  set_error("tcgen05 backward not built yet");
-  return SPN_E_ARG;
 }
 
 }  // namespace spn

@@ -1,0 +1,53 @@
+// Layout constants shared by the tcgen05 MLP kernels (forward: mlp_tc.cu, backward: mlp_tc_bwd.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace spn {
+
+// ---- packed weight image (spn_mlp_pack_weights) ------------------------------------------------------
+constexpr int kChunkBig = 256 * 128;   // [256 rows x 64 bf16] SWIZZLE_128B = 32 KB
+constexpr int kChunkV = 128 * 128;     // [128 rows x 64 bf16] = 16 KB
+constexpr int kFwdChunks = 39;
+constexpr int kBwdChunks = 34;
+constexpr size_t kFwdBytes = 34 * (size_t)kChunkBig + 5 * (size_t)kChunkV;
+constexpr size_t kBwdBytes = (size_t)kBwdChunks * kChunkBig;
+// fp32 constants the epilogues read (float offsets inside the constant block that follows the chunks)
+constexpr int C_B = 0;          // b0..b7 [8][256]
+constexpr int C_BF = 2048;      // feature bias [256]
+constexpr int C_BV = 2304;      // views bias [128]
+constexpr int C_WA = 2432;      // alpha weight [256]
+constexpr int C_BA = 2688;      // alpha bias (padded to 4)
+constexpr int C_WR = 2692;      // rgb weight [3][128]
+constexpr int C_BR = 3076;      // rgb bias (padded to 4)
+constexpr int kConstFloats = 3080;
+constexpr size_t kPackedBytes = kFwdBytes + kBwdBytes + kConstFloats * sizeof(float);
+
+// ---- tile geometry ------------------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kAtomBytes = kTileM * 128;        // [128 rows x 64 bf16] swizzle atom = 16 KB
+constexpr int kActBytes = 4 * kAtomBytes;       // 256-wide activation tile = 64 KB
+constexpr int kStages = 3;
+constexpr int kThreads = 320;
+constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
+constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
+constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers + tmem pointer
+constexpr int kSmemBytes = SM_BAR + 256 + 1024;            // + slack for 1024-byte alignment
+
+// ---- per-tile forward stash (training): bf16 SWIZZLE_128B images, 16 KB atoms -----------------------------
+//   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)
+//   atoms 33-36 feature                          atoms 37-38   hv (128 wide)
+//   atom 39     gamma(viewdir) (27 + pad)
+// followed by ReLU masks: 9 slots (h0..h7, hv) x 128 rows x 8 words
+constexpr int kStashAtoms = 40;
+constexpr int SA_ENC = 0, SA_H0 = 1, SA_FEAT = 33, SA_HV = 37, SA_DENC = 39;
+constexpr size_t kStashMaskOff = (size_t)kStashAtoms * kAtomBytes;
+constexpr size_t kStashTileBytes = kStashMaskOff + 9 * 128 * 32;   // 692224 B per 128 samples
+
+// ---- per-tile backward stash (dgrad -> wgrad): d(pre-activation) as bf16 images -----------------------------
+//   atoms 0-1  d_hv (128 wide)    atoms 2-5  d_feat     atoms 6+4*(7-i) .. : d_h{i} for i = 7..0
+constexpr int kDstashAtoms = 38;
+constexpr int DA_HV = 0, DA_FEAT = 2, DA_H7 = 6;
+constexpr size_t kDstashTileBytes = (size_t)kDstashAtoms * kAtomBytes;   // 622592 B per 128 samples
+
+}  // namespace spn

@@ -1,0 +1,528 @@
+// Backward of the NeRF MLP (what autograd does for DS_NeRF/run_nerf_helpers.py:104-127) on tcgen05.
+//
+// Three kernels, all reading the bf16 activation stash the training forward wrote (mlp_tc.cu):
+//   mlp_dgrad_kernel   per 128-sample tile, the chain  d_hv -> d_feat -> d_h7 -> ... -> d_h0  as nine fused GEMMs
+//                      against the transposed weight images (same ping-pong / TMEM / bulk-copy-ring skeleton as
+//                      the forward); ReLU masks come from the 1-bit-per-activation mask stash; every
+//                      d(pre-activation) tile is written once as a bf16 SWIZZLE_128B image (the "dstash").
+//   mlp_wgrad_kernel   dW_l = dpre_l^T . in_l  as a split-K GEMM over ALL samples: operands are the stash /
+//                      dstash tiles used directly as MN-major UMMA operands (K = sample index), fp32 accumulators
+//                      for a full 256x256 weight gradient live in the 512 TMEM columns, one red.global flush per
+//                      (layer, sample-range) segment.  Bias gradients are column sums taken from the same
+//                      shared-memory slabs by otherwise idle warps.
+//   mlp_heads_wgrad_kernel   the 3x128 rgb / 1x256 sigma heads on CUDA cores.
+// No gradient flows to the sampled points (z_samples are detached, run_nerf.py:700).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "mlp_tc.cuh"
+
+namespace spn {
+using namespace tc;
+
+static int check_arch_bwd() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      major = 0;
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) {
+    set_error("the tcgen05 MLP kernels need an sm_100 device (B200)");
+    return SPN_E_ARCH;
+  }
+  return SPN_OK;
+}
+
+static inline int64_t even_tiles(int64_t m) { return (m + 2 * kTileM - 1) / (2 * kTileM) * 2; }
+size_t mlp_tc_bwd_ws_bytes(int64_t m) { return (size_t)even_tiles(m) * kDstashTileBytes + 256; }
+
+// =====================================================================================================
+// dgrad
+// =====================================================================================================
+constexpr int kDgSteps = 9;
+__constant__ int c_dg_chunks[kDgSteps] = {2, 4, 4, 4, 4, 4, 4, 4, 4};
+// ReLU-mask slot applied by the step's epilogue (-1: none) and destination atom inside the dstash tile
+__constant__ int c_dg_mask[kDgSteps] = {-1, 7, 6, 5, 4, 3, 2, 1, 0};
+__constant__ int c_dg_dst[kDgSteps] = {DA_FEAT, DA_H7, DA_H7 + 4, DA_H7 + 8, DA_H7 + 12, DA_H7 + 16, DA_H7 + 20,
+                                       DA_H7 + 24, DA_H7 + 28};
+
+struct DgradParams {
+  const uint8_t* packed;
+  const uint8_t* stash;
+  const float* d_raw;
+  uint8_t* dstash;
+  int64_t m;
+  int num_pairs;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
+  const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- weight producer (transposed images)
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_pairs; ++it) {
+        const uint8_t* src = p.packed + kFwdBytes;
+        for (int s = 0; s < kDgSteps; ++s) {
+          for (int t = 0; t < 2; ++t) {
+            const uint8_t* sp = src;
+            for (int c = 0; c < c_dg_chunks[s]; ++c) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(bar_full + 8 * stage, kChunkBig);
+              bulk_g2s(sbase + SM_RING + stage * kChunkBig, sp, kChunkBig, bar_full + 8 * stage);
+              sp += kChunkBig;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          src += (size_t)c_dg_chunks[s] * kChunkBig;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer
+      uint32_t stage = 0, phase = 0;
+      uint32_t act_phase[2] = {0, 0};
+      const uint32_t idesc = make_idesc(kTileM, 256, 0, 0);
+      for (int it = 0; it < my_pairs; ++it) {
+        for (int s = 0; s < kDgSteps; ++s) {
+          const int nch = c_dg_chunks[s];
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(bar_act + 8 * t, act_phase[t]);
+            act_phase[t] ^= 1;
+            tcgen05_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+            uint32_t accumulate = 0;
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tcgen05_fence_after_sync();
+              const uint64_t a_desc = make_smem_desc(sbase + SM_ACT + t * kActBytes + c * kAtomBytes, 16, 1024);
+              const uint64_t b_desc = make_smem_desc(sbase + SM_RING + stage * kChunkBig, 16, 1024);
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(bar_empty + 8 * stage);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_acc + 8 * t);
+          }
+        }
+      }
+    }
+  } else {
+    // ---- prologue + epilogue warps
+    const int t = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint8_t* act = smem + SM_ACT + t * kActBytes;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    uint32_t acc_phase = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + t;
+      const int64_t row = tile * kTileM + r;
+      const bool live = row < p.m;
+      const uint8_t* stash_tile = p.stash + (size_t)tile * kStashTileBytes;
+      uint8_t* dst_tile = p.dstash + (size_t)tile * kDstashTileBytes;
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
+      // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide]  -> A atoms 0-1 and dstash atoms 0-1
+      float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const uint4 mk = *reinterpret_cast<const uint4*>(masks + (8 * 128 + r) * 8);
+        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int col = cb * 32 + j;
+            float v0 = dr.x * __ldg(cst + C_WR + col) + dr.y * __ldg(cst + C_WR + 128 + col) + dr.z * __ldg(cst + C_WR + 256 + col);
+            float v1 = dr.x * __ldg(cst + C_WR + col + 1) + dr.y * __ldg(cst + C_WR + 129 + col) + dr.z * __ldg(cst + C_WR + 257 + col);
+            v0 = ((mw[cb] >> j) & 1u) ? v0 : 0.f;
+            v1 = ((mw[cb] >> (j + 1)) & 1u) ? v1 : 0.f;
+            pk[j / 2] = pack_bf16(v0, v1);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = cb * 32 + g * 8;
+            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
+            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            *reinterpret_cast<uint4*>(act + off) = v4;
+            *reinterpret_cast<uint4*>(dst_tile + (size_t)DA_HV * kAtomBytes + off) = v4;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_act + 8 * t);
+      }
+      for (int s = 0; s < kDgSteps; ++s) {
+        mbar_wait(bar_acc + 8 * t, acc_phase);
+        acc_phase ^= 1;
+        tcgen05_fence_after_sync();
+        const int mslot = c_dg_mask[s];
+        uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        if (mslot >= 0) {
+          const uint4 m0 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8);
+          const uint4 m1 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8 + 4);
+          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+        }
+        const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
+        const int dst_atom = c_dg_dst[s];
+        const bool last = s == kDgSteps - 1;
+#pragma unroll 1
+        for (int cb = 0; cb < 8; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_lane + cb * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          const uint32_t mb = mw[cb];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(v[j]), v1 = __uint_as_float(v[j + 1]);
+            if (s == 1) {
+              v0 = fmaf(dalpha, __ldg(cst + C_WA + cb * 32 + j), v0);
+              v1 = fmaf(dalpha, __ldg(cst + C_WA + cb * 32 + j + 1), v1);
+            }
+            v0 = ((mb >> j) & 1u) ? v0 : 0.f;
+            v1 = ((mb >> (j + 1)) & 1u) ? v1 : 0.f;
+            pk[j / 2] = pack_bf16(v0, v1);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = cb * 32 + g * 8;
+            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
+            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            if (!last) *reinterpret_cast<uint4*>(act + off) = v4;
+            *reinterpret_cast<uint4*>(dst_tile + (size_t)dst_atom * kAtomBytes + off) = v4;
+          }
+        }
+        tcgen05_fence_before_sync();
+        if (!last) {
+          fence_proxy_async_smem();
+          mbar_arrive(bar_act + 8 * t);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// wgrad
+// =====================================================================================================
+constexpr int kWgUnits = 12;
+constexpr int kWgStages = 6;
+constexpr int kWgSlabRows = 32;                 // samples per pipeline stage
+constexpr int kWgSlabBytes = kWgSlabRows * 128; // one atom's slab: 4 KB
+constexpr int kWgStageBytes = 8 * kWgSlabBytes; // 4 A slabs + 4 B slabs = 32 KB
+constexpr int kWgThreads = 192;
+constexpr int WG_BAR = kWgStages * kWgStageBytes;
+constexpr int kWgSmemBytes = WG_BAR + 256 + 1024;
+
+struct WgUnit {
+  int d_atom;      // first atom of dpre inside the dstash tile
+  int m_out;       // 256 | 128 output features
+  int in_atom;     // first atom of the layer input inside the forward stash tile
+  int n_in;        // 256 | 64 (padded) input features
+  int n_valid;     // real input features (<= n_in)
+  int w_off;       // float offset of dW[0][0] in the flat gradient
+  int ld;          // row stride of dW
+  int b_off;       // float offset of the bias gradient, -1 if another unit owns it
+  int cost;        // relative tensor work per tile (1/8 of a 256x256x128 GEMM)
+};
+struct WgTable { WgUnit u[kWgUnits]; int total_cost; };
+
+static WgTable build_wg_table() {
+  WgTable t;
+  ParamOffsets po = param_offsets();
+  auto W = [&](int i) { return (int)po.off[2 * i]; };
+  auto B = [&](int i) { return (int)po.off[2 * i + 1]; };
+  auto DH = [&](int i) { return DA_H7 + 4 * (7 - i); };
+  auto H = [&](int i) { return SA_H0 + 4 * i; };
+  int n = 0;
+  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 2};
+  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, H(i - 1), 256, 256, W(i), kW, B(i), 8};
+  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 2};
+  t.u[n++] = WgUnit{DH(5), 256, H(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 8};
+  t.u[n++] = WgUnit{DH(6), 256, H(5), 256, 256, W(6), kW, B(6), 8};
+  t.u[n++] = WgUnit{DH(7), 256, H(6), 256, 256, W(7), kW, B(7), 8};
+  t.u[n++] = WgUnit{DA_FEAT, 256, H(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 8};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 4};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 1};
+  t.total_cost = 0;
+  for (int i = 0; i < kWgUnits; ++i) t.total_cost += t.u[i].cost;
+  return t;
+}
+
+struct WgradParams {
+  const uint8_t* stash;
+  const uint8_t* dstash;
+  float* grads;
+  int64_t tiles;      // number of 128-sample tiles that hold real samples
+  WgTable tab;
+};
+
+__device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = sbase + WG_BAR, bar_empty = bar_full + 8 * kWgStages;
+  const uint32_t bar_acc_full = bar_empty + 8 * kWgStages, bar_acc_empty = bar_acc_full + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + WG_BAR + 192);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + 128); }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // this CTA's share of the (unit, tile) work list, balanced by tensor cost
+  const int64_t T = p.tiles;
+  const int64_t total = (int64_t)p.tab.total_cost * T;
+  const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+
+  uint32_t stage = 0, phase = 0;          // ring position: every role walks the same sequence
+  uint32_t seg_phase = 0;
+  int64_t ustart = 0;
+  for (int ui = 0; ui < kWgUnits; ++ui) {
+    const WgUnit u = p.tab.u[ui];
+    const int64_t uend = ustart + (int64_t)u.cost * T;
+    const int64_t a = lo > ustart ? lo : ustart, b = hi < uend ? hi : uend;
+    int64_t t0 = 0, t1 = 0;
+    if (a < b) { t0 = ceil_div64(a - ustart, u.cost); t1 = ceil_div64(b - ustart, u.cost); if (t1 > T) t1 = T; }
+    ustart = uend;
+    if (t0 >= t1) continue;
+    const int a_atoms = u.m_out / 64, b_atoms = u.n_in / 64;
+    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * kWgSlabBytes;
+    const int64_t nslabs = (t1 - t0) * (kTileM / kWgSlabRows);
+
+    if (warp == 0) {
+      if (lane == 0) {   // ---- producer: 32-sample slabs of dpre (A) and layer input (B)
+        for (int64_t sl = 0; sl < nslabs; ++sl) {
+          const int64_t tile = t0 + sl / 4;
+          const int j = (int)(sl % 4);
+          const uint8_t* dsrc = p.dstash + (size_t)tile * kDstashTileBytes + (size_t)u.d_atom * kAtomBytes + j * kWgSlabBytes;
+          const uint8_t* isrc = p.stash + (size_t)tile * kStashTileBytes + (size_t)u.in_atom * kAtomBytes + j * kWgSlabBytes;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+          const uint32_t dstA = sbase + stage * kWgStageBytes, dstB = dstA + 4 * kWgSlabBytes;
+          for (int at = 0; at < a_atoms; ++at)
+            bulk_g2s(dstA + at * kWgSlabBytes, dsrc + (size_t)at * kAtomBytes, kWgSlabBytes, bar_full + 8 * stage);
+          for (int at = 0; at < b_atoms; ++at)
+            bulk_g2s(dstB + at * kWgSlabBytes, isrc + (size_t)at * kAtomBytes, kWgSlabBytes, bar_full + 8 * stage);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        for (int64_t sl = 0; sl < nslabs; ++sl) if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {   // ---- MMA issuer: D[out, in] += dpre^T[out, k] . in[k, in],  k = sample
+        const uint32_t idesc = make_idesc(128, u.n_in, 1, 1);
+        mbar_wait(bar_acc_empty, seg_phase ^ 1);     // previous segment's accumulators flushed
+        tcgen05_fence_after_sync();
+        uint32_t accumulate = 0;
+        for (int64_t sl = 0; sl < nslabs; ++sl) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after_sync();
+          const uint32_t aA = sbase + stage * kWgStageBytes, aB = aA + 4 * kWgSlabBytes;
+          for (int k = 0; k < kWgSlabRows / 16; ++k) {
+            const uint64_t b_desc = make_smem_desc(aB + k * 2048, kWgSlabBytes, 1024);
+            for (int h = 0; h < u.m_out / 128; ++h) {
+              const uint64_t a_desc = make_smem_desc(aA + h * 2 * kWgSlabBytes + k * 2048, kWgSlabBytes, 1024);
+              umma_bf16(tmem_base + (uint32_t)h * 256u, a_desc, b_desc, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_acc_full);
+      } else {
+        for (int64_t sl = 0; sl < nslabs; ++sl) if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      // ---- column sums (bias gradient) from the dpre slabs, then the accumulator flush
+      const int tid = threadIdx.x - 64;           // 0..127 : output-feature pair (2*tid, 2*tid+1)
+      const int q = warp & 3;
+      float bs0 = 0.f, bs1 = 0.f;
+      const bool do_bias = u.b_off >= 0 && 2 * tid < u.m_out;
+      const int c = 2 * tid;
+      for (int64_t sl = 0; sl < nslabs; ++sl) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        if (do_bias) {
+          const uint8_t* A = smem + stage * kWgStageBytes + (c / 64) * kWgSlabBytes + (c % 8) * 2;
+          const uint32_t c16 = (uint32_t)(c % 64) / 8;
+#pragma unroll 8
+          for (int rr = 0; rr < kWgSlabRows; ++rr) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(A + sw128_off(rr, c16));
+            bs0 += __uint_as_float(w << 16);
+            bs1 += __uint_as_float(w & 0xffff0000u);
+          }
+        }
+        mbar_arrive(bar_empty + 8 * stage);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      if (do_bias) { atomicAdd(p.grads + u.b_off + c, bs0); atomicAdd(p.grads + u.b_off + c + 1, bs1); }
+      mbar_wait(bar_acc_full, seg_phase);
+      tcgen05_fence_after_sync();
+      for (int h = 0; h < u.m_out / 128; ++h) {
+        const int out = h * 128 + q * 32 + lane;
+        float* grow = p.grads + u.w_off + (int64_t)out * u.ld;
+        for (int cb = 0; cb < u.n_in / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 256u + cb * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cb * 32 + j < u.n_valid) atomicAdd(grow + cb * 32 + j, __uint_as_float(v[j]));
+        }
+      }
+      tcgen05_fence_before_sync();
+      mbar_arrive(bar_acc_empty);
+    }
+    seg_phase ^= 1;
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// rgb / sigma heads: dWr[3,128] += d_rgb^T hv,  dbr,  dWa[256] += d_sigma h7,  dba
+// =====================================================================================================
+__global__ void __launch_bounds__(256) mlp_heads_wgrad_kernel(const uint8_t* __restrict__ stash,
+                                                              const float* __restrict__ d_raw, int64_t m,
+                                                              int64_t tiles, float* __restrict__ g_wr,
+                                                              float* __restrict__ g_br, float* __restrict__ g_wa,
+                                                              float* __restrict__ g_ba) {
+  __shared__ float4 s_d[kTileM];
+  const int tid = threadIdx.x;
+  // threads 0..127: column pair of h7 (256 wide); threads 128..191: column pair of hv (128 wide)
+  float a0 = 0.f, a1 = 0.f, r0[3] = {0, 0, 0}, r1[3] = {0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __syncthreads();
+    if (tid < kTileM) {
+      const int64_t row = tile * kTileM + tid;
+      s_d[tid] = row < m ? *reinterpret_cast<const float4*>(d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const uint8_t* st = stash + (size_t)tile * kStashTileBytes;
+    if (tid < 128) {
+      const int c = 2 * tid;
+      const uint8_t* base = st + (size_t)(SA_H0 + 28 + c / 64) * kAtomBytes + (c % 8) * 2;
+      const uint32_t c16 = (uint32_t)(c % 64) / 8;
+#pragma unroll 4
+      for (int rr = 0; rr < kTileM; ++rr) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + sw128_off(rr, c16)));
+        const float da = s_d[rr].w;
+        a0 = fmaf(da, __uint_as_float(w << 16), a0);
+        a1 = fmaf(da, __uint_as_float(w & 0xffff0000u), a1);
+      }
+    } else if (tid < 192) {
+      const int c = 2 * (tid - 128);
+      const uint8_t* base = st + (size_t)(SA_HV + c / 64) * kAtomBytes + (c % 8) * 2;
+      const uint32_t c16 = (uint32_t)(c % 64) / 8;
+#pragma unroll 4
+      for (int rr = 0; rr < kTileM; ++rr) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + sw128_off(rr, c16)));
+        const float h0 = __uint_as_float(w << 16), h1 = __uint_as_float(w & 0xffff0000u);
+        const float4 d = s_d[rr];
+        r0[0] = fmaf(d.x, h0, r0[0]); r0[1] = fmaf(d.y, h0, r0[1]); r0[2] = fmaf(d.z, h0, r0[2]);
+        r1[0] = fmaf(d.x, h1, r1[0]); r1[1] = fmaf(d.y, h1, r1[1]); r1[2] = fmaf(d.z, h1, r1[2]);
+      }
+    } else if (tid == 192) {
+      for (int rr = 0; rr < kTileM; ++rr) { const float4 d = s_d[rr]; sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
+    }
+  }
+  if (tid < 128) {
+    atomicAdd(g_wa + 2 * tid, a0); atomicAdd(g_wa + 2 * tid + 1, a1);
+  } else if (tid < 192) {
+    const int c = 2 * (tid - 128);
+    for (int k = 0; k < 3; ++k) { atomicAdd(g_wr + k * kWV + c, r0[k]); atomicAdd(g_wr + k * kWV + c + 1, r1[k]); }
+  } else if (tid == 192) {
+    atomicAdd(g_br, sb[0]); atomicAdd(g_br + 1, sb[1]); atomicAdd(g_br + 2, sb[2]); atomicAdd(g_ba, sb[3]);
+  }
+}
+
+// =====================================================================================================
+int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_t m, float* grads, void* ws,
+               cudaStream_t st) {
+  int rc = check_arch_bwd();
+  if (rc != SPN_OK) return rc;
+  SPN_CHECK_ARG(ws, "spn_mlp_bwd: BF16 mode needs a workspace of spn_mlp_bwd_workspace_bytes(m)");
+  SPN_CHECK_ARG((((uintptr_t)packed | (uintptr_t)stash | (uintptr_t)ws | (uintptr_t)d_raw) & 15) == 0,
+                "spn_mlp_bwd: buffers must be 16-byte aligned");
+  static const WgTable wg_tab = build_wg_table();
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SPN_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  const int64_t tiles = (m + kTileM - 1) / kTileM;
+  ParamOffsets po = param_offsets();
+  // 1. dgrad chain
+  DgradParams dp;
+  dp.packed = (const uint8_t*)packed; dp.stash = (const uint8_t*)stash; dp.d_raw = d_raw;
+  dp.dstash = (uint8_t*)ws; dp.m = m; dp.num_pairs = (int)((tiles + 1) / 2);
+  int grid = dp.num_pairs < sm_count() ? dp.num_pairs : sm_count();
+  prof_begin(PROF_MLP_DGRAD, st);
+  mlp_dgrad_kernel<<<grid, kThreads, kSmemBytes, st>>>(dp);
+  prof_end(PROF_MLP_DGRAD, st);
+  SPN_LAUNCH_CHECK("mlp_dgrad_kernel");
+  // 2. weight / bias gradients of the ten wide layers
+  WgradParams wp;
+  wp.stash = (const uint8_t*)stash; wp.dstash = (const uint8_t*)ws; wp.grads = grads; wp.tiles = tiles; wp.tab = wg_tab;
+  int64_t want = (int64_t)wg_tab.total_cost * tiles / 16;     // at least ~2 big tile-GEMMs of work per CTA
+  int wgrid = (int)(want < 1 ? 1 : (want < sm_count() ? want : sm_count()));
+  prof_begin(PROF_MLP_WGRAD, st);
+  mlp_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemBytes, st>>>(wp);
+  prof_end(PROF_MLP_WGRAD, st);
+  SPN_LAUNCH_CHECK("mlp_wgrad_kernel");
+  // 3. heads
+  int hgrid = (int)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
+  mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, d_raw, m, tiles, grads + po.off[T_WR],
+                                                grads + po.off[T_BR], grads + po.off[T_WA], grads + po.off[T_BA]);
+  SPN_LAUNCH_CHECK("mlp_heads_wgrad_kernel");
+  return SPN_OK;
+}
+
+}  // namespace spn

@@ -26,44 +26,88 @@ def _flags(lindisp, white_bkgd, detach_weights, perturb, need_alpha):
             (L.F_NEED_ALPHA if need_alpha else 0))
 
 
+_GRAD_NAMES = (("g_rgb", "rgb_map"), ("g_disp", "disp_map"), ("g_acc", "acc_map"), ("g_depth", "depth_map"),
+               ("g_weights", "weights"), ("g_rgb0", "rgb0"), ("g_disp0", "disp0"), ("g_acc0", "acc0"))
+
+
+def _bind_io(keep, net_c, net_f):
+    flat_c, packed_c = net_c._sync()
+    flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
+    io = L.RenderIO()
+    for k, v in keep.items():
+        setattr(io, k, ptr(v))
+    io.params_coarse, io.packed_coarse = ptr(flat_c), ptr(packed_c)
+    io.params_fine, io.packed_fine = ptr(flat_f), ptr(packed_f)
+    return io, (flat_c, packed_c, flat_f, packed_f)
+
+
+def chunk_forward(opts, rays, net_c, net_f, t_rand=None, u=None, noise0=None, noise1=None, train=False, pool=None):
+    """spn_render_rays_fwd on one ray chunk.  Returns (cfg, keep): `keep` holds every output / saved buffer
+    by its spn_render_io field name.  `pool(name, shape, dtype)` may supply reusable buffers."""
+    rays = f32(rays)
+    n, ncols = rays.shape
+    S, NI = opts["N_samples"], opts["N_importance"]
+    S2 = S + NI
+    prec = net_c.precision
+    dev = rays.device
+    if pool is None:
+        E = lambda name, *sh: torch.empty(sh, device=dev, dtype=torch.float32)
+        stash = lambda name, m: ops.mlp_stash(m, prec, dev)
+    else:
+        E = lambda name, *sh: pool(name, sh, torch.float32)
+        stash = lambda name, m: pool(name, (int(lib().spn_mlp_stash_bytes(int(m), int(prec))),), torch.uint8)
+    cfg = L.RenderCfg(n, ncols, S, NI, _flags(opts["lindisp"], opts["white_bkgd"], opts["detach_weights"],
+                                             opts["perturb"], opts["need_alpha"]), prec, float(opts["raw_noise_std"]))
+    keep = dict(rays=rays, t_rand=t_rand, u=u, noise0=noise0, noise1=noise1,
+                rgb_map=E("rgb_map", n, 3), disp_map=E("disp_map", n), acc_map=E("acc_map", n),
+                depth_map=E("depth_map", n), weights=E("weights", n, S2), z_vals=E("z_vals", n, S2),
+                raw=E("raw", n, S2, 4))
+    if NI > 0:
+        keep.update(rgb0=E("rgb0", n, 3), disp0=E("disp0", n), acc0=E("acc0", n), z_std=E("z_std", n),
+                    z_coarse=E("z_coarse", n, S), raw_coarse=E("raw_coarse", n, S, 4))
+    if opts["need_alpha"]:
+        keep.update(alpha=E("alpha", n, S2), alpha0=E("alpha0", n, S))
+    if train or prec == L.PREC_FP32:          # fp32 mode materialises activations even for inference
+        keep["stash_coarse"] = stash("stash_coarse", n * S)
+        if NI > 0:
+            keep["stash_fine"] = stash("stash_fine", n * S2)
+    io, hold = _bind_io(keep, net_c, net_f)
+    check(lib().spn_render_rays_fwd(C.byref(cfg), C.byref(io), stream()), "spn_render_rays_fwd")
+    return cfg, keep
+
+
+def chunk_backward(cfg, keep, net_c, net_f, g, gc, gf, scratch=None, ws=None):
+    """spn_render_rays_bwd: accumulates d(loss)/d(params) into the flat buffers gc / gf.
+    g: dict output-name -> upstream gradient tensor (missing = zero)."""
+    dev = keep["rays"].device
+    n, S2 = cfg.n_rays, cfg.n_samples + cfg.n_importance
+    io, hold = _bind_io(keep, net_c, net_f)
+    gr = L.RenderGrads()
+    live = []
+    for cname, k in _GRAD_NAMES:
+        t = g.get(k)
+        if t is not None:
+            t = f32(t); live.append(t)
+            setattr(gr, cname, ptr(t))
+    if scratch is None:
+        scratch = torch.empty(n * S2 * 4, device=dev)
+    if ws is None:
+        ws = ops.mlp_bwd_workspace(n * S2, cfg.precision, dev)
+    gr.grads_coarse, gr.grads_fine = ptr(gc), ptr(gf)
+    gr.d_raw_scratch, gr.workspace = ptr(scratch), ptr(ws)
+    check(lib().spn_render_rays_bwd(C.byref(cfg), C.byref(io), C.byref(gr), stream()), "spn_render_rays_bwd")
+
+
 class RenderChunk(torch.autograd.Function):
     """One ray chunk through spn_render_rays_fwd; backward = spn_render_rays_bwd into flat grads."""
 
     @staticmethod
     def forward(ctx, opts, rays, net_c, net_f, t_rand, u, noise0, noise1, *params):
-        rays = f32(rays)
-        n, ncols = rays.shape
-        S, NI = opts["N_samples"], opts["N_importance"]
-        S2 = S + NI
-        prec = net_c.precision
-        dev = rays.device
-        E = lambda *sh: torch.empty(sh, device=dev, dtype=torch.float32)
         train = opts["train"]       # decided by the caller: grad mode is off inside Function.forward
-        flat_c, packed_c = net_c._sync()
-        flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
-        cfg = L.RenderCfg(n, ncols, S, NI, _flags(opts["lindisp"], opts["white_bkgd"], opts["detach_weights"],
-                                                 opts["perturb"], opts["need_alpha"]), prec, float(opts["raw_noise_std"]))
-        io = L.RenderIO()
-        keep = dict(rays=rays, t_rand=t_rand, u=u, noise0=noise0, noise1=noise1,
-                    rgb_map=E(n, 3), disp_map=E(n), acc_map=E(n), depth_map=E(n), weights=E(n, S2), z_vals=E(n, S2),
-                    raw=E(n, S2, 4))
-        if NI > 0:
-            keep.update(rgb0=E(n, 3), disp0=E(n), acc0=E(n), z_std=E(n), z_coarse=E(n, S), raw_coarse=E(n, S, 4))
-        if opts["need_alpha"]:
-            keep.update(alpha=E(n, S2), alpha0=E(n, S))
-        need_stash = train or prec == L.PREC_FP32
-        if need_stash:
-            keep["stash_coarse"] = ops.mlp_stash(n * S, prec, dev)
-            if NI > 0:
-                keep["stash_fine"] = ops.mlp_stash(n * S2, prec, dev)
-        for k, v in keep.items():
-            setattr(io, k, ptr(v))
-        io.params_coarse, io.packed_coarse = ptr(flat_c), ptr(packed_c)
-        io.params_fine, io.packed_fine = ptr(flat_f), ptr(packed_f)
-        check(lib().spn_render_rays_fwd(C.byref(cfg), C.byref(io), stream()), "spn_render_rays_fwd")
+        cfg, keep = chunk_forward(opts, rays, net_c, net_f, t_rand, u, noise0, noise1, train)
         ctx.state = (cfg, keep, net_c, net_f, train)
         names = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "raw"]
-        if NI > 0:
+        if opts["N_importance"] > 0:
             names += ["rgb0", "disp0", "acc0", "z_std"]
         if opts["need_alpha"]:
             names += ["alpha", "alpha0"]
@@ -77,31 +121,10 @@ class RenderChunk(torch.autograd.Function):
         cfg, keep, net_c, net_f, train = ctx.state
         if not train:
             raise RuntimeError("RenderChunk.backward without a training forward")
-        g = dict(zip(ctx.names, gouts))
         dev = keep["rays"].device
-        n, S, NI = cfg.n_rays, cfg.n_samples, cfg.n_importance
-        flat_c, packed_c = net_c._sync()
-        flat_f, packed_f = (net_f._sync() if net_f is not None else (None, None))
-        io = L.RenderIO()
-        for k, v in keep.items():
-            setattr(io, k, ptr(v))
-        io.params_coarse, io.packed_coarse = ptr(flat_c), ptr(packed_c)
-        io.params_fine, io.packed_fine = ptr(flat_f), ptr(packed_f)
         gc = torch.zeros(L.MLP_NPARAMS, device=dev)
         gf = torch.zeros(L.MLP_NPARAMS, device=dev) if net_f is not None else None
-        gr = L.RenderGrads()
-        hold = []
-        for cname, k in (("g_rgb", "rgb_map"), ("g_disp", "disp_map"), ("g_acc", "acc_map"), ("g_depth", "depth_map"),
-                         ("g_weights", "weights"), ("g_rgb0", "rgb0"), ("g_disp0", "disp0"), ("g_acc0", "acc0")):
-            t = g.get(k)
-            if t is not None:
-                t = f32(t); hold.append(t)
-                setattr(gr, cname, ptr(t))
-        scratch = torch.empty(n * (S + NI) * 4, device=dev)
-        ws = ops.mlp_bwd_workspace(n * (S + NI), cfg.precision, dev)
-        gr.grads_coarse, gr.grads_fine = ptr(gc), ptr(gf)
-        gr.d_raw_scratch, gr.workspace = ptr(scratch), ptr(ws)
-        check(lib().spn_render_rays_bwd(C.byref(cfg), C.byref(io), C.byref(gr), stream()), "spn_render_rays_bwd")
+        chunk_backward(cfg, keep, net_c, net_f, dict(zip(ctx.names, gouts)), gc, gf)
         ctx.state = None
         grads = [gc[o:o + p.numel()].view(p.shape) for o, p in zip(net_c._offsets, net_c._flat_params())]
         if net_f is not None:

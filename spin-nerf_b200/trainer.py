@@ -1,0 +1,151 @@
+"""Fused train step of the SPIn-NeRF hot path (DS_NeRF/run_nerf.py:1455-1521, 1611-1622) without autograd:
+three render calls (unmasked rays -> rgb loss; masked rays of the kept view -> rgb loss with detached
+weights; inpainted-disparity rays -> disparity loss), analytic loss gradients, backward through the fused
+CUDA chunk pipeline into ONE flat fp32 gradient vector per network, optional NCCL all-reduce of that
+vector (rays are sharded across ranks), one flat Adam launch per network.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .render import chunk_backward, chunk_forward
+
+
+class RaySharder:
+    """Contiguous ray shards per rank: rank r gets rays [r*n/W, (r+1)*n/W) of every batch (equal shards when
+    W divides n, so mean-of-means == global mean for the MSE losses; otherwise gradients are weighted by
+    the shard's share of the batch)."""
+
+    def __init__(self, rank=0, world=1):
+        self.rank, self.world = int(rank), int(world)
+
+    def bounds(self, n):
+        return (n * self.rank) // self.world, (n * (self.rank + 1)) // self.world
+
+    def shard(self, t, dim=0):
+        lo, hi = self.bounds(t.shape[dim])
+        return t.narrow(dim, lo, hi - lo)
+
+
+class BufferPool:
+    """Reusable device buffers keyed by name (stash / outputs of the step's render calls): the train loop
+    allocates once and launches kernels only."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def __call__(self, name, shape, dtype):
+        need = 1
+        for s in shape:
+            need *= int(s)
+        b = self.bufs.get(name)
+        if b is None or b.numel() < need or b.dtype != dtype:
+            b = torch.empty(max(need, 1), device=self.device, dtype=dtype)
+            self.bufs[name] = b
+        return b[:need].view(*shape) if need else b[:0].view(*shape)
+
+
+class Trainer:
+    def __init__(self, net_c, net_f, lr=5e-4, lrate_decay=250, N_samples=64, N_importance=64, lindisp=True,
+                 white_bkgd=True, perturb=1.0, raw_noise_std=1.0, near=1.2, far=8.0, ndc=False, hwf=None,
+                 process_group=None, sharder=None, betas=(0.9, 0.999), eps=1e-8):
+        self.net_c, self.net_f = net_c, net_f
+        self.lr0, self.lrate_decay = float(lr), lrate_decay
+        self.betas, self.eps = betas, eps
+        self.cfg = dict(N_samples=int(N_samples), N_importance=int(N_importance), lindisp=bool(lindisp),
+                        white_bkgd=bool(white_bkgd), perturb=perturb > 0, need_alpha=False,
+                        raw_noise_std=float(raw_noise_std))
+        self.near, self.far, self.ndc, self.hwf = float(near), float(far), bool(ndc), hwf
+        self.pg = process_group
+        self.sharder = sharder or RaySharder()
+        dev = net_c.flat_params().device
+        self.device = dev
+        z = lambda: torch.zeros(L.MLP_NPARAMS, device=dev)
+        self.grads = [z(), z()]
+        self.m = [z(), z()]
+        self.v = [z(), z()]
+        self.global_step = 0
+        self.pools = [BufferPool(dev)] * 3      # each render is consumed (backward) before the next starts
+        self.shared = BufferPool(dev)
+
+    # ---------------------------------------------------------------------------------------
+    def _forward(self, idx, rays_od, detach_weights):
+        """rays_od [2,n,3] (origin, direction) -> chunk state; random draws made on the device."""
+        o, d = rays_od[0], rays_od[1]
+        H, W, f = self.hwf if self.hwf is not None else (0, 0, 1.0)
+        rb = ops.build_ray_batch(o, d, self.near, self.far, self.ndc, H, W, f)
+        n = rb.shape[0]
+        S, NI = self.cfg["N_samples"], self.cfg["N_importance"]
+        opts = dict(self.cfg, detach_weights=detach_weights)
+        t_rand = u = n0 = n1 = None
+        if opts["perturb"]:
+            t_rand = torch.rand(n, S, device=self.device)
+            u = torch.rand(n, NI, device=self.device) if NI else None
+        if opts["raw_noise_std"] > 0:
+            n0 = torch.randn(n, S, device=self.device)
+            n1 = torch.randn(n, S + NI, device=self.device) if NI else None
+        return chunk_forward(opts, rb, self.net_c, self.net_f, t_rand, u, n0, n1, train=True, pool=self.pools[idx])
+
+    def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
+        """One optimisation step on this rank's shard of the three ray batches.  Returns the (local) loss and
+        psnr like run_nerf.py:1481-1521 defines them for the default flags."""
+        sh = self.sharder
+        rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
+        rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
+        rays_inp, depth_inp = sh.shard(rays_inp, 1), sh.shard(depth_inp)
+        for g in self.grads:
+            g.zero_()
+        gc, gf = self.grads
+        mse_g = lambda x, t: (2.0 / x.numel()) * (x - t)
+        losses = []
+        # 1) unmasked rays: rgb + rgb0 vs target (run_nerf.py:1455, 1481, 1511-1513)
+        cfg, k = self._forward(0, rays_clf, False)
+        losses += [torch.mean((k["rgb_map"] - target_clf) ** 2), torch.mean((k["rgb0"] - target_clf) ** 2)]
+        chunk_backward(cfg, k, self.net_c, self.net_f, {"rgb_map": mse_g(k["rgb_map"], target_clf),
+                                                        "rgb0": mse_g(k["rgb0"], target_clf)}, gc, gf,
+                       self._scratch(cfg), self._ws(cfg))
+        # 2) masked rays of the kept view, weights detached (run_nerf.py:1465, 1484-1489)
+        cfg, k = self._forward(1, rays_s, True)
+        losses += [torch.mean((k["rgb_map"] - target_s) ** 2), torch.mean((k["rgb0"] - target_s) ** 2)]
+        chunk_backward(cfg, k, self.net_c, self.net_f, {"rgb_map": mse_g(k["rgb_map"], target_s),
+                                                        "rgb0": mse_g(k["rgb0"], target_s)}, gc, gf,
+                       self._scratch(cfg), self._ws(cfg))
+        # 3) inpainted-disparity rays (run_nerf.py:1470, 1516-1521)
+        cfg, k = self._forward(2, rays_inp, False)
+        losses += [torch.mean((k["disp_map"] - depth_inp) ** 2), torch.mean((k["disp0"] - depth_inp) ** 2)]
+        chunk_backward(cfg, k, self.net_c, self.net_f, {"disp_map": mse_g(k["disp_map"], depth_inp),
+                                                        "disp0": mse_g(k["disp0"], depth_inp)}, gc, gf,
+                       self._scratch(cfg), self._ws(cfg))
+        self.apply_gradients()
+        loss = sum(losses)
+        return loss, -10.0 * torch.log10(losses[0])
+
+    def _scratch(self, cfg):
+        return self.shared("d_raw", (cfg.n_rays * (cfg.n_samples + cfg.n_importance) * 4,), torch.float32)
+
+    def _ws(self, cfg):
+        nbytes = int(L.lib().spn_mlp_bwd_workspace_bytes(cfg.n_rays * (cfg.n_samples + cfg.n_importance), cfg.precision))
+        return self.shared("bwd_ws", (nbytes,), torch.uint8)
+
+    # ---------------------------------------------------------------------------------------
+    def apply_gradients(self):
+        """NCCL all-reduce (mean over ranks) of the two flat gradient vectors, then one Adam launch per network;
+        learning-rate schedule of run_nerf.py:1616-1622."""
+        scale = 1.0
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                   and self.sharder.world > 1):
+            import torch.distributed as dist
+            for g in self.grads:
+                dist.all_reduce(g, group=self.pg)
+            scale = 1.0 / self.sharder.world
+        self.global_step += 1
+        lr = self.lr0 * (0.1 ** ((self.global_step - 1) / (self.lrate_decay * 1000)))
+        for net, g, m, v in zip((self.net_c, self.net_f), self.grads, self.m, self.v):
+            if net is None:
+                continue
+            ops.adam_step(net.flat_params(), g, m, v, self.global_step, lr, self.betas, self.eps, grad_scale=scale)
+            net.mark_params_changed()

@@ -306,7 +306,8 @@ def test_tc_selftest_gemm(N_, K):
     rng = np.random.default_rng(N_ + K)
     A = rng.standard_normal((128, K)).astype(np.float32); B = rng.standard_normal((N_, K)).astype(np.float32)
     D = torch.full((128, N_), float("nan"), device=DEV)
-    spn._lib.check(spn._lib.lib().spn_tc_selftest_gemm(spn._lib.ptr(T(A)), spn._lib.ptr(T(B)), spn._lib.ptr(D), N_, K,
+    tA, tB = T(A), T(B)            # keep the device buffers alive across the call
+    spn._lib.check(spn._lib.lib().spn_tc_selftest_gemm(spn._lib.ptr(tA), spn._lib.ptr(tB), spn._lib.ptr(D), N_, K,
                                                        spn._lib.stream()), "selftest")
     torch.cuda.synchronize()
     ref = bf16r(A).astype(np.float64) @ bf16r(B).astype(np.float64).T
@@ -338,6 +339,121 @@ def test_mlp_bf16_ragged_and_multi_tile(m):
     sel = rng.choice(m, min(m, 512), replace=False)
     emu, _ = mlp_forward_bf16(p, x6[sel])
     assert np.abs(raw[sel] - emu).max() <= 3e-3 * max(1.0, np.abs(emu).max())
+
+
+def mlp_backward_bf16(p, acts, masks_from, draw):
+    """The backward kernels' arithmetic on the CPU: bf16 operands (transposed weights, d(pre-activations),
+    stashed activations), fp32 accumulation; heads use fp32 d_raw and fp32 head weights."""
+    W = lambda k: bf16r(p[k])
+    d_rgb, d_alpha = draw[:, :3], draw[:, 3:4]
+    g, dpre = {}, {}
+    hv, h7 = acts["hv"], acts["h7"]
+    g["rgb_linear.weight"] = d_rgb.T @ hv; g["rgb_linear.bias"] = d_rgb.sum(0)
+    g["alpha_linear.weight"] = d_alpha.T @ h7; g["alpha_linear.bias"] = d_alpha.sum(0)
+    d_hv = bf16r((d_rgb @ p["rgb_linear.weight"]) * (masks_from["hv"] > 0)); dpre["hv"] = d_hv
+    wv = W("views_linears.0.weight")
+    g["views_linears.0.weight"] = np.concatenate([d_hv.T @ acts["feat"], d_hv.T @ acts["xd"]], 1)
+    g["views_linears.0.bias"] = d_hv.sum(0)
+    d_feat = bf16r(d_hv @ wv[:, :256]); dpre["feat"] = d_feat
+    g["feature_linear.weight"] = d_feat.T @ h7; g["feature_linear.bias"] = d_feat.sum(0)
+    d = bf16r((d_feat @ W("feature_linear.weight") + d_alpha * p["alpha_linear.weight"]) * (masks_from["h7"] > 0))
+    for i in range(7, -1, -1):
+        dpre[f"h{i}"] = d
+        inp = acts["xp"] if i == 0 else (np.concatenate([acts["xp"], acts["h4"]], 1) if i == 5 else acts[f"h{i-1}"])
+        g[f"pts_linears.{i}.weight"] = d.T @ inp
+        g[f"pts_linears.{i}.bias"] = d.sum(0)
+        if i > 0:
+            w = W(f"pts_linears.{i}.weight")
+            w = w[:, 63:] if i == 5 else w
+            d = bf16r((d @ w) * (masks_from[f"h{i-1}"] > 0))
+    return {k: v.astype(np.float32) for k, v in g.items()}, dpre
+
+
+def decode_tiles(buf, tile_bytes, atom0, natoms, ntiles, rows):
+    """bf16 SWIZZLE_128B tile images -> float32 [rows, 64*natoms] (spin-nerf_b200/csrc/mlp_tc.cuh layouts)."""
+    raw = N(buf[:ntiles * tile_bytes]).reshape(ntiles, tile_bytes)
+    out = np.zeros((ntiles * 128, 64 * natoms), np.float32)
+    r = np.arange(128)
+    for t in range(ntiles):
+        for a in range(natoms):
+            atom = raw[t, (atom0 + a) * 16384:(atom0 + a + 1) * 16384].reshape(128, 8, 16)
+            for j in range(8):
+                chunk = atom[r, j ^ (r & 7)]                                # [128,16] bytes
+                vals = chunk.copy().view(np.uint16).astype(np.uint32) << 16
+                out[t * 128:(t + 1) * 128, a * 64 + j * 8:a * 64 + j * 8 + 8] = vals.view(np.float32)
+    return out[:rows]
+
+
+@pytest.mark.parametrize("m", [192, 1000])
+def test_mlp_bf16_backward(m):
+    net, p = make_net(11, spn.PREC_BF16)
+    rng = np.random.default_rng(m)
+    if m == 192:
+        g, x90, x6 = _mlp_case(); draw = g["draw"]
+    else:
+        x6 = np.concatenate([rng.standard_normal((m, 3)) * 2, rng.standard_normal((m, 3))], -1).astype(np.float32)
+        x6[:, 3:] /= np.linalg.norm(x6[:, 3:], axis=1, keepdims=True)
+        draw = rng.standard_normal((m, 4)).astype(np.float32)
+    flat, packed = net._sync()
+    stash = ops.mlp_stash(m, spn.PREC_BF16, DEV); stash.zero_()
+    raw, _ = ops.mlp_forward_points(flat, packed, T(x6), spn.PREC_BF16, stash)
+    ws = ops.mlp_bwd_workspace(m, spn.PREC_BF16, DEV); ws.zero_()
+    grads = torch.zeros(spn.MLP_NPARAMS, device=DEV)
+    ops.mlp_backward(flat, packed, stash, T(draw), grads, spn.PREC_BF16, workspace=ws)
+    torch.cuda.synchronize()
+    emu_raw, acts = mlp_forward_bf16(p, x6)
+    ntiles = (m + 127) // 128
+    SB, DB = 692224, 622592
+    # forward stash == emulated activations (bf16 exact up to accumulation-order flips of the last bit)
+    h3 = decode_tiles(stash, SB, 1 + 4 * 3, 4, ntiles, m)
+    assert np.abs(h3 - acts["h3"]).max() <= 2e-2 * max(1.0, np.abs(acts["h3"]).max())
+    gpu_acts = {"xp": decode_tiles(stash, SB, 0, 1, ntiles, m)[:, :63], "xd": decode_tiles(stash, SB, 39, 1, ntiles, m)[:, :27],
+                "feat": decode_tiles(stash, SB, 33, 4, ntiles, m), "hv": decode_tiles(stash, SB, 37, 2, ntiles, m)}
+    for i in range(8):
+        gpu_acts[f"h{i}"] = decode_tiles(stash, SB, 1 + 4 * i, 4, ntiles, m)
+    # emulate the backward on the GPU's own stashed activations (so only the backward is under test)
+    emu_g, dpre = mlp_backward_bf16(p, gpu_acts, gpu_acts, draw)
+    d_h7 = decode_tiles(ws, DB, 6, 4, ntiles, m); d_h0 = decode_tiles(ws, DB, 34, 4, ntiles, m)
+    d_hv = decode_tiles(ws, DB, 0, 2, ntiles, m)
+    off = spn._lib.param_offsets()
+    names = [k for k, _ in O.PARAM_SHAPES]
+    G = {k: N(grads[off[i]:off[i + 1]]).reshape(p[k].shape) for i, k in enumerate(names)}
+    if __import__("os").path.isdir("gpurun_out"):
+        np.savez(f"gpurun_out/mlp_bwd_dbg_{m}.npz", d_h7=d_h7, d_h0=d_h0, d_hv=d_hv, e_h7=dpre["h7"], e_h0=dpre["h0"],
+                 e_hv=dpre["hv"], **{"G_" + k: v for k, v in G.items()}, **{"E_" + k: v for k, v in emu_g.items()})
+    for got, want in ((d_hv, dpre["hv"]), (d_h7, dpre["h7"]), (d_h0, dpre["h0"])):
+        assert np.abs(got - want).max() <= 2e-2 * max(1e-6, np.abs(want).max()), np.abs(got - want).max()
+    for k in names:
+        scale = max(1e-6, np.abs(emu_g[k]).max())
+        assert np.abs(G[k] - emu_g[k]).max() <= 2e-2 * scale, (k, np.abs(G[k] - emu_g[k]).max() / scale)
+    if m == 192:        # and against the fp32 reference autograd (golden)
+        g = load_golden("mlp")
+        for k in names:
+            ref_abs = float(g["g_abs__" + k])
+            assert abs(np.abs(G[k]).sum(dtype=np.float64) - ref_abs) <= 6e-2 * ref_abs + 1e-4, k
+            close_mostly(G[k].reshape(-1)[::97], g["g_sub__" + k], rtol=5e-2, atol=3e-2 * np.abs(G[k]).max() + 1e-6,
+                         max_frac=0.05, hard=1.0)
+
+
+def test_train_step_bf16_tracks_reference():
+    """Two Adam steps in bf16 mode: loss within 1%% of the reference's fp32 autograd run."""
+    g = load_golden("render"); tr = load_golden("train_step")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    netc, _ = make_net(11, spn.PREC_BF16, 1.0)
+    netf, _ = make_net(12, spn.PREC_BF16, 1.0)
+    opt = torch.optim.Adam(list(netc.parameters()) + list(netf.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    target, tdisp = T(tr["target"]), T(tr["tdisp"])
+    mse = lambda a, b: torch.mean((a - b) ** 2)
+    for it in range(2):
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=32768, rays=T(g["rays"]), retraw=True, use_viewdirs=True,
+                                               network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64,
+                                               N_importance=64, ndc=False, lindisp=True, white_bkgd=True, perturb=0.,
+                                               raw_noise_std=0., near=1.2, far=8.0)
+        opt.zero_grad()
+        loss = mse(rgb, target) + mse(ex["rgb0"], target) + mse(disp, tdisp) + mse(ex["disp0"], tdisp)
+        loss.backward()
+        assert abs(loss.item() - float(tr[f"loss{it}"])) <= 1e-2 * abs(float(tr[f"loss{it}"])), (it, loss.item())
+        opt.step()
 
 
 def test_render_bf16_psnr_vs_reference():
