@@ -150,12 +150,12 @@ def workload_config(n_gpus, n_rand):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n_rand", type=int, default=1024)
     ap.add_argument("--precision", default="bf16")
-    ap.add_argument("--cpu_rays", type=int, default=64, help="rays per render call in the CPU sample")
+    ap.add_argument("--cpu_rays", type=int, default=128, help="rays per render call in the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -219,11 +219,12 @@ def main():
         return [a.elapsed_time(b) for a, b in evs], loss
 
     barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    clocks = ClockSampler(local); clocks.start()         # nvidia-smi needs ~1 s to start streaming samples
     run_steps(args.warmup, device_batches, False)
     barrier(); torch.cuda.synchronize()
     L = spn._lib.lib()
     L.spn_profile_enable(1); L.spn_launch_count(1)
-    clocks = ClockSampler(local); clocks.start()
+    clocks.rows.clear()                                   # keep only samples taken during the timed region
     t_wall = time.perf_counter()
     times, loss = run_steps(args.steps, device_batches, True)
     torch.cuda.synchronize(); barrier()

@@ -36,7 +36,10 @@ static int check_arch_bwd() {
 }
 
 static inline int64_t even_tiles(int64_t m) { return (m + 2 * kTileM - 1) / (2 * kTileM) * 2; }
-size_t mlp_tc_bwd_ws_bytes(int64_t m) { return (size_t)even_tiles(m) * kDstashTileBytes + 256; }
+constexpr int kWgMaxCtas = 192;   // >= SM count of any sm_100 part
+size_t mlp_tc_bwd_ws_bytes(int64_t m) {
+  return (size_t)even_tiles(m) * kDstashTileBytes + (size_t)kWgMaxCtas * 256 * 256 * sizeof(float) + 256;
+}
 
 // =====================================================================================================
 // dgrad
@@ -285,6 +288,8 @@ struct WgradParams {
   float* grads;
   int64_t tiles;      // number of 128-sample tiles that hold real samples
   WgTable tab;
+  int cta_begin[kWgUnits + 1];   // CTAs [cta_begin[u], cta_begin[u+1]) split unit u's tiles evenly
+  float* partial;                // [gridDim.x][256][256] fp32 per-CTA weight-gradient partials
 };
 
 __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -310,22 +315,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
   tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // this CTA's share of the (unit, tile) work list, balanced by tensor cost
+  // one (unit, tile range) segment per CTA: the host gave every unit a CTA count proportional to its tensor cost
   const int64_t T = p.tiles;
-  const int64_t total = (int64_t)p.tab.total_cost * T;
-  const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
-
   uint32_t stage = 0, phase = 0;          // ring position: every role walks the same sequence
   uint32_t seg_phase = 0;
-  int64_t ustart = 0;
   for (int ui = 0; ui < kWgUnits; ++ui) {
+    if ((int)blockIdx.x < p.cta_begin[ui] || (int)blockIdx.x >= p.cta_begin[ui + 1]) continue;
     const WgUnit u = p.tab.u[ui];
-    const int64_t uend = ustart + (int64_t)u.cost * T;
-    const int64_t a = lo > ustart ? lo : ustart, b = hi < uend ? hi : uend;
-    int64_t t0 = 0, t1 = 0;
-    if (a < b) { t0 = ceil_div64(a - ustart, u.cost); t1 = ceil_div64(b - ustart, u.cost); if (t1 > T) t1 = T; }
-    ustart = uend;
-    if (t0 >= t1) continue;
+    const int64_t gu = p.cta_begin[ui + 1] - p.cta_begin[ui], ju = (int)blockIdx.x - p.cta_begin[ui];
+    const int64_t t0 = T * ju / gu, t1 = T * (ju + 1) / gu;
     const int a_atoms = u.m_out / 64, b_atoms = u.n_in / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * kWgSlabBytes;
     const int64_t nslabs = (t1 - t0) * (kTileM / kWgSlabRows);
@@ -370,7 +368,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
           umma_commit(bar_empty + 8 * stage);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_acc_full);
+        if (nslabs > 0) umma_commit(bar_acc_full);
       } else {
         for (int64_t sl = 0; sl < nslabs; ++sl) if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
@@ -397,18 +395,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
       if (do_bias) { atomicAdd(p.grads + u.b_off + c, bs0); atomicAdd(p.grads + u.b_off + c + 1, bs1); }
-      mbar_wait(bar_acc_full, seg_phase);
+      if (t0 < t1) mbar_wait(bar_acc_full, seg_phase);
       tcgen05_fence_after_sync();
+      float* part = p.partial + (size_t)blockIdx.x * 256 * 256;
       for (int h = 0; h < u.m_out / 128; ++h) {
         const int out = h * 128 + q * 32 + lane;
-        float* grow = p.grads + u.w_off + (int64_t)out * u.ld;
+        float4* prow = reinterpret_cast<float4*>(part + (size_t)out * 256);
         for (int cb = 0; cb < u.n_in / 32; ++cb) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 256u + cb * 32, v);
-          tmem_ld_wait();
+          if (t0 < t1) {
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 256u + cb * 32, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb * 32 + j < u.n_valid) atomicAdd(grow + cb * 32 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)   // one full 128-byte line per thread and batch, no atomics
+            prow[cb * 8 + j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
       }
       tcgen05_fence_before_sync();
@@ -423,6 +428,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
     tcgen05_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// dW[unit] += sum over the unit's CTAs of their partials (deterministic, coalesced; replaces ~10^7 atomics/launch)
+__global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const WgradParams p) {
+  const WgUnit u = p.tab.u[blockIdx.y];
+  const int c0 = p.cta_begin[blockIdx.y], c1 = p.cta_begin[blockIdx.y + 1];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // over m_out * n_in
+  if (idx >= u.m_out * u.n_in) return;
+  const int o = idx / u.n_in, i = idx % u.n_in;
+  if (i >= u.n_valid) return;
+  float acc = 0.f;
+  for (int c = c0; c < c1; ++c) acc += p.partial[(size_t)c * 256 * 256 + (size_t)o * 256 + i];
+  p.grads[u.w_off + (int64_t)o * u.ld + i] += acc;
 }
 
 // =====================================================================================================
@@ -511,12 +529,35 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   // 2. weight / bias gradients of the ten wide layers
   WgradParams wp;
   wp.stash = (const uint8_t*)stash; wp.dstash = (const uint8_t*)ws; wp.grads = grads; wp.tiles = tiles; wp.tab = wg_tab;
-  int64_t want = (int64_t)wg_tab.total_cost * tiles / 16;     // at least ~2 big tile-GEMMs of work per CTA
-  int wgrid = (int)(want < 1 ? 1 : (want < sm_count() ? want : sm_count()));
+  // CTAs per unit proportional to tensor cost (>= 1, <= tiles); every CTA owns exactly one (unit, tile range)
+  int target = sm_count();
+  if ((int64_t)wg_tab.total_cost * tiles / 16 < target) target = (int)((int64_t)wg_tab.total_cost * tiles / 16);
+  if (target < kWgUnits) target = kWgUnits;
+  int assigned = 0;
+  wp.cta_begin[0] = 0;
+  for (int ui = 0; ui < kWgUnits; ++ui) {
+    int g = (int)((int64_t)target * wg_tab.u[ui].cost / wg_tab.total_cost);
+    if (g < 1) g = 1;
+    if (g > tiles) g = (int)tiles;
+    assigned += g;
+    wp.cta_begin[ui + 1] = assigned;
+  }
+  // hand left-over SMs to the big units
+  for (int ui = 0; assigned < sm_count() && ui < kWgUnits; ++ui) {
+    if (wg_tab.u[ui].cost < 8) continue;
+    int have = wp.cta_begin[ui + 1] - wp.cta_begin[ui];
+    if (have >= tiles) continue;
+    for (int k = ui + 1; k <= kWgUnits; ++k) wp.cta_begin[k] += 1;
+    ++assigned;
+  }
+  const int wgrid = assigned;
+  wp.partial = reinterpret_cast<float*>((uint8_t*)ws + (size_t)even_tiles(m) * kDstashTileBytes);
   prof_begin(PROF_MLP_WGRAD, st);
   mlp_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemBytes, st>>>(wp);
-  prof_end(PROF_MLP_WGRAD, st);
   SPN_LAUNCH_CHECK("mlp_wgrad_kernel");
+  mlp_wgrad_reduce_kernel<<<dim3(256, kWgUnits), 256, 0, st>>>(wp);
+  prof_end(PROF_MLP_WGRAD, st);
+  SPN_LAUNCH_CHECK("mlp_wgrad_reduce_kernel");
   // 3. heads
   int hgrid = (int)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
   mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, d_raw, m, tiles, grads + po.off[T_WR],

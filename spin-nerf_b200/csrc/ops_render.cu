@@ -273,10 +273,14 @@ raw2outputs_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__
   float gdisp = g_disp ? g_disp[ray] : 0.0f;
   float ratio = sdepth / sacc;
   // disp = 1/max(1e-10, ratio): gradient flows through ratio only where ratio wins the max
-  float gratio = (ratio > 1e-10f) ? -gdisp / (ratio * ratio) : 0.0f;
-  if (gdisp != 0.0f && ratio != ratio) gratio = ratio;   // NaN propagates like autograd
-  gdepth += gratio / sacc;
-  gacc -= gratio * sdepth / (sacc * sacc);
+  // (skipped entirely when disp carries no gradient: autograd never visits that branch, so an empty ray
+  //  (acc == 0, ratio = NaN) must not poison the other outputs' gradients)
+  if (gdisp != 0.0f) {
+    float gratio = (ratio > 1e-10f) ? -gdisp / (ratio * ratio) : 0.0f;
+    if (ratio != ratio) gratio = ratio;   // NaN propagates like autograd
+    gdepth += gratio / sacc;
+    gacc -= gratio * sdepth / (sacc * sacc);
+  }
   // reverse sweep: suffix_i = sum_{k>i} gw_k * w_k, small tail terms accumulated first
   float tail = 0.0f;
 #pragma unroll

@@ -12,23 +12,8 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .dist import RaySharder, allreduce_sum_
 from .render import chunk_backward, chunk_forward
-
-
-class RaySharder:
-    """Contiguous ray shards per rank: rank r gets rays [r*n/W, (r+1)*n/W) of every batch (equal shards when
-    W divides n, so mean-of-means == global mean for the MSE losses; otherwise gradients are weighted by
-    the shard's share of the batch)."""
-
-    def __init__(self, rank=0, world=1):
-        self.rank, self.world = int(rank), int(world)
-
-    def bounds(self, n):
-        return (n * self.rank) // self.world, (n * (self.rank + 1)) // self.world
-
-    def shard(self, t, dim=0):
-        lo, hi = self.bounds(t.shape[dim])
-        return t.narrow(dim, lo, hi - lo)
 
 
 class BufferPool:
@@ -116,9 +101,15 @@ class Trainer:
                        self._scratch(cfg), self._ws(cfg))
         # 3) inpainted-disparity rays (run_nerf.py:1470, 1516-1521)
         cfg, k = self._forward(2, rays_inp, False)
-        losses += [torch.mean((k["disp_map"] - depth_inp) ** 2), torch.mean((k["disp0"] - depth_inp) ** 2)]
-        chunk_backward(cfg, k, self.net_c, self.net_f, {"disp_map": mse_g(k["disp_map"], depth_inp),
-                                                        "disp0": mse_g(k["disp0"], depth_inp)}, gc, gf,
+        l_d, l_d0 = torch.mean((k["disp_map"] - depth_inp) ** 2), torch.mean((k["disp0"] - depth_inp) ** 2)
+        # `if not inp_loss.isnan(): loss += inp_loss` (run_nerf.py:1520) without a host sync: a NaN disparity loss
+        # (a ray with zero accumulated opacity) contributes neither loss nor gradient
+        bad = torch.isnan(l_d + l_d0)
+        zero = torch.zeros((), device=self.device)
+        losses += [torch.where(bad, zero, l_d), torch.where(bad, zero, l_d0)]
+        g_d = torch.where(bad, torch.zeros_like(depth_inp), mse_g(k["disp_map"], depth_inp))
+        g_d0 = torch.where(bad, torch.zeros_like(depth_inp), mse_g(k["disp0"], depth_inp))
+        chunk_backward(cfg, k, self.net_c, self.net_f, {"disp_map": g_d, "disp0": g_d0}, gc, gf,
                        self._scratch(cfg), self._ws(cfg))
         self.apply_gradients()
         loss = sum(losses)
@@ -135,13 +126,7 @@ class Trainer:
     def apply_gradients(self):
         """NCCL all-reduce (mean over ranks) of the two flat gradient vectors, then one Adam launch per network;
         learning-rate schedule of run_nerf.py:1616-1622."""
-        scale = 1.0
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                   and self.sharder.world > 1):
-            import torch.distributed as dist
-            for g in self.grads:
-                dist.all_reduce(g, group=self.pg)
-            scale = 1.0 / self.sharder.world
+        scale = allreduce_sum_(self.grads, self.pg) if self.sharder.world > 1 else 1.0
         self.global_step += 1
         lr = self.lr0 * (0.1 ** ((self.global_step - 1) / (self.lrate_decay * 1000)))
         for net, g, m, v in zip((self.net_c, self.net_f), self.grads, self.m, self.v):
