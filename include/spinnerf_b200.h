@@ -143,6 +143,10 @@ int spn_mlp_bwd(const float* params_flat, const void* packed, const void* stash,
  * cores) with exactly the shared-memory/TMEM conventions of the MLP kernels. N in {128,256}, K in {64,128,192,256}. */
 int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
 
+/* Diagnostic: cycles (clock64, written to cycles_dev[0]) for `reps` back-to-back tcgen05.mma M=128 x N x K=16 with
+ * K-major (0) or MN-major (1) shared-memory operands — the measurement behind DESIGN.md's wgrad layout choice. */
+int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream);
+
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */
 int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,

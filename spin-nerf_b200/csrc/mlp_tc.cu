@@ -146,6 +146,17 @@ struct FwdParams {
   int num_pairs;
 };
 
+// sin/cos for the bf16 encodings: two-constant Cody-Waite reduction to [-pi, pi] (exact product via fma) followed by
+// the SFU approximations.  |abs error| < 1e-6 for |x| < 1e4, three orders below the bf16 rounding (4e-3) that follows;
+// no local-memory slow path like sincosf's Payne-Hanek branch.  (The fp32 mode uses the accurate sinf/cosf.)
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(k, 1.7484556e-7f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
 // packs [v, sin(2^k v), cos(2^k v)]_k (helpers:28-52 order) as bf16 pairs; unused tail = 0
 template <int NFREQ, int NWORDS>
 __device__ __forceinline__ void encode_point(const float v[3], uint32_t (&out)[NWORDS]) {
@@ -158,13 +169,97 @@ __device__ __forceinline__ void encode_point(const float v[3], uint32_t (&out)[N
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       float s, c;
-      sincosf(__fmul_rn(v[a], (float)(1 << k)), &s, &c);
+      fast_sincos(__fmul_rn(v[a], (float)(1 << k)), s, c);
       vals[3 + 6 * k + a] = s;
       vals[3 + 6 * k + 3 + a] = c;
     }
   }
 #pragma unroll
   for (int i = 0; i < NWORDS; ++i) out[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
+}
+
+// gamma(v) (3 + 6*NFREQ values, zero padded to 64) as bf16 -> row r of a [128 x 64] swizzled atom in shared memory
+// (and, in training, the same image in the stash).  Dead rows (beyond m) get zeros.
+template <int NFREQ, bool kStash>
+__device__ __forceinline__ void write_encoding(const float v[3], bool live, uint8_t* act_atom, uint8_t* stash_atom, int r) {
+  constexpr int NW = NFREQ == 10 ? 32 : 16;
+  uint32_t w[NW];
+  encode_point<NFREQ, NW>(v, w);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 q4 = make_uint4(0, 0, 0, 0);
+    if (4 * j < NW && live) q4 = make_uint4(w[(4 * j) % NW], w[(4 * j + 1) % NW], w[(4 * j + 2) % NW], w[(4 * j + 3) % NW]);
+    *reinterpret_cast<uint4*>(act_atom + sw128_off(r, j)) = q4;
+    if (kStash) *reinterpret_cast<uint4*>(stash_atom + sw128_off(r, j)) = q4;
+  }
+}
+
+// one 32-column batch of a hidden layer's epilogue: h = acc + bias (ReLU), bf16, swizzled store; returns ReLU mask bits
+template <bool kTrain, bool kRelu, bool kAlpha>
+__device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, const float* __restrict__ bias,
+                                              const float* __restrict__ cst, float& alpha, uint8_t* act,
+                                              uint8_t* stash_layer, int r) {
+  uint32_t mb = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = cb * 32 + g * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    float h[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
+                  __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
+                  __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                  __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (kRelu) h[e] = fmaxf(h[e], 0.f);
+      if (kTrain) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
+    }
+    if (kAlpha) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col + 4));
+      alpha = fmaf(h[0], w0.x, fmaf(h[1], w0.y, fmaf(h[2], w0.z, fmaf(h[3], w0.w, alpha))));
+      alpha = fmaf(h[4], w1.x, fmaf(h[5], w1.y, fmaf(h[6], w1.z, fmaf(h[7], w1.w, alpha))));
+    }
+    const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
+    *reinterpret_cast<uint4*>(act + off) = v4;
+    if (kTrain) *reinterpret_cast<uint4*>(stash_layer + off) = v4;
+  }
+  return mb;
+}
+
+// one 32-column batch of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv  (fp32), hv stashed in training
+template <bool kTrain>
+__device__ __forceinline__ uint32_t epi_final_batch(const uint32_t (&v)[32], int cb, const float* __restrict__ bias,
+                                                    const float* __restrict__ cst, float (&rgb)[3], uint8_t* stash_tile,
+                                                    int r) {
+  uint32_t mb = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = cb * 32 + g * 8;
+    float h[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + e));
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + col + e));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 128 + col + e));
+      const float4 r2 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 256 + col + e));
+      h[e + 0] = fmaxf(__uint_as_float(v[g * 8 + e + 0]) + b4.x, 0.f);
+      h[e + 1] = fmaxf(__uint_as_float(v[g * 8 + e + 1]) + b4.y, 0.f);
+      h[e + 2] = fmaxf(__uint_as_float(v[g * 8 + e + 2]) + b4.z, 0.f);
+      h[e + 3] = fmaxf(__uint_as_float(v[g * 8 + e + 3]) + b4.w, 0.f);
+      rgb[0] = fmaf(h[e], r0.x, fmaf(h[e + 1], r0.y, fmaf(h[e + 2], r0.z, fmaf(h[e + 3], r0.w, rgb[0]))));
+      rgb[1] = fmaf(h[e], r1.x, fmaf(h[e + 1], r1.y, fmaf(h[e + 2], r1.z, fmaf(h[e + 3], r1.w, rgb[1]))));
+      rgb[2] = fmaf(h[e], r2.x, fmaf(h[e + 1], r2.y, fmaf(h[e + 2], r2.z, fmaf(h[e + 3], r2.w, rgb[2]))));
+    }
+    if (kTrain) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
+      const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+      *reinterpret_cast<uint4*>(stash_tile + (size_t)(SA_HV + col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
+    }
+  }
+  return mb;
 }
 
 template <bool kTrain>
@@ -266,32 +361,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
       const int64_t row = tile * kTileM + r;
       const bool live = row < p.m;
       uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
-      // ---- prologue: sample point -> encodings (kept packed in registers), gamma(pts) -> A atom 0
-      uint32_t encp[32], encd[16];
-      {
-        float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
-        if (live) fetch_sample(p.src, row, pt, dir);
-        encode_point<10, 32>(pt, encp);
-        encode_point<4, 16>(dir, encd);
-        if (!live) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) encp[i] = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) encd[i] = 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 v = make_uint4(encp[4 * j], encp[4 * j + 1], encp[4 * j + 2], encp[4 * j + 3]);
-          *reinterpret_cast<uint4*>(act + sw128_off(r, j)) = v;
-          if (kTrain) {
-            *reinterpret_cast<uint4*>(stash_tile + sw128_off(r, j)) = v;
-            uint4 dv = j < 4 ? make_uint4(encd[4 * j], encd[4 * j + 1], encd[4 * j + 2], encd[4 * j + 3]) : make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(stash_tile + (size_t)39 * kAtomBytes + sw128_off(r, j)) = dv;
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_act + 8 * t);
-      }
+      // ---- prologue: sample point -> gamma(pts) -> A atom 0.  Only the 3-D point / direction stay in registers;
+      //      the encodings are re-derived when the skip / view passes need them (cheaper than 48 live registers).
+      float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+      if (live) fetch_sample(p.src, row, pt, dir);
+      write_encoding<10, kTrain>(pt, live, act, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_act + 8 * t);
       float alpha = 0.0f;
       for (int s = 0; s < kNumSteps; ++s) {
         mbar_wait(bar_acc + 8 * t, acc_phase);
@@ -300,13 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         const int epi = c_step_epi[s];
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 v;
-            if (epi == EPI_WRITE_ENC) v = make_uint4(encp[4 * j], encp[4 * j + 1], encp[4 * j + 2], encp[4 * j + 3]);
-            else v = j < 4 ? make_uint4(encd[4 * j], encd[4 * j + 1], encd[4 * j + 2], encd[4 * j + 3]) : make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(act + sw128_off(r, j)) = v;
-          }
+          if (epi == EPI_WRITE_ENC) write_encoding<10, false>(pt, live, act, nullptr, r);
+          else write_encoding<4, kTrain>(dir, live, act, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
           fence_proxy_async_smem();
           mbar_arrive(bar_act + 8 * t);
           continue;
@@ -316,84 +387,49 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
           // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123)
           float rgb[3] = {cst[C_BR], cst[C_BR + 1], cst[C_BR + 2]};
           uint32_t mask[4];
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(tmem_lane + cb * 32, v);
-            tmem_ld_wait();
-            uint32_t mb = 0, pk[16];
+          uint32_t va[32], vb[32];
+          tmem_ld32(tmem_lane, va);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = cb * 32 + j;
-              float h = fmaxf(__uint_as_float(v[j]) + __ldg(bias + col), 0.0f);
-              mb |= (h > 0.0f ? 1u : 0u) << j;
-              rgb[0] = fmaf(h, __ldg(cst + C_WR + col), rgb[0]);
-              rgb[1] = fmaf(h, __ldg(cst + C_WR + 128 + col), rgb[1]);
-              rgb[2] = fmaf(h, __ldg(cst + C_WR + 256 + col), rgb[2]);
-              v[j] = __float_as_uint(h);
-            }
-            mask[cb] = mb;
-            if (kTrain) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = cb * 32 + g * 8;
-                *reinterpret_cast<uint4*>(stash_tile + (size_t)(37 + col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) =
-                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-              }
-            }
+          for (int cb = 0; cb < 4; cb += 2) {
+            tmem_ld_wait_dep(va);
+            tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
+            mask[cb] = epi_final_batch<kTrain>(va, cb, bias, cst, rgb, stash_tile, r);
+            tmem_ld_wait_dep(vb);
+            if (cb + 2 < 4) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
+            mask[cb + 1] = epi_final_batch<kTrain>(vb, cb + 1, bias, cst, rgb, stash_tile, r);
           }
           if (kTrain) {
-            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + (size_t)kStashAtoms * kAtomBytes) + (8 * 128 + r) * 8;
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (8 * 128 + r) * 8;
             *reinterpret_cast<uint4*>(mrow) = make_uint4(mask[0], mask[1], mask[2], mask[3]);
           }
           if (live) *reinterpret_cast<float4*>(p.raw + row * 4) = make_float4(rgb[0], rgb[1], rgb[2], alpha + cst[C_BA]);
           tcgen05_fence_before_sync();
           continue;   // next arrival on act_ready comes from the next tile's prologue
         }
-        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
-        const bool relu = epi != EPI_LINEAR;
-        const int stash_atom = c_step_stash_atom[s];
+        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7.
+        //      TMEM loads are double-buffered: batch cb+1 is in flight while batch cb is processed.
+        uint8_t* stash_layer = kTrain ? stash_tile + (size_t)c_step_stash_atom[s] * kAtomBytes : nullptr;
         uint32_t maskw[8];
-#pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tmem_lane + cb * 32, v);
-          tmem_ld_wait();
-          uint32_t mb = 0, pk[16];
+        uint32_t va[32], vb[32];
+        tmem_ld32(tmem_lane, va);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + j));
-            float h0 = __uint_as_float(v[j]) + b4.x, h1 = __uint_as_float(v[j + 1]) + b4.y;
-            float h2 = __uint_as_float(v[j + 2]) + b4.z, h3 = __uint_as_float(v[j + 3]) + b4.w;
-            if (relu) { h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f); }
-            mb |= (h0 > 0.f ? 1u : 0u) << j | (h1 > 0.f ? 1u : 0u) << (j + 1) | (h2 > 0.f ? 1u : 0u) << (j + 2) |
-                  (h3 > 0.f ? 1u : 0u) << (j + 3);
-            if (epi == EPI_RELU_ALPHA) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + cb * 32 + j));
-              alpha = fmaf(h0, w4.x, fmaf(h1, w4.y, fmaf(h2, w4.z, fmaf(h3, w4.w, alpha))));
-            }
-            pk[j / 2] = pack_bf16(h0, h1);
-            pk[j / 2 + 1] = pack_bf16(h2, h3);
-          }
-          maskw[cb] = mb;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = cb * 32 + g * 8;
-            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            *reinterpret_cast<uint4*>(act + off) = v4;
-            if (kTrain) *reinterpret_cast<uint4*>(stash_tile + (size_t)stash_atom * kAtomBytes + off) = v4;
-          }
+        for (int cb = 0; cb < 8; cb += 2) {
+          tmem_ld_wait_dep(va);
+          tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
+          if (epi == EPI_RELU) maskw[cb] = epi_batch<kTrain, true, false>(va, cb, bias, cst, alpha, act, stash_layer, r);
+          else if (epi == EPI_RELU_ALPHA) maskw[cb] = epi_batch<kTrain, true, true>(va, cb, bias, cst, alpha, act, stash_layer, r);
+          else maskw[cb] = epi_batch<kTrain, false, false>(va, cb, bias, cst, alpha, act, stash_layer, r);
+          tmem_ld_wait_dep(vb);
+          if (cb + 2 < 8) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
+          if (epi == EPI_RELU) maskw[cb + 1] = epi_batch<kTrain, true, false>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
+          else if (epi == EPI_RELU_ALPHA) maskw[cb + 1] = epi_batch<kTrain, true, true>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
+          else maskw[cb + 1] = epi_batch<kTrain, false, false>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
         }
         if (kTrain && c_step_mask_slot[s] >= 0) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + (size_t)kStashAtoms * kAtomBytes) +
-                           (c_step_mask_slot[s] * 128 + r) * 8;
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8;
           *reinterpret_cast<uint4*>(mrow) = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
           *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(maskw[4], maskw[5], maskw[6], maskw[7]);
         }
-        if (s == 0) alpha = 0.0f;
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
@@ -500,6 +536,52 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __re
   tcgen05_fence_before_sync();
   __syncthreads();
   if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ---- diagnostic: issue rate of back-to-back tcgen05.mma for K-major / MN-major operand combinations ---------------
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_mn, int b_mn, int n, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t bar = sbase + 64 * 1024;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 64 * 1024 + 64);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(tptr), 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(128, n, a_mn, b_mn);
+    // K-major: [rows x 64] atoms, +32 B per k-step; MN-major: 64-wide blocks 4 KB apart, 2 KB per k-step
+    const uint64_t a0 = a_mn ? make_smem_desc(sbase, 4096, 1024) : make_smem_desc(sbase, 16, 1024);
+    const uint64_t b0 = b_mn ? make_smem_desc(sbase + 16384, 4096, 1024) : make_smem_desc(sbase + 16384, 16, 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      const int k = i & 1;
+      umma_bf16(tmem_base, a0 + (uint64_t)(a_mn ? 128 * k : 2 * k), b0 + (uint64_t)(b_mn ? 128 * k : 2 * k), idesc, 1);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != SPN_OK) return rc;
+  const int smem_bytes = 64 * 1024 + 256 + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  mma_rate_kernel<<<1, 128, smem_bytes, st>>>(a_mn, b_mn, n, reps, cycles_dev);
+  SPN_LAUNCH_CHECK("mma_rate_kernel");
+  return SPN_OK;
 }
 
 int tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, cudaStream_t st) {

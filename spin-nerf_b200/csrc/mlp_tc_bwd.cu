@@ -60,6 +60,30 @@ struct DgradParams {
   int num_pairs;
 };
 
+// one 32-column batch of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask -> bf16 -> A operand of the next GEMM + dstash
+__device__ __forceinline__ void dg_batch(const uint32_t (&v)[32], int cb, uint32_t mb, float dalpha, bool add_alpha,
+                                         const float* __restrict__ cst, uint8_t* act, uint8_t* dst, int r) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = cb * 32 + g * 8;
+    float h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __uint_as_float(v[g * 8 + e]);
+    if (add_alpha) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col + 4));
+      h[0] = fmaf(dalpha, w0.x, h[0]); h[1] = fmaf(dalpha, w0.y, h[1]); h[2] = fmaf(dalpha, w0.z, h[2]); h[3] = fmaf(dalpha, w0.w, h[3]);
+      h[4] = fmaf(dalpha, w1.x, h[4]); h[5] = fmaf(dalpha, w1.y, h[5]); h[6] = fmaf(dalpha, w1.z, h[6]); h[7] = fmaf(dalpha, w1.w, h[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = ((mb >> (g * 8 + e)) & 1u) ? h[e] : 0.f;
+    const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
+    if (act) *reinterpret_cast<uint4*>(act + off) = v4;
+    *reinterpret_cast<uint4*>(dst + off) = v4;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -191,32 +215,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
         const int dst_atom = c_dg_dst[s];
         const bool last = s == kDgSteps - 1;
-#pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tmem_lane + cb * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          const uint32_t mb = mw[cb];
+        uint32_t va[32], vb[32];
+        tmem_ld32(tmem_lane, va);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(v[j]), v1 = __uint_as_float(v[j + 1]);
-            if (s == 1) {
-              v0 = fmaf(dalpha, __ldg(cst + C_WA + cb * 32 + j), v0);
-              v1 = fmaf(dalpha, __ldg(cst + C_WA + cb * 32 + j + 1), v1);
-            }
-            v0 = ((mb >> j) & 1u) ? v0 : 0.f;
-            v1 = ((mb >> (j + 1)) & 1u) ? v1 : 0.f;
-            pk[j / 2] = pack_bf16(v0, v1);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = cb * 32 + g * 8;
-            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            if (!last) *reinterpret_cast<uint4*>(act + off) = v4;
-            *reinterpret_cast<uint4*>(dst_tile + (size_t)dst_atom * kAtomBytes + off) = v4;
-          }
+        for (int cb = 0; cb < 8; cb += 2) {      // double-buffered TMEM loads, like the forward epilogue
+          tmem_ld_wait_dep(va);
+          tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
+          dg_batch(va, cb, mw[cb], dalpha, s == 1, cst, last ? nullptr : act, dst_tile + (size_t)dst_atom * kAtomBytes, r);
+          tmem_ld_wait_dep(vb);
+          if (cb + 2 < 8) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
+          dg_batch(vb, cb + 1, mw[cb + 1], dalpha, s == 1, cst, last ? nullptr : act, dst_tile + (size_t)dst_atom * kAtomBytes, r);
         }
         tcgen05_fence_before_sync();
         if (!last) {
