@@ -223,7 +223,6 @@ __device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, c
     const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
     const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
     *reinterpret_cast<uint4*>(act + off) = v4;
-    if (kTrain) *reinterpret_cast<uint4*>(stash_layer + off) = v4;
   }
   return mb;
 }
@@ -373,6 +372,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
+        if (kTrain) {          // the previous layer's smem->HBM stash store must have finished READING the tile
+          if (r == 0) bulk_wait_read0();
+          named_bar_sync(1 + t, 128);
+        }
         const int epi = c_step_epi[s];
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
@@ -433,7 +436,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
+        if (kTrain) {
+          named_bar_sync(1 + t, 128);            // every row of the tile is written and fenced
+          if (r == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              bulk_s2g(stash_layer + a * kAtomBytes, smem_u32(act) + a * kAtomBytes, kAtomBytes);
+            bulk_commit();
+          }
+        }
       }
+      if (kTrain && r == 0) bulk_wait0();        // stash complete before the tile slot is reused / the kernel exits
     }
   }
 

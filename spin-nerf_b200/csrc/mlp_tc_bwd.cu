@@ -62,7 +62,7 @@ struct DgradParams {
 
 // one 32-column batch of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask -> bf16 -> A operand of the next GEMM + dstash
 __device__ __forceinline__ void dg_batch(const uint32_t (&v)[32], int cb, uint32_t mb, float dalpha, bool add_alpha,
-                                         const float* __restrict__ cst, uint8_t* act, uint8_t* dst, int r) {
+                                         const float* __restrict__ cst, uint8_t* act, int r) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = cb * 32 + g * 8;
@@ -79,8 +79,7 @@ __device__ __forceinline__ void dg_batch(const uint32_t (&v)[32], int cb, uint32
     for (int e = 0; e < 8; ++e) h[e] = ((mb >> (g * 8 + e)) & 1u) ? h[e] : 0.f;
     const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
     const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-    if (act) *reinterpret_cast<uint4*>(act + off) = v4;
-    *reinterpret_cast<uint4*>(dst + off) = v4;
+    *reinterpret_cast<uint4*>(act + off) = v4;
   }
 }
 
@@ -174,6 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
       // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide]  -> A atoms 0-1 and dstash atoms 0-1
       float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r == 0) bulk_wait_read0();             // previous tile's last dstash store has left shared memory
+      named_bar_sync(1 + t, 128);
       {
         const uint4 mk = *reinterpret_cast<const uint4*>(masks + (8 * 128 + r) * 8);
         const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
@@ -195,16 +196,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
             const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
             const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
             *reinterpret_cast<uint4*>(act + off) = v4;
-            *reinterpret_cast<uint4*>(dst_tile + (size_t)DA_HV * kAtomBytes + off) = v4;
           }
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
+        named_bar_sync(1 + t, 128);              // tile rows complete -> one thread streams them to the dstash
+        if (r == 0) {
+          bulk_s2g(dst_tile + (size_t)DA_HV * kAtomBytes, smem_u32(act), 2 * kAtomBytes);
+          bulk_commit();
+        }
       }
       for (int s = 0; s < kDgSteps; ++s) {
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
+        if (r == 0) bulk_wait_read0();           // the previous store has finished reading the tile we overwrite
+        named_bar_sync(1 + t, 128);
         const int mslot = c_dg_mask[s];
         uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
         if (mslot >= 0) {
@@ -221,17 +228,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         for (int cb = 0; cb < 8; cb += 2) {      // double-buffered TMEM loads, like the forward epilogue
           tmem_ld_wait_dep(va);
           tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
-          dg_batch(va, cb, mw[cb], dalpha, s == 1, cst, last ? nullptr : act, dst_tile + (size_t)dst_atom * kAtomBytes, r);
+          dg_batch(va, cb, mw[cb], dalpha, s == 1, cst, act, r);
           tmem_ld_wait_dep(vb);
           if (cb + 2 < 8) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
-          dg_batch(vb, cb + 1, mw[cb + 1], dalpha, s == 1, cst, last ? nullptr : act, dst_tile + (size_t)dst_atom * kAtomBytes, r);
+          dg_batch(vb, cb + 1, mw[cb + 1], dalpha, s == 1, cst, act, r);
         }
         tcgen05_fence_before_sync();
-        if (!last) {
-          fence_proxy_async_smem();
-          mbar_arrive(bar_act + 8 * t);
+        fence_proxy_async_smem();
+        if (!last) mbar_arrive(bar_act + 8 * t);
+        named_bar_sync(1 + t, 128);
+        if (r == 0) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            bulk_s2g(dst_tile + (size_t)(dst_atom + a) * kAtomBytes, smem_u32(act) + a * kAtomBytes, kAtomBytes);
+          bulk_commit();
         }
       }
+      if (r == 0) bulk_wait0();                  // dstash complete before the kernel can exit
     }
   }
   tcgen05_fence_before_sync();
@@ -382,27 +395,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
       }
     } else {
       // ---- column sums (bias gradient) from the dpre slabs, then the accumulator flush
-      const int tid = threadIdx.x - 64;           // 0..127 : output-feature pair (2*tid, 2*tid+1)
+      // thread = (row group rg of 8 samples) x (16-byte chunk j = 8 output features): 8 x LDS.128 per slab, all
+      // issued before the first use, so the slab is released (empty barrier) after ~100 instructions
+      const int tid = threadIdx.x - 64;           // 0..127
       const int q = warp & 3;
-      float bs0 = 0.f, bs1 = 0.f;
-      const bool do_bias = u.b_off >= 0 && 2 * tid < u.m_out;
-      const int c = 2 * tid;
+      const int j = tid & 31, rg = tid >> 5;
+      float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool do_bias = u.b_off >= 0 && 8 * j < u.m_out;
       for (int64_t sl = 0; sl < nslabs; ++sl) {
         mbar_wait(bar_full + 8 * stage, phase);
         if (do_bias) {
-          const uint8_t* A = smem + stage * kWgStageBytes + (c / 64) * kWgSlabBytes + (c % 8) * 2;
-          const uint32_t c16 = (uint32_t)(c % 64) / 8;
-#pragma unroll 8
-          for (int rr = 0; rr < kWgSlabRows; ++rr) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(A + sw128_off(rr, c16));
-            bs0 += __uint_as_float(w << 16);
-            bs1 += __uint_as_float(w & 0xffff0000u);
+          const uint32_t abase = sbase + stage * kWgStageBytes + (j >> 3) * kWgSlabBytes;
+          uint4 w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t addr = abase + sw128_off((uint32_t)(rg * 8 + i), (uint32_t)(j & 7));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(addr));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            bs[0] += __uint_as_float(w[i].x << 16); bs[1] += __uint_as_float(w[i].x & 0xffff0000u);
+            bs[2] += __uint_as_float(w[i].y << 16); bs[3] += __uint_as_float(w[i].y & 0xffff0000u);
+            bs[4] += __uint_as_float(w[i].z << 16); bs[5] += __uint_as_float(w[i].z & 0xffff0000u);
+            bs[6] += __uint_as_float(w[i].w << 16); bs[7] += __uint_as_float(w[i].w & 0xffff0000u);
           }
         }
         mbar_arrive(bar_empty + 8 * stage);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      if (do_bias) { atomicAdd(p.grads + u.b_off + c, bs0); atomicAdd(p.grads + u.b_off + c + 1, bs1); }
+      if (do_bias) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(p.grads + u.b_off + 8 * j + e, bs[e]);
+      }
       if (t0 < t1) mbar_wait(bar_acc_full, seg_phase);
       tcgen05_fence_after_sync();
       float* part = p.partial + (size_t)blockIdx.x * 256 * 256;

@@ -309,6 +309,33 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
     return rgbs, disps, (Xs, Ys)
 
 
+def render_path_sharded(render_poses, hwf, chunk, render_kwargs, render_factor=0, group=None):
+    """Config 5 (BASELINE.json): novel-view video over several GPUs.  Frames are independent, so rank r renders
+    frames r, r+W, ... (spin-nerf_b200/dist.py:frames_for_rank) with the same `render_path` code and the frames are
+    gathered to every rank (12.2 MB per 1008x756 RGBD frame).  Single process: identical to render_path."""
+    import torch.distributed as dist
+    from .dist import frames_for_rank
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    mine = frames_for_rank(len(render_poses), rank, world)
+    poses = [render_poses[i] for i in mine]
+    if poses:
+        rgbs, disps, _ = render_path(poses, hwf, chunk, render_kwargs, render_factor=render_factor)
+    else:
+        H, W = (int(hwf[0]) // max(render_factor, 1), int(hwf[1]) // max(render_factor, 1))
+        rgbs, disps = np.zeros((0, H, W, 3), np.float32), np.zeros((0, H, W), np.float32)
+    if world == 1:
+        return rgbs, disps
+    parts = [None] * world
+    dist.all_gather_object(parts, (mine, rgbs, disps), group=group)
+    n = len(render_poses)
+    out_rgb = np.zeros((n,) + rgbs.shape[1:], np.float32); out_disp = np.zeros((n,) + disps.shape[1:], np.float32)
+    for idx, r_, d_ in parts:
+        for j, i in enumerate(idx):
+            out_rgb[i], out_disp[i] = r_[j], d_[j]
+    return out_rgb, out_disp
+
+
 def _dump_frame(savedir, i, rgb, gt_imgs, depth, disp, extras, need_alpha, c2w):
     import cv2
     sub = lambda d: os.path.join(savedir, d)
