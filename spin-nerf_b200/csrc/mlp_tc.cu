@@ -196,15 +196,15 @@ __device__ __forceinline__ void write_encoding(const float v[3], bool live, uint
 
 // one 32-column batch of a hidden layer's epilogue: h = acc + bias (ReLU), bf16, swizzled store; returns ReLU mask bits
 template <bool kTrain, bool kRelu, bool kAlpha>
-__device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, const float* __restrict__ bias,
+__device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, const float* bias,
                                               const float* __restrict__ cst, float& alpha, uint8_t* act,
                                               uint8_t* stash_layer, int r) {
   uint32_t mb = 0;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = cb * 32 + g * 8;
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col);        // staged in shared memory
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
     float h[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
                   __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
                   __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, c
 
 // one 32-column batch of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv  (fp32), hv stashed in training
 template <bool kTrain>
-__device__ __forceinline__ uint32_t epi_final_batch(const uint32_t (&v)[32], int cb, const float* __restrict__ bias,
+__device__ __forceinline__ uint32_t epi_final_batch(const uint32_t (&v)[32], int cb, const float* bias,
                                                     const float* __restrict__ cst, float (&rgb)[3], uint8_t* stash_tile,
                                                     int r) {
   uint32_t mb = 0;
@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t epi_final_batch(const uint32_t (&v)[32], int
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; e += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + e));
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + col + e);   // staged in shared memory
       const float4 r0 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + col + e));
       const float4 r1 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 128 + col + e));
       const float4 r2 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 256 + col + e));
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack: the dynamic window must start 1024-aligned
   // barriers: full[3] empty[3] acc_full[2] act_ready[2]; tmem pointer after them
   const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
@@ -368,15 +369,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
       fence_proxy_async_smem();
       mbar_arrive(bar_act + 8 * t);
       float alpha = 0.0f;
+      float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS) + t * 256;
       for (int s = 0; s < kNumSteps; ++s) {
+        const int epi = c_step_epi[s];
+        // Stage this step's bias row in shared memory while the MMAs of the step are still running: with 227 KB of
+        // the SM carved out as shared memory there is no L1 left, so a __ldg in the epilogue costs an L2 round trip.
+        named_bar_sync(1 + t, 128);                           // everyone is done reading the previous bias row
+        if (epi != EPI_WRITE_ENC && epi != EPI_WRITE_DENC) {
+          const float2 b2 = __ldg(reinterpret_cast<const float2*>(cst + c_step_bias[s]) + (epi == EPI_FINAL ? (r & 63) : r));
+          *reinterpret_cast<float2*>(bias_s + 2 * (epi == EPI_FINAL ? (r & 63) : r)) = b2;
+        }
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (kTrain) {          // the previous layer's smem->HBM stash store must have finished READING the tile
-          if (r == 0) bulk_wait_read0();
-          named_bar_sync(1 + t, 128);
-        }
-        const int epi = c_step_epi[s];
+        if (kTrain && r == 0) bulk_wait_read0();               // previous stash store has finished READING the tile
+        named_bar_sync(1 + t, 128);
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
           if (epi == EPI_WRITE_ENC) write_encoding<10, false>(pt, live, act, nullptr, r);
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
           mbar_arrive(bar_act + 8 * t);
           continue;
         }
-        const float* bias = cst + c_step_bias[s];
+        const float* bias = bias_s;
         if (epi == EPI_FINAL) {
           // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123)
           float rgb[3] = {cst[C_BR], cst[C_BR + 1], cst[C_BR + 2]};
@@ -594,6 +601,49 @@ int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cuda
   SPN_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   mma_rate_kernel<<<1, 128, smem_bytes, st>>>(a_mn, b_mn, n, reps, cycles_dev);
   SPN_LAUNCH_CHECK("mma_rate_kernel");
+  return SPN_OK;
+}
+
+// ---- diagnostic: cp.async.bulk global->shared throughput per SM vs copy size and copies in flight ------------------
+__global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restrict__ src, size_t src_bytes, int copy_bytes,
+                                                          int depth, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + 200 * 1024;
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < depth; ++d) mbar_init(bar0 + 8 * d, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    // every CTA streams its own region (stride between CTAs = 1/grid of the buffer) so nothing is shared in L2
+    const size_t region = src_bytes / gridDim.x / 1024 * 1024;
+    const uint8_t* base = src + (size_t)blockIdx.x * region;
+    const size_t per = (size_t)copy_bytes;
+    const size_t wrap = region / per;
+    long long t0 = clock64();
+    for (int i = 0; i < iters + depth; ++i) {
+      const int slot = i % depth;
+      if (i >= depth) mbar_wait(bar0 + 8 * slot, (uint32_t)(((i - depth) / depth) & 1));   // retire the slot's previous copy
+      if (i < iters) {
+        mbar_arrive_expect_tx(bar0 + 8 * slot, copy_bytes);
+        bulk_g2s(sbase + slot * copy_bytes, base + ((size_t)i % wrap) * per, copy_bytes, bar0 + 8 * slot);
+      }
+    }
+    long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+}
+
+int tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, long long* out,
+                 cudaStream_t st) {
+  SPN_CHECK_ARG(src && out && copy_bytes >= 1024 && copy_bytes % 1024 == 0 && depth >= 1 && depth <= 32 &&
+                (size_t)copy_bytes * depth <= 200 * 1024 && grid >= 1, "spn_tc_bulk_rate: bad arguments");
+  const int smem_bytes = 200 * 1024 + 512 + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  bulk_rate_kernel<<<grid, 32, smem_bytes, st>>>((const uint8_t*)src, src_bytes, copy_bytes, depth, iters, out);
+  SPN_LAUNCH_CHECK("bulk_rate_kernel");
   return SPN_OK;
 }
 

@@ -32,7 +32,8 @@ constexpr int kThreads = 320;
 constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
 constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
 constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers + tmem pointer
-constexpr int kSmemBytes = SM_BAR + 256 + 1024;            // + slack for 1024-byte alignment
+constexpr int SM_BIAS = SM_BAR + 256;                      // 2 x 256 floats: the current layer's bias row per tile slot
+constexpr int kSmemBytes = SM_BIAS + 2048;                 // dynamic shared memory starts 1024-byte aligned (checked)
 
 // ---- per-tile forward stash (training): bf16 SWIZZLE_128B images, 16 KB atoms -----------------------------
 //   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)

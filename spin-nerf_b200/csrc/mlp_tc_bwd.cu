@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack
   const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
@@ -207,11 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         }
       }
       for (int s = 0; s < kDgSteps; ++s) {
-        mbar_wait(bar_acc + 8 * t, acc_phase);
-        acc_phase ^= 1;
-        tcgen05_fence_after_sync();
-        if (r == 0) bulk_wait_read0();           // the previous store has finished reading the tile we overwrite
-        named_bar_sync(1 + t, 128);
+        // the step's ReLU mask row is fetched while its MMAs are still running (no L1 left: every load is an L2 trip)
         const int mslot = c_dg_mask[s];
         uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
         if (mslot >= 0) {
@@ -219,6 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
           const uint4 m1 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8 + 4);
           mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
         }
+        mbar_wait(bar_acc + 8 * t, acc_phase);
+        acc_phase ^= 1;
+        tcgen05_fence_after_sync();
+        if (r == 0) bulk_wait_read0();           // the previous store has finished reading the tile we overwrite
+        named_bar_sync(1 + t, 128);
         const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
         const int dst_atom = c_dg_dst[s];
         const bool last = s == kDgSteps - 1;
@@ -591,7 +593,7 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   prof_end(PROF_MLP_WGRAD, st);
   SPN_LAUNCH_CHECK("mlp_wgrad_reduce_kernel");
   // 3. heads
-  int hgrid = (int)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
+  int hgrid = (int)(tiles < 8192 ? tiles : 8192);    // one tile per block: latency hidden by occupancy
   mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, d_raw, m, tiles, grads + po.off[T_WR],
                                                 grads + po.off[T_BR], grads + po.off[T_WA], grads + po.off[T_BA]);
   SPN_LAUNCH_CHECK("mlp_heads_wgrad_kernel");

@@ -1,0 +1,25 @@
+"""cp.async.bulk (1-D TMA bulk copy) throughput per SM vs copy size and copies in flight (spn_tc_bulk_rate)."""
+import importlib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+spn = importlib.import_module("spin-nerf_b200")
+L = spn._lib
+GRID = 148
+out = torch.zeros(GRID, dtype=torch.int64, device="cuda")
+for label, nbytes in (("HBM 2 GiB", 2 << 30), ("L2 64 MiB", 64 << 20)):
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda"); src.fill_(1)
+    for copy in (4096, 16384, 32768):
+        for depth in (1, 2, 4, 6):
+            if copy * depth > 200 * 1024:
+                continue
+            iters = max(64, (8 << 20) // copy)
+            for rep in range(2):   # second pass is the warm one for the L2-sized buffer
+                L.check(L.lib().spn_tc_bulk_rate(L.ptr(src), nbytes, copy, depth, iters, GRID, L.ptr(out), L.stream()))
+                torch.cuda.synchronize()
+            cyc = out.float().mean().item()
+            print(f"{label}: copy={copy:6d} depth={depth}: {copy * iters / cyc:6.1f} B/cycle/SM  ({cyc / iters:7.0f} cycles per copy)")
+    del src
