@@ -148,7 +148,7 @@ int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K,
 int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream);
 /* Diagnostic: per-CTA cycles (cycles_dev[grid]) to stream `iters` cp.async.bulk copies of `copy_bytes` each from `src`
  * into shared memory with `depth` copies in flight, one thread per CTA. */
-int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid,
+int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, int lanes,
                      long long* cycles_dev, void* stream);
 
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */

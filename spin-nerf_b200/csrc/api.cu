@@ -132,8 +132,8 @@ extern "C" int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, 
 }
 
 extern "C" int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid,
-                                long long* cycles_dev, void* stream) {
-  return tc_bulk_rate(src, src_bytes, copy_bytes, depth, iters, grid, cycles_dev, as_stream(stream));
+                                int lanes, long long* cycles_dev, void* stream) {
+  return tc_bulk_rate(src, src_bytes, copy_bytes, depth, iters, grid, lanes, cycles_dev, as_stream(stream));
 }
 
 extern "C" size_t spn_mlp_stash_bytes(int64_t m, int precision) {

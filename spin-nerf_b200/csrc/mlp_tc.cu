@@ -606,20 +606,22 @@ int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cuda
 
 // ---- diagnostic: cp.async.bulk global->shared throughput per SM vs copy size and copies in flight ------------------
 __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restrict__ src, size_t src_bytes, int copy_bytes,
-                                                          int depth, int iters, long long* out) {
+                                                          int depth, int iters, int lanes, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + 200 * 1024;
   if (threadIdx.x == 0) {
-    for (int d = 0; d < depth; ++d) mbar_init(bar0 + 8 * d, 1);
+    for (int d = 0; d < depth * lanes; ++d) mbar_init(bar0 + 8 * d, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  if (threadIdx.x == 0) {
-    // every CTA streams its own region (stride between CTAs = 1/grid of the buffer) so nothing is shared in L2
-    const size_t region = src_bytes / gridDim.x / 1024 * 1024;
-    const uint8_t* base = src + (size_t)blockIdx.x * region;
+  if ((int)threadIdx.x < lanes) {
+    // every issuing lane of every CTA streams its own region, so nothing is shared in L2; each lane owns `depth` slots
+    const size_t region = src_bytes / ((size_t)gridDim.x * lanes) / 1024 * 1024;
+    const uint8_t* base = src + ((size_t)blockIdx.x * lanes + threadIdx.x) * region;
+    const uint32_t bar0 = sbase + 200 * 1024 + 8 * depth * threadIdx.x;
+    const uint32_t sbase = smem_u32(smem) + (uint32_t)threadIdx.x * depth * copy_bytes;
     const size_t per = (size_t)copy_bytes;
     const size_t wrap = region / per;
     long long t0 = clock64();
@@ -632,17 +634,18 @@ __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restr
       }
     }
     long long t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
   }
 }
 
-int tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, long long* out,
-                 cudaStream_t st) {
+int tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, int lanes,
+                 long long* out, cudaStream_t st) {
   SPN_CHECK_ARG(src && out && copy_bytes >= 1024 && copy_bytes % 1024 == 0 && depth >= 1 && depth <= 32 &&
-                (size_t)copy_bytes * depth <= 200 * 1024 && grid >= 1, "spn_tc_bulk_rate: bad arguments");
+                lanes >= 1 && lanes * depth <= 32 && (size_t)copy_bytes * depth * lanes <= 200 * 1024 && grid >= 1,
+                "spn_tc_bulk_rate: bad arguments");
   const int smem_bytes = 200 * 1024 + 512 + 1024;
   SPN_CUDA(cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  bulk_rate_kernel<<<grid, 32, smem_bytes, st>>>((const uint8_t*)src, src_bytes, copy_bytes, depth, iters, out);
+  bulk_rate_kernel<<<grid, 32, smem_bytes, st>>>((const uint8_t*)src, src_bytes, copy_bytes, depth, iters, lanes, out);
   SPN_LAUNCH_CHECK("bulk_rate_kernel");
   return SPN_OK;
 }
