@@ -293,24 +293,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
 
   if (warp == 0) {
     // ================= weight producer =================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        const uint8_t* src = p.packed;
-        for (int s = 0; s < kNumSteps; ++s) {
-          const uint32_t bytes = (uint32_t)c_step_n[s] * 128u;
-          for (int t = 0; t < 2; ++t) {
-            const uint8_t* sp = src;
-            for (int c = 0; c < c_step_chunks[s]; ++c) {
+    // One thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py), so a chunk is split over
+    // kCopyLanes lanes that issue their pieces concurrently on the same mbarrier.
+    constexpr int kCopyLanes = 8;
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const uint8_t* src = p.packed;
+      for (int s = 0; s < kNumSteps; ++s) {
+        const uint32_t bytes = (uint32_t)c_step_n[s] * 128u;
+        const uint32_t piece = bytes / kCopyLanes;
+        for (int t = 0; t < 2; ++t) {
+          const uint8_t* sp = src;
+          for (int c = 0; c < c_step_chunks[s]; ++c) {
+            if (lane == 0) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-              bulk_g2s(sbase + SM_RING + stage * kChunkBig, sp, bytes, bar_full + 8 * stage);
-              sp += bytes;
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (lane < kCopyLanes)
+              bulk_g2s(sbase + SM_RING + stage * kChunkBig + lane * piece, sp + lane * piece, piece, bar_full + 8 * stage);
+            sp += bytes;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          src += (size_t)c_step_chunks[s] * bytes;
         }
+        src += (size_t)c_step_chunks[s] * bytes;
       }
     }
   } else if (warp == 1) {
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (kTrain && r == 0) bulk_wait_read0();               // previous stash store has finished READING the tile
+        if (kTrain && lane == 0) bulk_wait_read0();            // previous stash stores have finished READING the tile
         named_bar_sync(1 + t, 128);
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
@@ -445,15 +451,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         mbar_arrive(bar_act + 8 * t);
         if (kTrain) {
           named_bar_sync(1 + t, 128);            // every row of the tile is written and fenced
-          if (r == 0) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-              bulk_s2g(stash_layer + a * kAtomBytes, smem_u32(act) + a * kAtomBytes, kAtomBytes);
+          if (lane == 0) {                       // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+            bulk_s2g(stash_layer + q * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
             bulk_commit();
           }
         }
       }
-      if (kTrain && r == 0) bulk_wait0();        // stash complete before the tile slot is reused / the kernel exits
+      if (kTrain && lane == 0) bulk_wait0();        // stash complete before the tile slot is reused / the kernel exits
     }
   }
 

@@ -107,23 +107,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
   const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    if (lane == 0) {   // ---- weight producer (transposed images)
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        const uint8_t* src = p.packed + kFwdBytes;
-        for (int s = 0; s < kDgSteps; ++s) {
-          for (int t = 0; t < 2; ++t) {
-            const uint8_t* sp = src;
-            for (int c = 0; c < c_dg_chunks[s]; ++c) {
+    // ---- weight producer (transposed images); a chunk is split over 8 issuing lanes (one thread retires at most
+    //      one cp.async.bulk per ~700 cycles, tools/bulk_rate.py)
+    constexpr int kCopyLanes = 8;
+    constexpr uint32_t kPiece = kChunkBig / kCopyLanes;
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const uint8_t* src = p.packed + kFwdBytes;
+      for (int s = 0; s < kDgSteps; ++s) {
+        for (int t = 0; t < 2; ++t) {
+          const uint8_t* sp = src;
+          for (int c = 0; c < c_dg_chunks[s]; ++c) {
+            if (lane == 0) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               mbar_arrive_expect_tx(bar_full + 8 * stage, kChunkBig);
-              bulk_g2s(sbase + SM_RING + stage * kChunkBig, sp, kChunkBig, bar_full + 8 * stage);
-              sp += kChunkBig;
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (lane < kCopyLanes)
+              bulk_g2s(sbase + SM_RING + stage * kChunkBig + lane * kPiece, sp + lane * kPiece, kPiece, bar_full + 8 * stage);
+            sp += kChunkBig;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          src += (size_t)c_dg_chunks[s] * kChunkBig;
         }
+        src += (size_t)c_dg_chunks[s] * kChunkBig;
       }
     }
   } else if (warp == 1) {
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
       // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide]  -> A atoms 0-1 and dstash atoms 0-1
       float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r == 0) bulk_wait_read0();             // previous tile's last dstash store has left shared memory
+      if (lane == 0) bulk_wait_read0();          // previous tile's last dstash stores have left shared memory
       named_bar_sync(1 + t, 128);
       {
         const uint4 mk = *reinterpret_cast<const uint4*>(masks + (8 * 128 + r) * 8);
@@ -202,8 +208,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
         named_bar_sync(1 + t, 128);              // tile rows complete -> one thread streams them to the dstash
-        if (r == 0) {
-          bulk_s2g(dst_tile + (size_t)DA_HV * kAtomBytes, smem_u32(act), 2 * kAtomBytes);
+        if (lane == 0 && q < 2) {                // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+          bulk_s2g(dst_tile + (size_t)(DA_HV + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
           bulk_commit();
         }
       }
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (r == 0) bulk_wait_read0();           // the previous store has finished reading the tile we overwrite
+        if (lane == 0) bulk_wait_read0();        // the previous stores have finished reading the tile we overwrite
         named_bar_sync(1 + t, 128);
         const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
         const int dst_atom = c_dg_dst[s];
@@ -239,14 +245,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
         fence_proxy_async_smem();
         if (!last) mbar_arrive(bar_act + 8 * t);
         named_bar_sync(1 + t, 128);
-        if (r == 0) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            bulk_s2g(dst_tile + (size_t)(dst_atom + a) * kAtomBytes, smem_u32(act) + a * kAtomBytes, kAtomBytes);
+        if (lane == 0) {
+          bulk_s2g(dst_tile + (size_t)(dst_atom + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
           bulk_commit();
         }
       }
-      if (r == 0) bulk_wait0();                  // dstash complete before the kernel can exit
+      if (lane == 0) bulk_wait0();                  // dstash complete before the kernel can exit
     }
   }
   tcgen05_fence_before_sync();
@@ -352,23 +356,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
     const int64_t nslabs = (t1 - t0) * (kTileM / kWgSlabRows);
 
     if (warp == 0) {
-      if (lane == 0) {   // ---- producer: 32-sample slabs of dpre (A) and layer input (B)
-        for (int64_t sl = 0; sl < nslabs; ++sl) {
-          const int64_t tile = t0 + sl / 4;
-          const int j = (int)(sl % 4);
-          const uint8_t* dsrc = p.dstash + (size_t)tile * kDstashTileBytes + (size_t)u.d_atom * kAtomBytes + j * kWgSlabBytes;
-          const uint8_t* isrc = p.stash + (size_t)tile * kStashTileBytes + (size_t)u.in_atom * kAtomBytes + j * kWgSlabBytes;
+      // ---- producer: 32-sample slabs of dpre (A) and layer input (B).  Each of the <= 8 slab copies of a stage is
+      //      issued by its own lane (one thread retires at most one cp.async.bulk per ~700 cycles, tools/bulk_rate.py)
+      for (int64_t sl = 0; sl < nslabs; ++sl) {
+        const int64_t tile = t0 + sl / 4;
+        const int j = (int)(sl % 4);
+        if (lane == 0) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
-          const uint32_t dstA = sbase + stage * kWgStageBytes, dstB = dstA + 4 * kWgSlabBytes;
-          for (int at = 0; at < a_atoms; ++at)
-            bulk_g2s(dstA + at * kWgSlabBytes, dsrc + (size_t)at * kAtomBytes, kWgSlabBytes, bar_full + 8 * stage);
-          for (int at = 0; at < b_atoms; ++at)
-            bulk_g2s(dstB + at * kWgSlabBytes, isrc + (size_t)at * kAtomBytes, kWgSlabBytes, bar_full + 8 * stage);
-          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
-      } else {
-        for (int64_t sl = 0; sl < nslabs; ++sl) if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        __syncwarp();
+        const uint32_t dstA = sbase + stage * kWgStageBytes, dstB = dstA + 4 * kWgSlabBytes;
+        if (lane < a_atoms) {
+          const uint8_t* dsrc = p.dstash + (size_t)tile * kDstashTileBytes + (size_t)(u.d_atom + lane) * kAtomBytes + j * kWgSlabBytes;
+          bulk_g2s(dstA + lane * kWgSlabBytes, dsrc, kWgSlabBytes, bar_full + 8 * stage);
+        } else if (lane < a_atoms + b_atoms) {
+          const int at = lane - a_atoms;
+          const uint8_t* isrc = p.stash + (size_t)tile * kStashTileBytes + (size_t)(u.in_atom + at) * kAtomBytes + j * kWgSlabBytes;
+          bulk_g2s(dstB + at * kWgSlabBytes, isrc, kWgSlabBytes, bar_full + 8 * stage);
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
       if (lane == 0) {   // ---- MMA issuer: D[out, in] += dpre^T[out, k] . in[k, in],  k = sample
