@@ -610,7 +610,9 @@ int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cuda
 
 // ---- diagnostic: cp.async.bulk global->shared throughput per SM vs copy size and copies in flight ------------------
 __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restrict__ src, size_t src_bytes, int copy_bytes,
-                                                          int depth, int iters, int lanes, long long* out) {
+                                                          int depth, int iters, int lanes_arg, long long* out) {
+  const int poll = lanes_arg >= 100;           // lanes + 100 selects the polling (test_wait) variant
+  const int lanes = poll ? lanes_arg - 100 : lanes_arg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -631,7 +633,10 @@ __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restr
     long long t0 = clock64();
     for (int i = 0; i < iters + depth; ++i) {
       const int slot = i % depth;
-      if (i >= depth) mbar_wait(bar0 + 8 * slot, (uint32_t)(((i - depth) / depth) & 1));   // retire the slot's previous copy
+      if (i >= depth) {                                    // retire the slot's previous copy
+        if (poll) mbar_wait_poll(bar0 + 8 * slot, (uint32_t)(((i - depth) / depth) & 1));
+        else mbar_wait(bar0 + 8 * slot, (uint32_t)(((i - depth) / depth) & 1));
+      }
       if (i < iters) {
         mbar_arrive_expect_tx(bar0 + 8 * slot, copy_bytes);
         bulk_g2s(sbase + slot * copy_bytes, base + ((size_t)i % wrap) * per, copy_bytes, bar0 + 8 * slot);
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restr
 int tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, int lanes,
                  long long* out, cudaStream_t st) {
   SPN_CHECK_ARG(src && out && copy_bytes >= 1024 && copy_bytes % 1024 == 0 && depth >= 1 && depth <= 32 &&
-                lanes >= 1 && lanes * depth <= 32 && (size_t)copy_bytes * depth * lanes <= 200 * 1024 && grid >= 1,
+                lanes >= 1 && (lanes % 100) * depth <= 32 && (size_t)copy_bytes * depth * (lanes % 100) <= 200 * 1024 && grid >= 1,
                 "spn_tc_bulk_rate: bad arguments");
   const int smem_bytes = 200 * 1024 + 512 + 1024;
   SPN_CUDA(cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -1,5 +1,5 @@
-"""cp.async.bulk (1-D TMA bulk copy) throughput per SM vs copy size, copies in flight and issuing lanes
-(spn_tc_bulk_rate).  Finding on B200: one thread retires at most one bulk copy per ~640 cycles."""
+"""cp.async.bulk (1-D TMA bulk copy) throughput per SM vs copy size, copies in flight, issuing lanes and the
+kind of mbarrier wait (suspending try_wait vs polling test_wait) — spn_tc_bulk_rate."""
 import importlib
 import os
 import sys
@@ -11,17 +11,15 @@ spn = importlib.import_module("spin-nerf_b200")
 L = spn._lib
 GRID = 148
 out = torch.zeros(GRID, dtype=torch.int64, device="cuda")
-for label, nbytes in (("HBM 2 GiB", 2 << 30), ("L2 64 MiB", 64 << 20)):
-    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda"); src.fill_(1)
-    for copy in (4096, 16384, 32768):
-        for lanes, depth in ((1, 1), (1, 4), (2, 4), (4, 4), (8, 4), (8, 1), (16, 2)):
-            if copy * depth * lanes > 200 * 1024:
-                continue
-            iters = max(64, (4 << 20) // copy)
-            for rep in range(2):   # second pass is the warm one for the L2-sized buffer
-                L.check(L.lib().spn_tc_bulk_rate(L.ptr(src), nbytes, copy, depth, iters, GRID, lanes, L.ptr(out), L.stream()))
-                torch.cuda.synchronize()
-            cyc = out.float().mean().item()
-            print(f"{label}: copy={copy:6d} lanes={lanes:2d} depth={depth}: {copy * iters * lanes / cyc:6.1f} B/cycle/SM"
-                  f"  ({cyc / iters:7.0f} cycles per copy per lane)")
-    del src
+nbytes = 64 << 20
+src = torch.empty(nbytes, dtype=torch.uint8, device="cuda"); src.fill_(1)
+for copy in (4096, 16384):
+    for lanes, depth, poll in ((1, 4, 0), (1, 4, 1), (1, 32 if copy == 4096 else 8, 0), (1, 32 if copy == 4096 else 8, 1),
+                               (8, 4 if copy == 4096 else 1, 0), (8, 4 if copy == 4096 else 1, 1)):
+        iters = max(64, (4 << 20) // copy)
+        for rep in range(2):
+            L.check(L.lib().spn_tc_bulk_rate(L.ptr(src), nbytes, copy, depth, iters, GRID, lanes + 100 * poll, L.ptr(out), L.stream()))
+            torch.cuda.synchronize()
+        cyc = out.float().mean().item()
+        print(f"L2 64 MiB: copy={copy:6d} lanes={lanes:2d} depth={depth:2d} {'poll' if poll else 'wait'}: "
+              f"{copy * iters * lanes / cyc:6.1f} B/cycle/SM  ({cyc / iters:7.0f} cycles per copy per lane)")
