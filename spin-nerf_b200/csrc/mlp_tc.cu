@@ -611,8 +611,9 @@ int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cuda
 // ---- diagnostic: cp.async.bulk global->shared throughput per SM vs copy size and copies in flight ------------------
 __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restrict__ src, size_t src_bytes, int copy_bytes,
                                                           int depth, int iters, int lanes_arg, long long* out) {
-  const int poll = lanes_arg >= 100;           // lanes + 100 selects the polling (test_wait) variant
-  const int lanes = poll ? lanes_arg - 100 : lanes_arg;
+  const int shared_bar = lanes_arg >= 200;     // lanes + 200: all lanes' copies of a slot land on one mbarrier
+  const int poll = !shared_bar && lanes_arg >= 100;   // lanes + 100 selects the polling (test_wait) variant
+  const int lanes = lanes_arg % 100;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -631,6 +632,19 @@ __global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t* __restr
     const size_t per = (size_t)copy_bytes;
     const size_t wrap = region / per;
     long long t0 = clock64();
+    if (shared_bar) {
+      // wgrad's pattern: all lanes' copies of a slot complete on ONE mbarrier (lane 0 posts the byte count)
+      const uint32_t barS = smem_u32(smem) + 200 * 1024;
+      for (int i = 0; i < iters + depth; ++i) {
+        const int slot = i % depth;
+        if (i >= depth) mbar_wait(barS + 8 * slot, (uint32_t)(((i - depth) / depth) & 1));
+        if (i < iters) {
+          if (threadIdx.x == 0) mbar_arrive_expect_tx(barS + 8 * slot, copy_bytes * lanes);
+          __syncwarp((1u << lanes) - 1);
+          bulk_g2s(sbase + slot * copy_bytes, base + ((size_t)i % wrap) * per, copy_bytes, barS + 8 * slot);
+        }
+      }
+    } else
     for (int i = 0; i < iters + depth; ++i) {
       const int slot = i % depth;
       if (i >= depth) {                                    // retire the slot's previous copy
