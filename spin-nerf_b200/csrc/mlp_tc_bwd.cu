@@ -12,6 +12,8 @@
 //                      shared-memory slabs by otherwise idle warps.
 //   mlp_heads_wgrad_kernel   the 3x128 rgb / 1x256 sigma heads on CUDA cores.
 // No gradient flows to the sampled points (z_samples are detached, run_nerf.py:700).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_tc.cuh"
@@ -317,6 +319,7 @@ struct WgradParams {
   WgTable tab;
   int cta_begin[kWgUnits + 1];   // CTAs [cta_begin[u], cta_begin[u+1]) split unit u's tiles evenly
   float* partial;                // [gridDim.x][256][256] fp32 per-CTA weight-gradient partials
+  int debug;                     // SPN_WG_DEBUG bit0: skip MMAs, bit1: skip column sums, bit2: skip the copies (timing experiments)
 };
 
 __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -363,11 +366,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
         const int j = (int)(sl % 4);
         if (lane == 0) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+          if (p.debug & 4) mbar_arrive(bar_full + 8 * stage);
+          else mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
         }
         __syncwarp();
         const uint32_t dstA = sbase + stage * kWgStageBytes, dstB = dstA + 4 * kWgSlabBytes;
-        if (lane < a_atoms) {
+        if (p.debug & 4) {
+        } else if (lane < a_atoms) {
           const uint8_t* dsrc = p.dstash + (size_t)tile * kDstashTileBytes + (size_t)(u.d_atom + lane) * kAtomBytes + j * kWgSlabBytes;
           bulk_g2s(dstA + lane * kWgSlabBytes, dsrc, kWgSlabBytes, bar_full + 8 * stage);
         } else if (lane < a_atoms + b_atoms) {
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
             const uint64_t b_desc = make_smem_desc(aB + k * 2048, kWgSlabBytes, 1024);
             for (int h = 0; h < u.m_out / 128; ++h) {
               const uint64_t a_desc = make_smem_desc(aA + h * 2 * kWgSlabBytes + k * 2048, kWgSlabBytes, 1024);
-              umma_bf16(tmem_base + (uint32_t)h * 256u, a_desc, b_desc, idesc, accumulate);
+              if (!(p.debug & 1)) umma_bf16(tmem_base + (uint32_t)h * 256u, a_desc, b_desc, idesc, accumulate);
             }
             accumulate = 1;
           }
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
       const bool do_bias = u.b_off >= 0 && 8 * j < u.m_out;
       for (int64_t sl = 0; sl < nslabs; ++sl) {
         mbar_wait(bar_full + 8 * stage, phase);
-        if (do_bias) {
+        if (do_bias && !(p.debug & 2)) {
           const uint32_t abase = sbase + stage * kWgStageBytes + (j >> 3) * kWgSlabBytes;
           uint4 w[8];
 #pragma unroll
@@ -593,6 +598,8 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   }
   const int wgrid = assigned;
   wp.partial = reinterpret_cast<float*>((uint8_t*)ws + (size_t)even_tiles(m) * kDstashTileBytes);
+  static const int wg_debug = getenv("SPN_WG_DEBUG") ? atoi(getenv("SPN_WG_DEBUG")) : 0;
+  wp.debug = wg_debug;
   prof_begin(PROF_MLP_WGRAD, st);
   mlp_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemBytes, st>>>(wp);
   SPN_LAUNCH_CHECK("mlp_wgrad_kernel");
