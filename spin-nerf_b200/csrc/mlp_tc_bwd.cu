@@ -297,15 +297,16 @@ static WgTable build_wg_table() {
   auto DH = [&](int i) { return DA_H7 + 4 * (7 - i); };
   auto H = [&](int i) { return SA_H0 + 4 * i; };
   int n = 0;
-  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 2};
+  // cost = measured per-slab time (HBM bytes + the ~1000-cycle copy round dominate; the MMAs are a minor part), /8 of a big unit
+  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 5};
   for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, H(i - 1), 256, 256, W(i), kW, B(i), 8};
-  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 2};
+  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 5};
   t.u[n++] = WgUnit{DH(5), 256, H(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 8};
   t.u[n++] = WgUnit{DH(6), 256, H(5), 256, 256, W(6), kW, B(6), 8};
   t.u[n++] = WgUnit{DH(7), 256, H(6), 256, 256, W(7), kW, B(7), 8};
   t.u[n++] = WgUnit{DA_FEAT, 256, H(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 8};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 4};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 1};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 6};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 4};
   t.total_cost = 0;
   for (int i = 0; i < kWgUnits; ++i) t.total_cost += t.u[i].cost;
   return t;
