@@ -273,6 +273,9 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = rays_per_step * args.steps / (e2e_ms * 1e-3)
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (fused MLP forward, tcgen05): MLP FLOPs / CUDA-event time

@@ -194,15 +194,14 @@ __device__ __forceinline__ void write_encoding(const float v[3], bool live, uint
   }
 }
 
-// one 32-column batch of a hidden layer's epilogue: h = acc + bias (ReLU), bf16, swizzled store; returns ReLU mask bits
+// 16 accumulator columns of a hidden layer: h = acc + bias (ReLU), bf16, swizzled store; returns 16 ReLU mask bits
 template <bool kTrain, bool kRelu, bool kAlpha>
-__device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, const float* bias,
-                                              const float* __restrict__ cst, float& alpha, uint8_t* act,
-                                              uint8_t* stash_layer, int r) {
+__device__ __forceinline__ uint32_t epi_cols16(const uint32_t (&v)[16], int col0, const float* bias,
+                                               const float* __restrict__ cst, float& alpha, uint8_t* act, int r) {
   uint32_t mb = 0;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = cb * 32 + g * 8;
+  for (int g = 0; g < 2; ++g) {
+    const int col = col0 + g * 8;
     const float4 b0 = *reinterpret_cast<const float4*>(bias + col);        // staged in shared memory
     const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
     float h[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
@@ -221,21 +220,19 @@ __device__ __forceinline__ uint32_t epi_batch(const uint32_t (&v)[32], int cb, c
       alpha = fmaf(h[4], w1.x, fmaf(h[5], w1.y, fmaf(h[6], w1.z, fmaf(h[7], w1.w, alpha))));
     }
     const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-    const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-    *reinterpret_cast<uint4*>(act + off) = v4;
+    *reinterpret_cast<uint4*>(act + (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
   }
   return mb;
 }
 
-// one 32-column batch of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv  (fp32), hv stashed in training
+// 16 columns of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv (fp32 partial), hv stashed in training
 template <bool kTrain>
-__device__ __forceinline__ uint32_t epi_final_batch(const uint32_t (&v)[32], int cb, const float* bias,
-                                                    const float* __restrict__ cst, float (&rgb)[3], uint8_t* stash_tile,
-                                                    int r) {
+__device__ __forceinline__ uint32_t epi_final16(const uint32_t (&v)[16], int col0, const float* bias,
+                                                const float* __restrict__ cst, float (&rgb)[3], uint8_t* stash_tile, int r) {
   uint32_t mb = 0;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = cb * 32 + g * 8;
+  for (int g = 0; g < 2; ++g) {
+    const int col = col0 + g * 8;
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; e += 4) {
@@ -276,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 128); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators
@@ -355,11 +352,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
       }
     }
   } else {
-    // ================= prologue + epilogue warps =================
-    const int t = (warp - 2) >> 2;                       // tile slot 0/1
-    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    // ================= prologue + epilogue warps: 8 per tile =================
+    // warp (q, cg): TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column half cg (columns 128cg..128cg+127)
+    const int ew = warp - 2;
+    const int t = ew >> 3;                               // tile slot 0/1
+    const int cg = (ew >> 2) & 1;
+    const int q = warp & 3;
     const int r = q * 32 + lane;                         // row inside the tile
+    const int tix = cg * 128 + r;                        // 0..255 inside the tile's epilogue group
     uint8_t* act = smem + SM_ACT + t * kActBytes;
+    float4* xchg = reinterpret_cast<float4*>(act + 3 * kAtomBytes);   // FINAL-step scratch (tile is dead by then)
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     uint32_t acc_phase = 0;
     for (int it = 0; it < my_pairs; ++it) {
@@ -367,97 +369,105 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
       const int64_t row = tile * kTileM + r;
       const bool live = row < p.m;
       uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
-      // ---- prologue: sample point -> gamma(pts) -> A atom 0.  Only the 3-D point / direction stay in registers;
-      //      the encodings are re-derived when the skip / view passes need them (cheaper than 48 live registers).
+      // ---- prologue: sample point -> gamma(pts) -> A atom 0 (column half 0; half 1 later writes gamma(dir)).
+      //      Only the 3-D point / direction stay in registers; encodings are re-derived when a pass needs them.
       float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
       if (live) fetch_sample(p.src, row, pt, dir);
-      write_encoding<10, kTrain>(pt, live, act, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
+      if (cg == 0) write_encoding<10, kTrain>(pt, live, act, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
       fence_proxy_async_smem();
       mbar_arrive(bar_act + 8 * t);
-      float alpha = 0.0f;
+      float alpha = 0.0f;                                // this half's partial of the sigma head
       float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS) + t * 256;
       for (int s = 0; s < kNumSteps; ++s) {
         const int epi = c_step_epi[s];
         // Stage this step's bias row in shared memory while the MMAs of the step are still running: with 227 KB of
         // the SM carved out as shared memory there is no L1 left, so a __ldg in the epilogue costs an L2 round trip.
-        named_bar_sync(1 + t, 128);                           // everyone is done reading the previous bias row
-        if (epi != EPI_WRITE_ENC && epi != EPI_WRITE_DENC) {
-          const float2 b2 = __ldg(reinterpret_cast<const float2*>(cst + c_step_bias[s]) + (epi == EPI_FINAL ? (r & 63) : r));
-          *reinterpret_cast<float2*>(bias_s + 2 * (epi == EPI_FINAL ? (r & 63) : r)) = b2;
-        }
+        named_bar_sync(1 + t, kEpiThreads);                   // everyone is done reading the previous bias row
+        if (epi != EPI_WRITE_ENC && epi != EPI_WRITE_DENC)
+          bias_s[tix] = __ldg(cst + c_step_bias[s] + (epi == EPI_FINAL ? (tix & 127) : tix));
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (kTrain && lane == 0) bulk_wait_read0();            // previous stash stores have finished READING the tile
-        named_bar_sync(1 + t, 128);
+        if (kTrain && lane == 0 && cg == 0) bulk_wait_read0();   // previous stash stores have finished READING the tile
+        named_bar_sync(1 + t, kEpiThreads);
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
-          if (epi == EPI_WRITE_ENC) write_encoding<10, false>(pt, live, act, nullptr, r);
-          else write_encoding<4, kTrain>(dir, live, act, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
+          if (epi == EPI_WRITE_ENC) { if (cg == 0) write_encoding<10, false>(pt, live, act, nullptr, r); }
+          else if (cg == 1) write_encoding<4, kTrain>(dir, live, act, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
           fence_proxy_async_smem();
           mbar_arrive(bar_act + 8 * t);
           continue;
         }
         const float* bias = bias_s;
+        uint32_t va[16], vb[16];
         if (epi == EPI_FINAL) {
-          // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123)
-          float rgb[3] = {cst[C_BR], cst[C_BR + 1], cst[C_BR + 2]};
-          uint32_t mask[4];
-          uint32_t va[32], vb[32];
-          tmem_ld32(tmem_lane, va);
+          // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123); 64 columns per half
+          float rgb[3] = {0.f, 0.f, 0.f};
+          uint32_t mask[2];
+          const int c0 = cg * 64;
+          tmem_ld16(tmem_lane + c0, va);
 #pragma unroll
-          for (int cb = 0; cb < 4; cb += 2) {
-            tmem_ld_wait_dep(va);
-            tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
-            mask[cb] = epi_final_batch<kTrain>(va, cb, bias, cst, rgb, stash_tile, r);
-            tmem_ld_wait_dep(vb);
-            if (cb + 2 < 4) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
-            mask[cb + 1] = epi_final_batch<kTrain>(vb, cb + 1, bias, cst, rgb, stash_tile, r);
+          for (int sb = 0; sb < 4; sb += 2) {
+            tmem_ld_wait_dep16(va);
+            tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
+            const uint32_t m0 = epi_final16<kTrain>(va, c0 + sb * 16, bias, cst, rgb, stash_tile, r);
+            tmem_ld_wait_dep16(vb);
+            if (sb + 2 < 4) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
+            const uint32_t m1 = epi_final16<kTrain>(vb, c0 + (sb + 1) * 16, bias, cst, rgb, stash_tile, r);
+            mask[sb / 2] = m0 | (m1 << 16);
           }
           if (kTrain) {
-            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (8 * 128 + r) * 8;
-            *reinterpret_cast<uint4*>(mrow) = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (8 * 128 + r) * 8 + cg * 2;
+            *reinterpret_cast<uint2*>(mrow) = make_uint2(mask[0], mask[1]);
           }
-          if (live) *reinterpret_cast<float4*>(p.raw + row * 4) = make_float4(rgb[0], rgb[1], rgb[2], alpha + cst[C_BA]);
+          if (cg == 1) xchg[r] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
           tcgen05_fence_before_sync();
+          named_bar_sync(1 + t, kEpiThreads);
+          if (cg == 0 && live) {
+            const float4 o = xchg[r];
+            *reinterpret_cast<float4*>(p.raw + row * 4) =
+                make_float4(rgb[0] + o.x + cst[C_BR], rgb[1] + o.y + cst[C_BR + 1], rgb[2] + o.z + cst[C_BR + 2],
+                            alpha + o.w + cst[C_BA]);
+          }
           continue;   // next arrival on act_ready comes from the next tile's prologue
         }
         // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7.
-        //      TMEM loads are double-buffered: batch cb+1 is in flight while batch cb is processed.
+        //      128 columns per warp in 16-column TMEM loads, double-buffered.
         uint8_t* stash_layer = kTrain ? stash_tile + (size_t)c_step_stash_atom[s] * kAtomBytes : nullptr;
-        uint32_t maskw[8];
-        uint32_t va[32], vb[32];
-        tmem_ld32(tmem_lane, va);
+        uint32_t maskw[4];
+        const int c0 = cg * 128;
+        tmem_ld16(tmem_lane + c0, va);
 #pragma unroll
-        for (int cb = 0; cb < 8; cb += 2) {
-          tmem_ld_wait_dep(va);
-          tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
-          if (epi == EPI_RELU) maskw[cb] = epi_batch<kTrain, true, false>(va, cb, bias, cst, alpha, act, stash_layer, r);
-          else if (epi == EPI_RELU_ALPHA) maskw[cb] = epi_batch<kTrain, true, true>(va, cb, bias, cst, alpha, act, stash_layer, r);
-          else maskw[cb] = epi_batch<kTrain, false, false>(va, cb, bias, cst, alpha, act, stash_layer, r);
-          tmem_ld_wait_dep(vb);
-          if (cb + 2 < 8) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
-          if (epi == EPI_RELU) maskw[cb + 1] = epi_batch<kTrain, true, false>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
-          else if (epi == EPI_RELU_ALPHA) maskw[cb + 1] = epi_batch<kTrain, true, true>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
-          else maskw[cb + 1] = epi_batch<kTrain, false, false>(vb, cb + 1, bias, cst, alpha, act, stash_layer, r);
+        for (int sb = 0; sb < 8; sb += 2) {
+          uint32_t m0, m1;
+          tmem_ld_wait_dep16(va);
+          tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
+          if (epi == EPI_RELU) m0 = epi_cols16<kTrain, true, false>(va, c0 + sb * 16, bias, cst, alpha, act, r);
+          else if (epi == EPI_RELU_ALPHA) m0 = epi_cols16<kTrain, true, true>(va, c0 + sb * 16, bias, cst, alpha, act, r);
+          else m0 = epi_cols16<kTrain, false, false>(va, c0 + sb * 16, bias, cst, alpha, act, r);
+          tmem_ld_wait_dep16(vb);
+          if (sb + 2 < 8) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
+          if (epi == EPI_RELU) m1 = epi_cols16<kTrain, true, false>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
+          else if (epi == EPI_RELU_ALPHA) m1 = epi_cols16<kTrain, true, true>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
+          else m1 = epi_cols16<kTrain, false, false>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
+          maskw[sb / 2] = m0 | (m1 << 16);
         }
         if (kTrain && c_step_mask_slot[s] >= 0) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8;
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
           *reinterpret_cast<uint4*>(mrow) = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
-          *reinterpret_cast<uint4*>(mrow + 4) = make_uint4(maskw[4], maskw[5], maskw[6], maskw[7]);
         }
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
         if (kTrain) {
-          named_bar_sync(1 + t, 128);            // every row of the tile is written and fenced
-          if (lane == 0) {                       // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+          named_bar_sync(1 + t, kEpiThreads);    // every row of the tile is written and fenced
+          if (lane == 0 && cg == 0) {            // one 16 KB atom per warp: bulk-copy issue is serialised per thread
             bulk_s2g(stash_layer + q * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
             bulk_commit();
           }
         }
       }
-      if (kTrain && lane == 0) bulk_wait0();        // stash complete before the tile slot is reused / the kernel exits
+      if (kTrain && lane == 0 && cg == 0) bulk_wait0();   // stash complete before the tile slot is reused / kernel exit
     }
   }
 

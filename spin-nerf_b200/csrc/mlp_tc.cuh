@@ -28,7 +28,9 @@ constexpr int kTileM = 128;
 constexpr int kAtomBytes = kTileM * 128;        // [128 rows x 64 bf16] swizzle atom = 16 KB
 constexpr int kActBytes = 4 * kAtomBytes;       // 256-wide activation tile = 64 KB
 constexpr int kStages = 3;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;                               // epilogue warps per tile (2 column halves x 4 lane quarters)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 32 * (2 + 2 * kEpiWarps);         // producer + MMA issuer + 2 tiles x 8 epilogue warps = 576
 constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
 constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
 constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers + tmem pointer

@@ -62,12 +62,12 @@ struct DgradParams {
   int num_pairs;
 };
 
-// one 32-column batch of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask -> bf16 -> A operand of the next GEMM + dstash
-__device__ __forceinline__ void dg_batch(const uint32_t (&v)[32], int cb, uint32_t mb, float dalpha, bool add_alpha,
-                                         const float* __restrict__ cst, uint8_t* act, int r) {
+// 16 columns of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask (16 bits) -> bf16 -> A operand of the next GEMM
+__device__ __forceinline__ void dg_cols16(const uint32_t (&v)[16], int col0, uint32_t mb, float dalpha, bool add_alpha,
+                                          const float* __restrict__ cst, uint8_t* act, int r) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = cb * 32 + g * 8;
+  for (int g = 0; g < 2; ++g) {
+    const int col = col0 + g * 8;
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = __uint_as_float(v[g * 8 + e]);
@@ -80,8 +80,7 @@ __device__ __forceinline__ void dg_batch(const uint32_t (&v)[32], int cb, uint32
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = ((mb >> (g * 8 + e)) & 1u) ? h[e] : 0.f;
     const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-    const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-    *reinterpret_cast<uint4*>(act + off) = v4;
+    *reinterpret_cast<uint4*>(act + (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
   }
 }
 
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 128); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
@@ -166,8 +165,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
       }
     }
   } else {
-    // ---- prologue + epilogue warps
-    const int t = (warp - 2) >> 2;
+    // ---- prologue + epilogue warps: 8 per tile; warp (q, cg) owns rows 32q..32q+31, columns 128cg..128cg+127
+    const int ew = warp - 2;
+    const int t = ew >> 3;
+    const int cg = (ew >> 2) & 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint8_t* act = smem + SM_ACT + t * kActBytes;
@@ -180,79 +181,78 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
       const uint8_t* stash_tile = p.stash + (size_t)tile * kStashTileBytes;
       uint8_t* dst_tile = p.dstash + (size_t)tile * kDstashTileBytes;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
-      // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide]  -> A atoms 0-1 and dstash atoms 0-1
+      // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide, 64 columns per half]  -> A atoms 0-1 and dstash atoms 0-1
       float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) bulk_wait_read0();          // previous tile's last dstash stores have left shared memory
-      named_bar_sync(1 + t, 128);
+      if (lane == 0 && cg == 0) bulk_wait_read0();   // previous tile's last dstash stores have left shared memory
+      named_bar_sync(1 + t, kEpiThreads);
       {
-        const uint4 mk = *reinterpret_cast<const uint4*>(masks + (8 * 128 + r) * 8);
-        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+        const uint2 mk = *reinterpret_cast<const uint2*>(masks + (8 * 128 + r) * 8 + cg * 2);
+        const uint32_t mw2[2] = {mk.x, mk.y};
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < 2; ++cb) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const int col = cb * 32 + j;
+            const int col = cg * 64 + cb * 32 + j;
             float v0 = dr.x * __ldg(cst + C_WR + col) + dr.y * __ldg(cst + C_WR + 128 + col) + dr.z * __ldg(cst + C_WR + 256 + col);
             float v1 = dr.x * __ldg(cst + C_WR + col + 1) + dr.y * __ldg(cst + C_WR + 129 + col) + dr.z * __ldg(cst + C_WR + 257 + col);
-            v0 = ((mw[cb] >> j) & 1u) ? v0 : 0.f;
-            v1 = ((mw[cb] >> (j + 1)) & 1u) ? v1 : 0.f;
+            v0 = ((mw2[cb] >> j) & 1u) ? v0 : 0.f;
+            v1 = ((mw2[cb] >> (j + 1)) & 1u) ? v1 : 0.f;
             pk[j / 2] = pack_bf16(v0, v1);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int col = cb * 32 + g * 8;
+            const int col = cg * 64 + cb * 32 + g * 8;
             const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-            const uint4 v4 = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            *reinterpret_cast<uint4*>(act + off) = v4;
+            *reinterpret_cast<uint4*>(act + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
-        named_bar_sync(1 + t, 128);              // tile rows complete -> one thread streams them to the dstash
-        if (lane == 0 && q < 2) {                // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+        named_bar_sync(1 + t, kEpiThreads);      // tile rows complete -> stream them to the dstash
+        if (lane == 0 && cg == 0 && q < 2) {     // one 16 KB atom per warp: bulk-copy issue is serialised per thread
           bulk_s2g(dst_tile + (size_t)(DA_HV + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
           bulk_commit();
         }
       }
       for (int s = 0; s < kDgSteps; ++s) {
-        // the step's ReLU mask row is fetched while its MMAs are still running (no L1 left: every load is an L2 trip)
+        // the step's ReLU mask words are fetched while its MMAs are still running (no L1 left: every load is an L2 trip)
         const int mslot = c_dg_mask[s];
-        uint32_t mw[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        uint32_t mw[4] = {~0u, ~0u, ~0u, ~0u};
         if (mslot >= 0) {
-          const uint4 m0 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8);
-          const uint4 m1 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8 + 4);
-          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+          const uint4 m0 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8 + cg * 4);
+          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
         }
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (lane == 0) bulk_wait_read0();        // the previous stores have finished reading the tile we overwrite
-        named_bar_sync(1 + t, 128);
+        if (lane == 0 && cg == 0) bulk_wait_read0();   // the previous stores have finished reading the tile we overwrite
+        named_bar_sync(1 + t, kEpiThreads);
         const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
         const int dst_atom = c_dg_dst[s];
         const bool last = s == kDgSteps - 1;
-        uint32_t va[32], vb[32];
-        tmem_ld32(tmem_lane, va);
+        const int c0 = cg * 128;
+        uint32_t va[16], vb[16];
+        tmem_ld16(tmem_lane + c0, va);
 #pragma unroll
-        for (int cb = 0; cb < 8; cb += 2) {      // double-buffered TMEM loads, like the forward epilogue
-          tmem_ld_wait_dep(va);
-          tmem_ld32(tmem_lane + (cb + 1) * 32, vb);
-          dg_batch(va, cb, mw[cb], dalpha, s == 1, cst, act, r);
-          tmem_ld_wait_dep(vb);
-          if (cb + 2 < 8) tmem_ld32(tmem_lane + (cb + 2) * 32, va);
-          dg_batch(vb, cb + 1, mw[cb + 1], dalpha, s == 1, cst, act, r);
+        for (int sb = 0; sb < 8; sb += 2) {      // 16-column TMEM loads, double-buffered
+          tmem_ld_wait_dep16(va);
+          tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
+          dg_cols16(va, c0 + sb * 16, mw[sb / 2] & 0xffffu, dalpha, s == 1, cst, act, r);
+          tmem_ld_wait_dep16(vb);
+          if (sb + 2 < 8) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
+          dg_cols16(vb, c0 + (sb + 1) * 16, mw[sb / 2] >> 16, dalpha, s == 1, cst, act, r);
         }
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
         if (!last) mbar_arrive(bar_act + 8 * t);
-        named_bar_sync(1 + t, 128);
-        if (lane == 0) {
+        named_bar_sync(1 + t, kEpiThreads);
+        if (lane == 0 && cg == 0) {
           bulk_s2g(dst_tile + (size_t)(dst_atom + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
           bulk_commit();
         }
       }
-      if (lane == 0) bulk_wait0();                  // dstash complete before the kernel can exit
+      if (lane == 0 && cg == 0) bulk_wait0();    // dstash complete before the kernel can exit
     }
   }
   tcgen05_fence_before_sync();
