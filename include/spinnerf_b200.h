@@ -151,6 +151,10 @@ int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* 
 int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, int lanes,
                      long long* cycles_dev, void* stream);
 
+/* Diagnostic: when stamps_dev != NULL the next spn_mlp_fwd_* launches (BF16 mode) record clock64 stamps of CTA 0's
+ * pipeline events into stamps_dev[3 rounds][12 steps][2 tiles][16 events] (1152 int64; see tools/trace_fwd.py). NULL = off. */
+int spn_tc_set_trace(long long* stamps_dev);
+
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */
 int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,

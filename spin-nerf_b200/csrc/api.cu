@@ -126,6 +126,11 @@ extern "C" int spn_tc_selftest_gemm(const float* A, const float* B, float* D, in
   return tc_selftest_gemm(A, B, D, N, K, as_stream(stream));
 }
 
+extern "C" int spn_tc_set_trace(long long* stamps_dev) {
+  tc_set_trace(stamps_dev);
+  return SPN_OK;
+}
+
 extern "C" int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream) {
   SPN_CHECK_ARG(cycles_dev && reps > 0 && (n == 64 || n == 128 || n == 256), "spn_tc_mma_rate: bad arguments");
   return tc_mma_rate(a_mn_major, b_mn_major, n, reps, cycles_dev, as_stream(stream));

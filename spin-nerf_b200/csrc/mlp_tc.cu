@@ -15,6 +15,8 @@
 // The 63-wide skip input of layer 5 and the 27-wide view encoding of the views layer are applied as a
 // second accumulating pass (K=64 / K=32) after the 256-wide pass, so the 128x256 activation tile can be
 // updated in place; the encodings stay packed in registers in between.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_tc.cuh"
@@ -23,6 +25,26 @@ namespace spn {
 using namespace tc;
 
 size_t mlp_tc_packed_bytes() { return kPackedBytes; }
+
+// bytes per bulk copy of the weight producers (SPN_W_PIECE = 4096 | 8192 | 16384 for timing experiments)
+// diagnostic timeline buffer (device pointer, kTraceSlots int64): see tools/trace_fwd.py
+static long long* g_trace = nullptr;
+void tc_set_trace(long long* dev) { g_trace = dev; }
+constexpr int kTraceRounds = 3, kTraceEvents = 16;
+constexpr int kTraceSlots = kTraceRounds * 12 * 2 * kTraceEvents;
+__device__ __forceinline__ void trace_stamp(long long* tr, int it, int s, int t, int e) {
+  if (tr && blockIdx.x == 0 && it < kTraceRounds) tr[((it * 12 + s) * 2 + t) * kTraceEvents + e] = clock64();
+}
+
+int weight_piece_bytes() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("SPN_W_PIECE");
+    v = e ? atoi(e) : 16384;
+    if (v != 4096 && v != 8192 && v != 16384) v = 16384;
+  }
+  return v;
+}
 
 struct ChunkDesc {
   int src_off;   // float offset of the tensor inside the flat parameter vector (+ n0 for transposed chunks)
@@ -144,6 +166,8 @@ struct FwdParams {
   float* raw;
   uint8_t* stash;   // nullable
   int num_pairs;
+  int piece;        // bytes per cp.async.bulk of the weight producer (a chunk is split into pieces)
+  long long* trace; // diagnostic (spn_tc_set_trace): clock64 stamps of CTA 0's pipeline events, NULL = off
 };
 
 // sin/cos for the bf16 encodings: two-constant Cody-Waite reduction to [-pi, pi] (exact product via fma) followed by
@@ -178,68 +202,121 @@ __device__ __forceinline__ void encode_point(const float v[3], uint32_t (&out)[N
   for (int i = 0; i < NWORDS; ++i) out[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
 }
 
-// gamma(v) (3 + 6*NFREQ values, zero padded to 64) as bf16 -> row r of a [128 x 64] swizzled atom in shared memory
-// (and, in training, the same image in the stash).  Dead rows (beyond m) get zeros.
-template <int NFREQ, bool kStash>
-__device__ __forceinline__ void write_encoding(const float v[3], bool live, uint8_t* act_atom, uint8_t* stash_atom, int r) {
-  constexpr int NW = NFREQ == 10 ? 32 : 16;
-  uint32_t w[NW];
-  encode_point<NFREQ, NW>(v, w);
+// One 32-element half (HALF = 0: elements 0..31, 1: elements 32..63) of gamma(pts) (L = 10, 63 values + zero pad) as
+// 16 packed bf16 pairs.  The two column halves of a tile's epilogue group each build one half: 15 / 16 sincos per thread.
+template <int HALF>
+__device__ __forceinline__ void encode_pts_half(const float v[3], uint32_t (&w)[16]) {
+  float vals[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+  if (HALF == 0) { vals[0] = v[0]; vals[1] = v[1]; vals[2] = v[2]; }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int is = 3 + 6 * k + a, ic = 6 + 6 * k + a;
+      const bool ns = (is >> 5) == HALF, nc = (ic >> 5) == HALF;
+      if (ns || nc) {
+        float sn, cs;
+        fast_sincos(__fmul_rn(v[a], (float)(1 << k)), sn, cs);
+        if (ns) vals[is & 31] = sn;
+        if (nc) vals[ic & 31] = cs;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
+}
+
+// 16-byte chunks [j0, j0+NJ) of row r of a [128 x 64] swizzled atom <- packed words (zeros for dead rows / beyond the words)
+template <int NW, int NJ, bool kStash>
+__device__ __forceinline__ void store_enc_chunks(const uint32_t (&w)[NW], int j0, bool live, uint32_t atom_a, uint8_t* stash_atom,
+                                                 int r) {
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
     uint4 q4 = make_uint4(0, 0, 0, 0);
-    if (4 * j < NW && live) q4 = make_uint4(w[(4 * j) % NW], w[(4 * j + 1) % NW], w[(4 * j + 2) % NW], w[(4 * j + 3) % NW]);
-    *reinterpret_cast<uint4*>(act_atom + sw128_off(r, j)) = q4;
-    if (kStash) *reinterpret_cast<uint4*>(stash_atom + sw128_off(r, j)) = q4;
+    if (4 * jj < NW && live) q4 = make_uint4(w[(4 * jj) % NW], w[(4 * jj + 1) % NW], w[(4 * jj + 2) % NW], w[(4 * jj + 3) % NW]);
+    const uint32_t off = sw128_off((uint32_t)r, (uint32_t)(j0 + jj));
+    sts128(atom_a + off, q4.x, q4.y, q4.z, q4.w);
+    if (kStash) *reinterpret_cast<uint4*>(stash_atom + off) = q4;
   }
 }
 
-// 16 accumulator columns of a hidden layer: h = acc + bias (ReLU), bf16, swizzled store; returns 16 ReLU mask bits
-template <bool kTrain, bool kRelu, bool kAlpha>
-__device__ __forceinline__ uint32_t epi_cols16(const uint32_t (&v)[16], int col0, const float* bias,
-                                               const float* __restrict__ cst, float& alpha, uint8_t* act, int r) {
+// 32 accumulator columns of a hidden layer: h = acc + bias (ReLU), bf16, swizzled store into the A tile; returns the 32
+// ReLU mask bits (bit = column).  MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
+//   bias_a: shared address of this thread's first bias entry (column cl = 0)    wa_a: bf16 sigma weights, same origin
+//   row_a:  shared address of (this tile, this column half, row r, chunk 0)     rx: (r & 7) << 4
+template <bool kTrain, int MODE>
+__device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const int cl, const uint32_t bias_a, const uint32_t wa_a,
+                                               float& alpha, const uint32_t row_a, const uint32_t rx) {
   uint32_t mb = 0;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int col = col0 + g * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + col);        // staged in shared memory
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-    float h[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
-                  __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
-                  __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
-                  __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+  for (int g = 0; g < 4; ++g) {
+    const int c = cl + g * 8;                       // column inside this thread's 128 (compile-time after unrolling)
+    const float4 b0 = lds128f(bias_a + c * 4), b1 = lds128f(bias_a + c * 4 + 16);
+    const float2 h01 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])), make_float2(b0.x, b0.y));
+    const float2 h23 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])), make_float2(b0.z, b0.w));
+    const float2 h45 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])), make_float2(b1.x, b1.y));
+    const float2 h67 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])), make_float2(b1.z, b1.w));
+    float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
+    if (kTrain && MODE != 2) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (kRelu) h[e] = fmaxf(h[e], 0.f);
-      if (kTrain) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
+      for (int e = 0; e < 8; ++e) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
     }
-    if (kAlpha) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col + 4));
-      alpha = fmaf(h[0], w0.x, fmaf(h[1], w0.y, fmaf(h[2], w0.z, fmaf(h[3], w0.w, alpha))));
-      alpha = fmaf(h[4], w1.x, fmaf(h[5], w1.y, fmaf(h[6], w1.z, fmaf(h[7], w1.w, alpha))));
+    if (MODE == 1) {
+      const uint4 wq = lds128u(wa_a + c * 2);       // 8 bf16 sigma weights
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        h[e] = fmaxf(h[e], 0.f); h[e + 1] = fmaxf(h[e + 1], 0.f);
+        alpha = fmaf(h[e], __uint_as_float(ww[e / 2] << 16), alpha);
+        alpha = fmaf(h[e + 1], __uint_as_float(ww[e / 2] & 0xffff0000u), alpha);
+      }
     }
-    const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-    *reinterpret_cast<uint4*>(act + (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = (MODE == 0) ? pack_relu_bf16(h[2 * e], h[2 * e + 1]) : pack_bf16(h[2 * e], h[2 * e + 1]);
+    sts128(row_a + (uint32_t)(c / 64) * kAtomBytes + ((uint32_t)(((c % 64) / 8) << 4) ^ rx), o[0], o[1], o[2], o[3]);
   }
   return mb;
 }
 
-// 16 columns of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv (fp32 partial), hv stashed in training
+// one 256-wide layer epilogue for this thread: 128 columns as four 32-column TMEM loads, two in flight
+template <bool kTrain, int MODE>
+__device__ __forceinline__ void epi_layer(const uint32_t tmem_a, const uint32_t bias_a, const uint32_t wa_a, float& alpha,
+                                          const uint32_t row_a, const uint32_t rx, uint32_t (&mk)[4]) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(tmem_a, va);
+  tmem_ld32(tmem_a + 32, vb);
+  tmem_ld_wait_dep(va);
+  tmem_ld_wait_dep(vb);
+  mk[0] = epi_cols32<kTrain, MODE>(va, 0, bias_a, wa_a, alpha, row_a, rx);
+  tmem_ld32(tmem_a + 64, va);
+  mk[1] = epi_cols32<kTrain, MODE>(vb, 32, bias_a, wa_a, alpha, row_a, rx);
+  tmem_ld32(tmem_a + 96, vb);
+  tmem_ld_wait_dep(va);
+  tmem_ld_wait_dep(vb);
+  mk[2] = epi_cols32<kTrain, MODE>(va, 64, bias_a, wa_a, alpha, row_a, rx);
+  mk[3] = epi_cols32<kTrain, MODE>(vb, 96, bias_a, wa_a, alpha, row_a, rx);
+}
+
+// 32 columns of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv (fp32 partial), hv stashed in training.
+//   col0: first column (0..127)   bias_a / wr_a: shared addresses of bias[0] / Wr[0][0] ([3][128] fp32)
 template <bool kTrain>
-__device__ __forceinline__ uint32_t epi_final16(const uint32_t (&v)[16], int col0, const float* bias,
-                                                const float* __restrict__ cst, float (&rgb)[3], uint8_t* stash_tile, int r) {
+__device__ __forceinline__ uint32_t epi_final32(const uint32_t (&v)[32], const int col0, const uint32_t bias_a, const uint32_t wr_a,
+                                                float (&rgb)[3], uint8_t* stash_tile, const int r) {
   uint32_t mb = 0;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < 4; ++g) {
     const int col = col0 + g * 8;
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; e += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(bias + col + e);   // staged in shared memory
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + col + e));
-      const float4 r1 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 128 + col + e));
-      const float4 r2 = __ldg(reinterpret_cast<const float4*>(cst + C_WR + 256 + col + e));
+      const float4 b4 = lds128f(bias_a + (col + e) * 4);
+      const float4 r0 = lds128f(wr_a + (col + e) * 4);
+      const float4 r1 = lds128f(wr_a + (128 + col + e) * 4);
+      const float4 r2 = lds128f(wr_a + (256 + col + e) * 4);
       h[e + 0] = fmaxf(__uint_as_float(v[g * 8 + e + 0]) + b4.x, 0.f);
       h[e + 1] = fmaxf(__uint_as_float(v[g * 8 + e + 1]) + b4.y, 0.f);
       h[e + 2] = fmaxf(__uint_as_float(v[g * 8 + e + 2]) + b4.z, 0.f);
@@ -258,6 +335,13 @@ __device__ __forceinline__ uint32_t epi_final16(const uint32_t (&v)[16], int col
   return mb;
 }
 
+// Weight-ring schedule shared by the producer and the MMA issuer.  Both tiles of a CTA run the same layer back to back,
+// so a chunk is loaded ONCE per layer where the 3-slot ring allows it: a 4-chunk layer is loaded as c0 c1 c2 c3 c0 —
+// tile 0 consumes c0..c3 (c0's slot is recycled for c3), tile 1 consumes c1 c2 c3 from the slots tile 0 left behind and
+// then the reloaded c0 — 5 loads instead of 8; layers of <= 3 chunks are loaded once for both tiles.  Slots are still
+// released in load order, so the ring stays a FIFO with one full/empty mbarrier pair per slot.
+__device__ __forceinline__ int ring_loads(int nch) { return nch == 4 ? 5 : nch; }
+
 template <bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -266,10 +350,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack: the dynamic window must start 1024-aligned
-  // barriers: full[3] empty[3] acc_full[2] act_ready[2]; tmem pointer after them
+  // barriers: full[3] empty[3] acc_full[2] act_ready[2]
   const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
+  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -280,46 +365,51 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
     tmem_alloc(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // sigma-head weights as bf16, read by the layer-7 epilogues
+    const int i = threadIdx.x - 64;
+    const __nv_bfloat16 w = __float2bfloat16_rn(__ldg(cst + C_WA + i));
+    sts16(sbase + SM_WA + 2 * i, *reinterpret_cast<const uint16_t*>(&w));
+  }
   tcgen05_fence_before_sync();
   __syncthreads();
   tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
   const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ================= weight producer =================
-    // One thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py), so a chunk is split over
-    // kCopyLanes lanes that issue their pieces concurrently on the same mbarrier.
-    constexpr int kCopyLanes = 8;
+    // Bulk copies have a fixed per-copy cost and ONE thread retires at most one per ~700 cycles (tools/bulk_rate.py):
+    // 4 KB pieces top out at 32 B/cycle/SM, 16 KB pieces reach ~70.  A chunk is therefore moved as 16 KB pieces and
+    // every (ring stage, piece) has its own issuing lane, so no lane issues more often than once per ring revolution.
+    const uint32_t piece = (uint32_t)p.piece;
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < my_pairs; ++it) {
       const uint8_t* src = p.packed;
       for (int s = 0; s < kNumSteps; ++s) {
         const uint32_t bytes = (uint32_t)c_step_n[s] * 128u;
-        const uint32_t piece = bytes / kCopyLanes;
-        for (int t = 0; t < 2; ++t) {
-          const uint8_t* sp = src;
-          for (int c = 0; c < c_step_chunks[s]; ++c) {
-            if (lane == 0) {
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-            }
-            __syncwarp();
-            if (lane < kCopyLanes)
-              bulk_g2s(sbase + SM_RING + stage * kChunkBig + lane * piece, sp + lane * piece, piece, bar_full + 8 * stage);
-            sp += bytes;
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        const int npieces = (int)(bytes / piece);
+        const int nch = c_step_chunks[s], nl = ring_loads(nch);
+        for (int j = 0; j < nl; ++j) {
+          const uint8_t* sp = src + (size_t)(j & 3) * bytes;     // load j carries chunk j mod 4
+          if (lane == 0) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
+            trace_stamp(p.trace, it, s, j >> 2, 12 + (j & 3));
           }
+          __syncwarp();
+          const int pi = lane - (int)stage * (int)(kChunkBig / piece);
+          if (pi >= 0 && pi < npieces)
+            bulk_g2s(sbase + SM_RING + stage * kChunkBig + pi * piece, sp + pi * piece, piece, bar_full + 8 * stage);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        src += (size_t)c_step_chunks[s] * bytes;
+        src += (size_t)nch * bytes;
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t ld_idx = 0;                                  // loads consumed so far: load i sits in slot i % 3, phase (i / 3) & 1
       uint32_t act_phase[2] = {0, 0};
       for (int it = 0; it < my_pairs; ++it) {
         for (int s = 0; s < kNumSteps; ++s) {
@@ -329,12 +419,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
             mbar_wait(bar_act + 8 * t, act_phase[t]);   // A operand written, accumulator drained
             act_phase[t] ^= 1;
             tcgen05_fence_after_sync();
+            trace_stamp(p.trace, it, s, t, 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             uint32_t accumulate = (uint32_t)c_step_acc[s];
-            for (int c = 0; c < nch; ++c) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              tcgen05_fence_after_sync();
-              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + (nch == 1 ? 0 : c) * kAtomBytes;
+            for (int ci = 0; ci < nch; ++ci) {
+              // which load / chunk this MMA group uses (see ring_loads)
+              const int j = (nch == 4 && t == 1) ? ci + 1 : ci;
+              const int c = (nch == 4) ? (j & 3) : ci;
+              const bool first_use = (t == 0) || (nch == 4 && ci == 3);
+              const bool last_use = (t == 1) || (nch == 4 && ci == 0);
+              const uint32_t li = ld_idx + (uint32_t)j;
+              const uint32_t stage = li % kStages, phase = (li / kStages) & 1u;
+              if (first_use) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tcgen05_fence_after_sync();
+              }
+              if (ci == 0) trace_stamp(p.trace, it, s, t, 1);
+              if (ci == nch - 1) trace_stamp(p.trace, it, s, t, 2);
+              trace_stamp(p.trace, it, s, t, 8 + ci);
+              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + c * kAtomBytes;
               const uint32_t b_addr = sbase + SM_RING + stage * kChunkBig;
               const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
               const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024);
@@ -343,11 +446,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
                 umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
                 accumulate = 1;
               }
-              umma_commit(bar_empty + 8 * stage);      // ring slot free once these MMAs have read it
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (last_use) umma_commit(bar_empty + 8 * stage);   // ring slot free once these MMAs have read it
             }
             umma_commit(bar_acc + 8 * t);              // accumulator complete -> epilogue of tile t
+            trace_stamp(p.trace, it, s, t, 3);
           }
+          ld_idx += (uint32_t)ring_loads(nch);
         }
       }
     }
@@ -361,64 +465,92 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
     const int r = q * 32 + lane;                         // row inside the tile
     const int tix = cg * 128 + r;                        // 0..255 inside the tile's epilogue group
     uint8_t* act = smem + SM_ACT + t * kActBytes;
+    const uint32_t act_a = sbase + SM_ACT + t * kActBytes;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    const uint32_t row_a = act_a + (uint32_t)cg * 2u * kAtomBytes + (uint32_t)r * 128u;   // this thread's row, its column half
+    const uint32_t bias_row = sbase + SM_BIAS + (uint32_t)t * 1024u;
+    const uint32_t wa_a = sbase + SM_WA + (uint32_t)cg * 256u;
+    const uint32_t wr_a = act_a + 2 * kAtomBytes;        // FINAL step: Wr [3][128] fp32 staged in the (dead) tile
     float4* xchg = reinterpret_cast<float4*>(act + 3 * kAtomBytes);   // FINAL-step scratch (tile is dead by then)
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    const bool store_lane = kTrain && lane == 0 && cg == 0;          // issues this warp's 16 KB stash stores
     uint32_t acc_phase = 0;
     for (int it = 0; it < my_pairs; ++it) {
       const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + t;
       const int64_t row = tile * kTileM + r;
       const bool live = row < p.m;
       uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
-      // ---- prologue: sample point -> gamma(pts) -> A atom 0 (column half 0; half 1 later writes gamma(dir)).
+      // ---- prologue: sample point -> gamma(pts) -> A atom 0, one 32-element half per column half.
       //      Only the 3-D point / direction stay in registers; encodings are re-derived when a pass needs them.
       float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
       if (live) fetch_sample(p.src, row, pt, dir);
-      if (cg == 0) write_encoding<10, kTrain>(pt, live, act, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
+      {
+        uint32_t w[16];
+        if (cg == 0) encode_pts_half<0>(pt, w); else encode_pts_half<1>(pt, w);
+        store_enc_chunks<16, 4, kTrain>(w, 4 * cg, live, act_a, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
+      }
       fence_proxy_async_smem();
       mbar_arrive(bar_act + 8 * t);
       float alpha = 0.0f;                                // this half's partial of the sigma head
-      float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS) + t * 256;
+      int pending_atom = -1;                             // stash atom of the layer output still to be streamed out
       for (int s = 0; s < kNumSteps; ++s) {
         const int epi = c_step_epi[s];
-        // Stage this step's bias row in shared memory while the MMAs of the step are still running: with 227 KB of
-        // the SM carved out as shared memory there is no L1 left, so a __ldg in the epilogue costs an L2 round trip.
-        named_bar_sync(1 + t, kEpiThreads);                   // everyone is done reading the previous bias row
-        if (epi != EPI_WRITE_ENC && epi != EPI_WRITE_DENC)
-          bias_s[tix] = __ldg(cst + c_step_bias[s] + (epi == EPI_FINAL ? (tix & 127) : tix));
+        // (1) the whole group has finished the previous epilogue: its bias row is free, its output tile complete
+        named_bar_sync(1 + t, kEpiThreads);
+        if (kTrain && pending_atom >= 0 && store_lane) {      // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+          bulk_s2g(stash_tile + (size_t)(pending_atom + q) * kAtomBytes, act_a + q * kAtomBytes, kAtomBytes);
+          bulk_commit();
+        }
+        // (2) everything that can be done while this step's MMAs are still running: bias row -> shared memory (there
+        //     is no L1 left with 227 KB carved out, so a __ldg costs an L2 round trip), encodings, head weights
+        uint32_t encw[16];
+        float wr0 = 0.f, wr1 = 0.f;
+        float4 brba = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (epi == EPI_WRITE_ENC) {
+          if (cg == 0) encode_pts_half<0>(pt, encw); else encode_pts_half<1>(pt, encw);
+        } else if (epi == EPI_WRITE_DENC) {
+          if (cg == 1) encode_point<4, 16>(dir, encw);
+        } else {
+          sts32f(bias_row + 4 * tix, __ldg(cst + c_step_bias[s] + (epi == EPI_FINAL ? (tix & 127) : tix)));
+          if (epi == EPI_FINAL) {
+            wr0 = __ldg(cst + C_WR + tix);
+            if (tix < 128) wr1 = __ldg(cst + C_WR + 256 + tix);
+            if (cg == 0) brba = make_float4(__ldg(cst + C_BR), __ldg(cst + C_BR + 1), __ldg(cst + C_BR + 2), __ldg(cst + C_BA));
+          }
+        }
+        if (store_lane && pending_atom >= 0) bulk_wait_read0();   // the stash store has finished READING the tile
+        pending_atom = -1;
+        named_bar_sync(1 + t, kEpiThreads);                   // bias row visible, tile free to overwrite after the MMAs
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (kTrain && lane == 0 && cg == 0) bulk_wait_read0();   // previous stash stores have finished READING the tile
-        named_bar_sync(1 + t, kEpiThreads);
+        if (tix == 0) trace_stamp(p.trace, it, s, t, 4);
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
-          if (epi == EPI_WRITE_ENC) { if (cg == 0) write_encoding<10, false>(pt, live, act, nullptr, r); }
-          else if (cg == 1) write_encoding<4, kTrain>(dir, live, act, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
+          if (epi == EPI_WRITE_ENC) store_enc_chunks<16, 4, false>(encw, 4 * cg, live, act_a, nullptr, r);
+          else if (cg == 1) store_enc_chunks<16, 8, kTrain>(encw, 0, live, act_a, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
           fence_proxy_async_smem();
           mbar_arrive(bar_act + 8 * t);
+          if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
           continue;
         }
-        const float* bias = bias_s;
-        uint32_t va[16], vb[16];
         if (epi == EPI_FINAL) {
           // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123); 64 columns per half
+          sts32f(wr_a + 4 * tix, wr0);
+          if (tix < 128) sts32f(wr_a + 4 * (256 + tix), wr1);
+          named_bar_sync(1 + t, kEpiThreads);
           float rgb[3] = {0.f, 0.f, 0.f};
-          uint32_t mask[2];
           const int c0 = cg * 64;
-          tmem_ld16(tmem_lane + c0, va);
-#pragma unroll
-          for (int sb = 0; sb < 4; sb += 2) {
-            tmem_ld_wait_dep16(va);
-            tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
-            const uint32_t m0 = epi_final16<kTrain>(va, c0 + sb * 16, bias, cst, rgb, stash_tile, r);
-            tmem_ld_wait_dep16(vb);
-            if (sb + 2 < 4) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
-            const uint32_t m1 = epi_final16<kTrain>(vb, c0 + (sb + 1) * 16, bias, cst, rgb, stash_tile, r);
-            mask[sb / 2] = m0 | (m1 << 16);
-          }
+          uint32_t va[32], vb[32];
+          tmem_ld32(tmem_lane + c0, va);
+          tmem_ld32(tmem_lane + c0 + 32, vb);
+          tmem_ld_wait_dep(va);
+          tmem_ld_wait_dep(vb);
+          const uint32_t m0 = epi_final32<kTrain>(va, c0, bias_row, wr_a, rgb, stash_tile, r);
+          const uint32_t m1 = epi_final32<kTrain>(vb, c0 + 32, bias_row, wr_a, rgb, stash_tile, r);
           if (kTrain) {
             uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (8 * 128 + r) * 8 + cg * 2;
-            *reinterpret_cast<uint2*>(mrow) = make_uint2(mask[0], mask[1]);
+            *reinterpret_cast<uint2*>(mrow) = make_uint2(m0, m1);
           }
           if (cg == 1) xchg[r] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
           tcgen05_fence_before_sync();
@@ -426,49 +558,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
           if (cg == 0 && live) {
             const float4 o = xchg[r];
             *reinterpret_cast<float4*>(p.raw + row * 4) =
-                make_float4(rgb[0] + o.x + cst[C_BR], rgb[1] + o.y + cst[C_BR + 1], rgb[2] + o.z + cst[C_BR + 2],
-                            alpha + o.w + cst[C_BA]);
+                make_float4(rgb[0] + o.x + brba.x, rgb[1] + o.y + brba.y, rgb[2] + o.z + brba.z, alpha + o.w + brba.w);
           }
+          if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
           continue;   // next arrival on act_ready comes from the next tile's prologue
         }
-        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7.
-        //      128 columns per warp in 16-column TMEM loads, double-buffered.
-        uint8_t* stash_layer = kTrain ? stash_tile + (size_t)c_step_stash_atom[s] * kAtomBytes : nullptr;
-        uint32_t maskw[4];
-        const int c0 = cg * 128;
-        tmem_ld16(tmem_lane + c0, va);
-#pragma unroll
-        for (int sb = 0; sb < 8; sb += 2) {
-          uint32_t m0, m1;
-          tmem_ld_wait_dep16(va);
-          tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
-          if (epi == EPI_RELU) m0 = epi_cols16<kTrain, true, false>(va, c0 + sb * 16, bias, cst, alpha, act, r);
-          else if (epi == EPI_RELU_ALPHA) m0 = epi_cols16<kTrain, true, true>(va, c0 + sb * 16, bias, cst, alpha, act, r);
-          else m0 = epi_cols16<kTrain, false, false>(va, c0 + sb * 16, bias, cst, alpha, act, r);
-          tmem_ld_wait_dep16(vb);
-          if (sb + 2 < 8) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
-          if (epi == EPI_RELU) m1 = epi_cols16<kTrain, true, false>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
-          else if (epi == EPI_RELU_ALPHA) m1 = epi_cols16<kTrain, true, true>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
-          else m1 = epi_cols16<kTrain, false, false>(vb, c0 + (sb + 1) * 16, bias, cst, alpha, act, r);
-          maskw[sb / 2] = m0 | (m1 << 16);
-        }
+        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
+        uint32_t mk[4];
+        const uint32_t my_bias = bias_row + (uint32_t)cg * 512u;
+        const uint32_t my_tmem = tmem_lane + (uint32_t)cg * 128u;
+        if (epi == EPI_RELU) epi_layer<kTrain, 0>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
+        else if (epi == EPI_RELU_ALPHA) epi_layer<kTrain, 1>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
+        else epi_layer<kTrain, 2>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
         if (kTrain && c_step_mask_slot[s] >= 0) {
           uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
-          *reinterpret_cast<uint4*>(mrow) = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
+          *reinterpret_cast<uint4*>(mrow) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
         }
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(bar_act + 8 * t);
-        if (kTrain) {
-          named_bar_sync(1 + t, kEpiThreads);    // every row of the tile is written and fenced
-          if (lane == 0 && cg == 0) {            // one 16 KB atom per warp: bulk-copy issue is serialised per thread
-            bulk_s2g(stash_layer + q * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
-            bulk_commit();
-          }
-        }
+        if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
+        if (kTrain) pending_atom = c_step_stash_atom[s];
       }
-      if (kTrain && lane == 0 && cg == 0) bulk_wait0();   // stash complete before the tile slot is reused / kernel exit
     }
+    if (store_lane) bulk_wait0();   // every stash store has landed before the kernel exits
   }
 
   tcgen05_fence_before_sync();
@@ -503,6 +616,8 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   p.packed = (const uint8_t*)packed; p.src = src; p.m = m; p.raw = raw; p.stash = (uint8_t*)stash;
   int64_t tiles = (m + kTileM - 1) / kTileM;
   p.num_pairs = (int)((tiles + 1) / 2);
+  p.piece = weight_piece_bytes();
+  p.trace = g_trace;
   int grid = p.num_pairs < sm_count() ? p.num_pairs : sm_count();
   auto kern = stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>;
   static bool attr_set[2] = {false, false};

@@ -60,6 +60,7 @@ struct DgradParams {
   uint8_t* dstash;
   int64_t m;
   int num_pairs;
+  int piece;        // bytes per cp.async.bulk of the weight producer
 };
 
 // 16 columns of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask (16 bits) -> bf16 -> A operand of the next GEMM
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
   if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack
   const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -108,10 +109,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
   const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    // ---- weight producer (transposed images); a chunk is split over 8 issuing lanes (one thread retires at most
-    //      one cp.async.bulk per ~700 cycles, tools/bulk_rate.py)
-    constexpr int kCopyLanes = 8;
-    constexpr uint32_t kPiece = kChunkBig / kCopyLanes;
+    // ---- weight producer (transposed images): 16 KB pieces, one issuing lane per (ring stage, piece) — see mlp_tc.cu
+    const uint32_t piece = (uint32_t)p.piece;
+    const int npieces = (int)(kChunkBig / piece);
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < my_pairs; ++it) {
       const uint8_t* src = p.packed + kFwdBytes;
@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
               mbar_arrive_expect_tx(bar_full + 8 * stage, kChunkBig);
             }
             __syncwarp();
-            if (lane < kCopyLanes)
-              bulk_g2s(sbase + SM_RING + stage * kChunkBig + lane * kPiece, sp + lane * kPiece, kPiece, bar_full + 8 * stage);
+            const int pi = lane - (int)stage * npieces;
+            if (pi >= 0 && pi < npieces)
+              bulk_g2s(sbase + SM_RING + stage * kChunkBig + pi * piece, sp + pi * piece, piece, bar_full + 8 * stage);
             sp += kChunkBig;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -567,7 +568,7 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   // 1. dgrad chain
   DgradParams dp;
   dp.packed = (const uint8_t*)packed; dp.stash = (const uint8_t*)stash; dp.d_raw = d_raw;
-  dp.dstash = (uint8_t*)ws; dp.m = m; dp.num_pairs = (int)((tiles + 1) / 2);
+  dp.dstash = (uint8_t*)ws; dp.m = m; dp.num_pairs = (int)((tiles + 1) / 2); dp.piece = weight_piece_bytes();
   int grid = dp.num_pairs < sm_count() ? dp.num_pairs : sm_count();
   prof_begin(PROF_MLP_DGRAD, st);
   mlp_dgrad_kernel<<<grid, kThreads, kSmemBytes, st>>>(dp);
