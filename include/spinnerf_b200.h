@@ -146,13 +146,17 @@ int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K,
 /* Diagnostic: cycles (clock64, written to cycles_dev[0]) for `reps` back-to-back tcgen05.mma M=128 x N x K=16 with
  * K-major (0) or MN-major (1) shared-memory operands — the measurement behind DESIGN.md's wgrad layout choice. */
 int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream);
+/* Diagnostic: TMEM -> register drain rate.  `nwarps` (1..16) warps each read 128 accumulator columns of their lane quarter
+ * `reps` times with tcgen05.ld 32x32b.x32; with_mma != 0 keeps M=128 N=256 MMAs running on the same SM meanwhile.
+ * out_dev[0] = cycles of the slowest warp, out_dev[1] = MMAs issued meanwhile (tools/tmem_rate.py). */
+int spn_tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long* out_dev, void* stream);
 /* Diagnostic: per-CTA cycles (cycles_dev[grid]) to stream `iters` cp.async.bulk copies of `copy_bytes` each from `src`
  * into shared memory with `depth` copies in flight, one thread per CTA. */
 int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, int iters, int grid, int lanes,
                      long long* cycles_dev, void* stream);
 
 /* Diagnostic: when stamps_dev != NULL the next spn_mlp_fwd_* launches (BF16 mode) record clock64 stamps of CTA 0's
- * pipeline events into stamps_dev[3 rounds][12 steps][2 tiles][16 events] (1152 int64; see tools/trace_fwd.py). NULL = off. */
+ * pipeline events into stamps_dev[3 rounds][12 steps][2 tiles][24 events] (1728 int64; see tools/trace_fwd.py). NULL = off. */
 int spn_tc_set_trace(long long* stamps_dev);
 
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */

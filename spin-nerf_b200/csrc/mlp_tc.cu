@@ -30,10 +30,15 @@ size_t mlp_tc_packed_bytes() { return kPackedBytes; }
 // diagnostic timeline buffer (device pointer, kTraceSlots int64): see tools/trace_fwd.py
 static long long* g_trace = nullptr;
 void tc_set_trace(long long* dev) { g_trace = dev; }
-constexpr int kTraceRounds = 3, kTraceEvents = 16;
+constexpr int kTraceRounds = 3, kTraceEvents = 24;
 constexpr int kTraceSlots = kTraceRounds * 12 * 2 * kTraceEvents;
+__device__ __forceinline__ long long gtimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void trace_stamp(long long* tr, int it, int s, int t, int e) {
-  if (tr && blockIdx.x == 0 && it < kTraceRounds) tr[((it * 12 + s) * 2 + t) * kTraceEvents + e] = clock64();
+  if (it < kTraceRounds) tr[((it * 12 + s) * 2 + t) * kTraceEvents + e] = clock64();
 }
 
 int weight_piece_bytes() {
@@ -155,7 +160,7 @@ __constant__ int c_step_stash_atom[kNumSteps] = {1, 5, 9, 13, 17, -1, 21, 25, 29
 __constant__ int c_step_mask_slot[kNumSteps] = {0, 1, 2, 3, 4, -1, 5, 6, 7, -1, -1, 8};
 
 size_t mlp_tc_stash_bytes(int64_t m) {
-  int64_t tiles = (m + 2 * kTileM - 1) / (2 * kTileM) * 2;   // tiles are processed in pairs
+  int64_t tiles = (m + 4 * kTileM - 1) / (4 * kTileM) * 4;   // a CTA pair processes 4 tiles per round
   return (size_t)tiles * kStashTileBytes + 256;
 }
 
@@ -165,8 +170,8 @@ struct FwdParams {
   int64_t m;
   float* raw;
   uint8_t* stash;   // nullable
-  int num_pairs;
-  int piece;        // bytes per cp.async.bulk of the weight producer (a chunk is split into pieces)
+  int num_quads;    // groups of 4 tiles: one round of a CTA pair (2 tile slots per CTA)
+  int prefetch;     // SPN_W_PREFETCH (experiment): L2-prefetch the next layer's chunks
   long long* trace; // diagnostic (spn_tc_set_trace): clock64 stamps of CTA 0's pipeline events, NULL = off
 };
 
@@ -250,10 +255,13 @@ template <bool kTrain, int MODE>
 __device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const int cl, const uint32_t bias_a, const uint32_t wa_a,
                                                float& alpha, const uint32_t row_a, const uint32_t rx) {
   uint32_t mb = 0;
+  // the bias row is read one 8-column group ahead: the shared-memory latency hides behind the previous group's math
+  float4 nb0 = lds128f(bias_a + cl * 4), nb1 = lds128f(bias_a + cl * 4 + 16);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c = cl + g * 8;                       // column inside this thread's 128 (compile-time after unrolling)
-    const float4 b0 = lds128f(bias_a + c * 4), b1 = lds128f(bias_a + c * 4 + 16);
+    const float4 b0 = nb0, b1 = nb1;
+    if (g < 3) { nb0 = lds128f(bias_a + (c + 8) * 4); nb1 = lds128f(bias_a + (c + 8) * 4 + 16); }
     const float2 h01 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])), make_float2(b0.x, b0.y));
     const float2 h23 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])), make_float2(b0.z, b0.w));
     const float2 h45 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])), make_float2(b1.x, b1.y));
@@ -285,20 +293,26 @@ __device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const in
 // one 256-wide layer epilogue for this thread: 128 columns as four 32-column TMEM loads, two in flight
 template <bool kTrain, int MODE>
 __device__ __forceinline__ void epi_layer(const uint32_t tmem_a, const uint32_t bias_a, const uint32_t wa_a, float& alpha,
-                                          const uint32_t row_a, const uint32_t rx, uint32_t (&mk)[4]) {
+                                          const uint32_t row_a, const uint32_t rx, uint32_t (&mk)[4], long long* tr) {
   uint32_t va[32], vb[32];
   tmem_ld32(tmem_a, va);
   tmem_ld32(tmem_a + 32, vb);
   tmem_ld_wait_dep(va);
   tmem_ld_wait_dep(vb);
+  if (tr) tr[16] = clock64();
   mk[0] = epi_cols32<kTrain, MODE>(va, 0, bias_a, wa_a, alpha, row_a, rx);
+  if (tr) tr[17] = clock64();
   tmem_ld32(tmem_a + 64, va);
   mk[1] = epi_cols32<kTrain, MODE>(vb, 32, bias_a, wa_a, alpha, row_a, rx);
+  if (tr) tr[18] = clock64();
   tmem_ld32(tmem_a + 96, vb);
   tmem_ld_wait_dep(va);
   tmem_ld_wait_dep(vb);
+  if (tr) tr[19] = clock64();
   mk[2] = epi_cols32<kTrain, MODE>(va, 64, bias_a, wa_a, alpha, row_a, rx);
+  if (tr) tr[20] = clock64();
   mk[3] = epi_cols32<kTrain, MODE>(vb, 96, bias_a, wa_a, alpha, row_a, rx);
+  if (tr) tr[21] = clock64();
 }
 
 // 32 columns of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv (fp32 partial), hv stashed in training.
@@ -335,35 +349,52 @@ __device__ __forceinline__ uint32_t epi_final32(const uint32_t (&v)[32], const i
   return mb;
 }
 
-// Weight-ring schedule shared by the producer and the MMA issuer.  Both tiles of a CTA run the same layer back to back,
-// so a chunk is loaded ONCE per layer where the 3-slot ring allows it: a 4-chunk layer is loaded as c0 c1 c2 c3 c0 —
-// tile 0 consumes c0..c3 (c0's slot is recycled for c3), tile 1 consumes c1 c2 c3 from the slots tile 0 left behind and
-// then the reloaded c0 — 5 loads instead of 8; layers of <= 3 chunks are loaded once for both tiles.  Slots are still
-// released in load order, so the ring stays a FIFO with one full/empty mbarrier pair per slot.
-__device__ __forceinline__ int ring_loads(int nch) { return nch == 4 ? 5 : nch; }
-
+// CTA pairs (cta_group::2).  Two CTAs on neighbouring SMs form a cluster; each owns two 128-sample tile slots that
+// ping-pong as before, but every tcgen05.mma spans the pair (M = 256: slot t of both CTAs), so each SM reads only ITS
+// half of the weight chunk from shared memory (128 of the 256 output rows) and loads only that half from L2: per-SM
+// shared-memory traffic per layer drops from 336 KB to 224 KB (operand reads 192 -> 128, weight writes 80 -> 32), which
+// is what bounded the single-CTA version (tools/trace_fwd.py: MMAs ran at ~190 instead of 128 cycles with the
+// 128 B/cycle/SM shared-memory pipe saturated).  With 16 KB half-chunks the 96 KB ring has 6 slots: a layer's four
+// chunks are loaded ONCE per round and stay resident for both tile slots, two slots prefetch the next layer.
+//   leader CTA (cluster rank 0): warp 1 lane 0 issues the MMAs and the multicast commits (ring slot free / accumulator
+//     ready arrive on the same barrier offsets in both CTAs)
+//   peer CTA: warp 1 lane 0 relays "my halves of this weight group have landed" to the leader's group barrier
+//   both: warp 0 loads the CTA's halves; the 16 epilogue warps signal "A tile written" to the leader's act barrier
+//     (one elected lane per warp; remote arrive from the peer)
 template <bool kTrain>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0: leader (issues the pair's MMAs)
 
   if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack: the dynamic window must start 1024-aligned
-  // barriers: full[3] empty[3] acc_full[2] act_ready[2]
-  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
+  // Weight ring: 3 slots, each one GROUP = two 16 KB half-chunks (chunks 2g, 2g+1 of a layer).  Every chunk is loaded
+  // once per round and used by BOTH tile slots; a layer occupies two slots, the third prefetches group 0 of the next
+  // layer, whose group 1 follows as soon as tile slot 1 is through group 0 of the current one.  FIFO.
+  // barriers: group_full[2][4]  group g of step s uses barrier [g][s % 4] — the ring never holds groups of two steps that
+  //             are 4 apart.  Armed by the local producer and, on the leader, by the peer's relay as well (count 2).
+  //           empty[3] (one multicast commit per group, after tile slot 1 has used it)   acc_full[2], act_ready[2]
+  // The MMA-issuing thread is the scarce resource (tools/trace_fwd.py): tcgen05.mma issue blocks once a few MMAs are
+  // queued, a tcgen05.commit costs it ~130 cycles and even a satisfied mbarrier wait 200-400, during which the tensor
+  // pipe drains.  Hence few, merged barriers: per layer it waits on group 0 (before the A tile, off the critical path),
+  // the two A tiles and group 1 (mid-layer, tile slot 0 only), and commits 4 times.
+  static_assert(kNumSteps % 4 == 0, "group barrier phase bookkeeping assumes a multiple of 4 steps per round");
+  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 64;
+  const uint32_t bar_acc = bar_empty + 8 * kSlots, bar_act = bar_acc + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
   const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, kEpiThreads); }
+    for (int s = 0; s < kSlots; ++s) mbar_init(bar_empty + 8 * s, 1);
+    for (int b = 0; b < 8; ++b) mbar_init(bar_full + 8 * b, rank == 0 ? 2 : 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 2 * kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators
-    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
-    tmem_relinquish();
+  if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators, in both CTAs of the pair
+    tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish2();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // sigma-head weights as bf16, read by the layer-7 epilogues
     const int i = threadIdx.x - 64;
@@ -371,87 +402,104 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
     sts16(sbase + SM_WA + 2 * i, *reinterpret_cast<const uint16_t*>(&w));
   }
   tcgen05_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();               // barriers of both CTAs initialised before anyone signals across the pair
   tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+  const int my_rounds = (p.num_quads - cid + ncl - 1) / ncl;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
 
   if (warp == 0) {
-    // ================= weight producer =================
-    // Bulk copies have a fixed per-copy cost and ONE thread retires at most one per ~700 cycles (tools/bulk_rate.py):
-    // 4 KB pieces top out at 32 B/cycle/SM, 16 KB pieces reach ~70.  A chunk is therefore moved as 16 KB pieces and
-    // every (ring stage, piece) has its own issuing lane, so no lane issues more often than once per ring revolution.
-    const uint32_t piece = (uint32_t)p.piece;
+    // ================= weight producer (this CTA's half of every chunk) =================
+    // One 16 KB (8 KB for the 128-wide views layer) bulk copy per chunk; the two chunks of a group are issued by two
+    // different lanes (slot, slot + 3): a thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py).
     uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < my_pairs; ++it) {
+    for (int it = 0; it < my_rounds; ++it) {
       const uint8_t* src = p.packed;
       for (int s = 0; s < kNumSteps; ++s) {
-        const uint32_t bytes = (uint32_t)c_step_n[s] * 128u;
-        const int npieces = (int)(bytes / piece);
-        const int nch = c_step_chunks[s], nl = ring_loads(nch);
-        for (int j = 0; j < nl; ++j) {
-          const uint8_t* sp = src + (size_t)(j & 3) * bytes;     // load j carries chunk j mod 4
-          if (lane == 0) {
+        const uint32_t half = (uint32_t)c_step_n[s] * 64u;       // bytes of this CTA's half chunk
+        const int nch = c_step_chunks[s];
+        for (int g = 0; 2 * g < nch; ++g) {
+          const int in_group = nch - 2 * g < 2 ? nch - 2 * g : 2;
+          const int sub = lane >= kSlots ? 1 : 0;                // which chunk of the group this lane copies
+          if (lane == (int)stage || lane == (int)stage + kSlots) {
+            const uint32_t gbar = bar_full + 8 * (s & 3) + 32 * g;
+            // BOTH lanes of the slot wait for every one of its releases, also when the group has a single chunk: a lane
+            // that skipped a revolution would find its next parity wait satisfied by the release before last
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-            trace_stamp(p.trace, it, s, j >> 2, 12 + (j & 3));
+            if (sub == 0) {
+              mbar_arrive_expect_tx(gbar, (uint32_t)in_group * half);
+              if (g == 0 && nch <= 2) mbar_arrive(gbar + 32);   // no second group: its barrier still advances one phase per step
+              if (tracing) trace_stamp(p.trace, it, s, 0, 12 + g);
+            }
+            const int c = 2 * g + sub;
+            if (sub < in_group)
+              bulk_g2s(sbase + SM_RING + stage * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)c * 2 * half + (size_t)rank * half,
+                       half, gbar);
           }
-          __syncwarp();
-          const int pi = lane - (int)stage * (int)(kChunkBig / piece);
-          if (pi >= 0 && pi < npieces)
-            bulk_g2s(sbase + SM_RING + stage * kChunkBig + pi * piece, sp + pi * piece, piece, bar_full + 8 * stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSlots) { stage = 0; phase ^= 1; }
         }
-        src += (size_t)nch * bytes;
+        src += (size_t)nch * 2 * half;
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 && rank != 0) {
+    // ================= peer CTA: relay "my half landed" to the leader =================
     if (lane == 0) {
-      uint32_t ld_idx = 0;                                  // loads consumed so far: load i sits in slot i % 3, phase (i / 3) & 1
+      const uint32_t full_leader = mapa_cluster(bar_full, 0);
+      for (int it = 0; it < my_rounds; ++it)
+        for (int s = 0; s < kNumSteps; ++s) {
+          const uint32_t lph = (uint32_t)(it * (kNumSteps / 4) + (s >> 2)) & 1u;
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(bar_full + 32 * g + 8 * (s & 3), lph);
+            mbar_arrive_cluster(full_leader + 32 * g + 8 * (s & 3));
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ================= leader CTA: MMA issuer for the pair =================
+    if (lane == 0) {
+      uint32_t grp = 0;                                     // groups consumed so far: group i sits in ring slot i % 3
       uint32_t act_phase[2] = {0, 0};
-      for (int it = 0; it < my_pairs; ++it) {
+      for (int it = 0; it < my_rounds; ++it) {
         for (int s = 0; s < kNumSteps; ++s) {
           const int nch = c_step_chunks[s], n = c_step_n[s], ksteps = c_step_ksteps[s];
-          const uint32_t idesc = make_idesc(kTileM, n, 0, 0);
+          const uint32_t idesc = make_idesc(2 * kTileM, n, 0, 0);
+          const uint32_t lph = (uint32_t)(it * (kNumSteps / 4) + (s >> 2)) & 1u;
+          const uint32_t gbar = bar_full + 8 * (s & 3);
+          mbar_wait_cluster(gbar, lph);                       // group 0 of both CTAs (prefetched a layer ahead)
+          if (tracing) trace_stamp(p.trace, it, s, 0, 1);
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(bar_act + 8 * t, act_phase[t]);   // A operand written, accumulator drained
+            mbar_wait_cluster(bar_act + 8 * t, act_phase[t]);   // A operands of both CTAs written, accumulators drained
             act_phase[t] ^= 1;
             tcgen05_fence_after_sync();
-            trace_stamp(p.trace, it, s, t, 0);
+            if (tracing) trace_stamp(p.trace, it, s, t, 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             uint32_t accumulate = (uint32_t)c_step_acc[s];
-            for (int ci = 0; ci < nch; ++ci) {
-              // which load / chunk this MMA group uses (see ring_loads)
-              const int j = (nch == 4 && t == 1) ? ci + 1 : ci;
-              const int c = (nch == 4) ? (j & 3) : ci;
-              const bool first_use = (t == 0) || (nch == 4 && ci == 3);
-              const bool last_use = (t == 1) || (nch == 4 && ci == 0);
-              const uint32_t li = ld_idx + (uint32_t)j;
-              const uint32_t stage = li % kStages, phase = (li / kStages) & 1u;
-              if (first_use) {
-                mbar_wait(bar_full + 8 * stage, phase);
+            for (int c = 0; c < nch; ++c) {
+              const uint32_t stage = (grp + (uint32_t)(c >> 1)) % kSlots;
+              if (t == 0 && c == 2) {                           // group 1: landed while group 0 ran (tile slot 1 follows slot 0)
+                mbar_wait_cluster(gbar + 32, lph);
                 tcgen05_fence_after_sync();
+                if (tracing) trace_stamp(p.trace, it, s, 0, 2);
               }
-              if (ci == 0) trace_stamp(p.trace, it, s, t, 1);
-              if (ci == nch - 1) trace_stamp(p.trace, it, s, t, 2);
-              trace_stamp(p.trace, it, s, t, 8 + ci);
-              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + c * kAtomBytes;
-              const uint32_t b_addr = sbase + SM_RING + stage * kChunkBig;
+              if (tracing) trace_stamp(p.trace, it, s, t, 8 + c);
+              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + (nch == 1 ? 0 : c) * kAtomBytes;
+              const uint32_t b_addr = sbase + SM_RING + stage * kSlotBytes + (c & 1) * (kSlotBytes / 2);
               const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
               const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024);
               for (int k = 0; k < ksteps; ++k) {
                 // +32 bytes (16 bf16) along K inside the 128-byte swizzle atom: start-address field += 2
-                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
                 accumulate = 1;
               }
-              if (last_use) umma_commit(bar_empty + 8 * stage);   // ring slot free once these MMAs have read it
+              // group free in both CTAs once tile slot 1's MMAs have read it
+              if (t == 1 && ((c & 1) || c == nch - 1)) umma_commit_2cta(bar_empty + 8 * stage, 3);
             }
-            umma_commit(bar_acc + 8 * t);              // accumulator complete -> epilogue of tile t
-            trace_stamp(p.trace, it, s, t, 3);
+            umma_commit_2cta(bar_acc + 8 * t, 3);            // accumulators complete -> epilogues of slot t in both CTAs
+            if (tracing) trace_stamp(p.trace, it, s, t, 3);
           }
-          ld_idx += (uint32_t)ring_loads(nch);
+          grp += (uint32_t)((nch + 1) >> 1);
         }
       }
     }
@@ -474,9 +522,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
     float4* xchg = reinterpret_cast<float4*>(act + 3 * kAtomBytes);   // FINAL-step scratch (tile is dead by then)
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     const bool store_lane = kTrain && lane == 0 && cg == 0;          // issues this warp's 16 KB stash stores
+    const uint32_t act_leader = mapa_cluster(bar_act + 8 * t, 0);    // the leader's "A tile written" barrier for slot t
     uint32_t acc_phase = 0;
-    for (int it = 0; it < my_pairs; ++it) {
-      const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + t;
+    for (int it = 0; it < my_rounds; ++it) {
+      const int64_t tile = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank + t;
       const int64_t row = tile * kTileM + r;
       const bool live = row < p.m;
       uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
@@ -490,7 +539,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         store_enc_chunks<16, 4, kTrain>(w, 4 * cg, live, act_a, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
       }
       fence_proxy_async_smem();
-      mbar_arrive(bar_act + 8 * t);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(act_leader);
       float alpha = 0.0f;                                // this half's partial of the sigma head
       int pending_atom = -1;                             // stash atom of the layer output still to be streamed out
       for (int s = 0; s < kNumSteps; ++s) {
@@ -524,14 +574,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (tix == 0) trace_stamp(p.trace, it, s, t, 4);
+        if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
         if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
           // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
           if (epi == EPI_WRITE_ENC) store_enc_chunks<16, 4, false>(encw, 4 * cg, live, act_a, nullptr, r);
           else if (cg == 1) store_enc_chunks<16, 8, kTrain>(encw, 0, live, act_a, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
           fence_proxy_async_smem();
-          mbar_arrive(bar_act + 8 * t);
-          if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(act_leader);
+          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
           continue;
         }
         if (epi == EPI_FINAL) {
@@ -560,36 +611,40 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams p)
             *reinterpret_cast<float4*>(p.raw + row * 4) =
                 make_float4(rgb[0] + o.x + brba.x, rgb[1] + o.y + brba.y, rgb[2] + o.z + brba.z, alpha + o.w + brba.w);
           }
-          if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
+          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
           continue;   // next arrival on act_ready comes from the next tile's prologue
         }
         // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
         uint32_t mk[4];
         const uint32_t my_bias = bias_row + (uint32_t)cg * 512u;
         const uint32_t my_tmem = tmem_lane + (uint32_t)cg * 128u;
-        if (epi == EPI_RELU) epi_layer<kTrain, 0>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
-        else if (epi == EPI_RELU_ALPHA) epi_layer<kTrain, 1>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
-        else epi_layer<kTrain, 2>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk);
+        long long* etr = (tix == 0 && tracing && it < kTraceRounds) ? p.trace + ((it * 12 + s) * 2 + t) * kTraceEvents : nullptr;
+        if (epi == EPI_RELU) epi_layer<kTrain, 0>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
+        else if (epi == EPI_RELU_ALPHA) epi_layer<kTrain, 1>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
+        else epi_layer<kTrain, 2>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
         if (kTrain && c_step_mask_slot[s] >= 0) {
           uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
           *reinterpret_cast<uint4*>(mrow) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
         }
         tcgen05_fence_before_sync();
+        if (etr) etr[22] = clock64();
         fence_proxy_async_smem();
-        mbar_arrive(bar_act + 8 * t);
-        if (tix == 0) trace_stamp(p.trace, it, s, t, 6);
+        if (etr) etr[23] = clock64();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(act_leader);
+        if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
         if (kTrain) pending_atom = c_step_stash_atom[s];
       }
     }
     if (store_lane) bulk_wait0();   // every stash store has landed before the kernel exits
   }
 
+  __syncwarp();                     // single-lane roles rejoin their warp before the aligned cluster barrier
   tcgen05_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();               // nobody signals into a CTA that has exited; all MMAs of the pair have completed
   if (warp == 1) {
-    __syncwarp();
     tcgen05_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -615,10 +670,11 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   FwdParams p;
   p.packed = (const uint8_t*)packed; p.src = src; p.m = m; p.raw = raw; p.stash = (uint8_t*)stash;
   int64_t tiles = (m + kTileM - 1) / kTileM;
-  p.num_pairs = (int)((tiles + 1) / 2);
-  p.piece = weight_piece_bytes();
+  p.num_quads = (int)((tiles + 3) / 4);
   p.trace = g_trace;
-  int grid = p.num_pairs < sm_count() ? p.num_pairs : sm_count();
+  { static int pf = getenv("SPN_W_PREFETCH") ? atoi(getenv("SPN_W_PREFETCH")) : 0; p.prefetch = pf; }
+  const int pairs = sm_count() / 2;
+  int grid = 2 * (p.num_quads < pairs ? p.num_quads : pairs);
   auto kern = stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[stash ? 1 : 0]) {
@@ -626,7 +682,7 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
     attr_set[stash ? 1 : 0] = true;
   }
   prof_begin(PROF_MLP_FWD, st);
-  kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+  kern<<<grid, kPairThreads, kSmemBytes, st>>>(p);
   prof_end(PROF_MLP_FWD, st);
   SPN_LAUNCH_CHECK("mlp_fwd_kernel");
   return SPN_OK;
@@ -721,6 +777,80 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int a_mn, int b_mn, in
   tcgen05_fence_before_sync();
   __syncthreads();
   if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+
+// ---- diagnostic: TMEM -> register drain rate (tcgen05.ld 32x32b.x32), optionally while MMAs run on the same SM ---------
+// warps 0..nwarps-1 (warp w reads lane quarter w % 4) each drain 128 columns `reps` times; with_mma != 0: warp 16 lane 0
+// keeps issuing M=128 N=256 K=16 MMAs into columns 256..511 for the whole time.  out[0] = cycles of the slowest drain
+// warp, out[1] = MMAs retired meanwhile.
+__global__ void __launch_bounds__(17 * 32, 1) tmem_ld_rate_kernel(int nwarps, int reps, int with_mma, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t bar = sbase + 64 * 1024;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 64 * 1024 + 64);
+  volatile int* stop = reinterpret_cast<volatile int*>(smem + 64 * 1024 + 128);
+  __shared__ long long s_cyc[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); *stop = 0; }
+  if (warp == 0) { tmem_alloc(smem_u32(tptr), 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  if (warp < nwarps) {
+    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) & 1) * 128u;
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      uint32_t va[32], vb[32];
+      tmem_ld32(ta, va); tmem_ld32(ta + 32, vb);
+      tmem_ld_wait_dep(va); tmem_ld_wait_dep(vb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= va[j] + vb[j];
+      tmem_ld32(ta + 64, va); tmem_ld32(ta + 96, vb);
+      tmem_ld_wait_dep(va); tmem_ld_wait_dep(vb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= va[j] + vb[j];
+    }
+    const long long t1 = clock64();
+    if (lane == 0) s_cyc[warp] = t1 - t0 + (acc == 0x12345u ? 1 : 0);
+    if (warp == 0 && lane == 0) *stop = 1;
+  } else if (warp == 16 && lane == 0 && with_mma) {
+    const uint32_t idesc = make_idesc(128, 256, 0, 0);
+    const uint64_t a0 = make_smem_desc(sbase, 16, 1024), b0 = make_smem_desc(sbase + 16384, 16, 1024);
+    long long n = 0;
+    while (!*stop) {
+      for (int i = 0; i < 16; ++i) umma_bf16(tmem_base + 256u, a0 + (uint64_t)(2 * (i & 3)), b0 + (uint64_t)(2 * (i & 3)), idesc, 1);
+      n += 16;
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    out[1] = n;
+  }
+  tcgen05_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long m = 0;
+    for (int w = 0; w < nwarps; ++w) m = s_cyc[w] > m ? s_cyc[w] : m;
+    out[0] = m;
+    if (!with_mma) out[1] = 0;
+  }
+  if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+int tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long* out, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != SPN_OK) return rc;
+  SPN_CHECK_ARG(out && nwarps >= 1 && nwarps <= 16 && reps > 0, "spn_tc_tmem_ld_rate: bad arguments");
+  const int smem_bytes = 64 * 1024 + 256 + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(tmem_ld_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  tmem_ld_rate_kernel<<<1, 17 * 32, smem_bytes, st>>>(nwarps, reps, with_mma, out);
+  SPN_LAUNCH_CHECK("tmem_ld_rate_kernel");
+  return SPN_OK;
 }
 
 int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cudaStream_t st) {

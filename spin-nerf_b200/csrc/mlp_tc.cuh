@@ -33,11 +33,16 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 32 * (2 + 2 * kEpiWarps);         // producer + MMA issuer + 2 tiles x 8 epilogue warps = 576
 constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
 constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
-constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers (10 x 8 B)
-constexpr int SM_TMEMPTR = SM_BAR + 96;                    // TMEM base address written by tcgen05.alloc
-constexpr int SM_BIAS = SM_BAR + 128;                      // 2 x 256 floats: the current layer's bias row per tile slot
+constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers (<= 24 x 8 B)
+constexpr int SM_TMEMPTR = SM_BAR + 240;                   // TMEM base address written by tcgen05.alloc
+constexpr int SM_BIAS = SM_BAR + 256;                      // 2 x 256 floats: the current layer's bias row per tile slot
 constexpr int SM_WA = SM_BIAS + 2048;                      // forward only: sigma-head weights, 256 x bf16
-constexpr int kSmemBytes = SM_WA + 512;                    // = 232064 <= 232448; starts 1024-byte aligned (checked)
+constexpr int kSmemBytes = SM_WA + 512;                    // = 232192 <= 232448; starts 1024-byte aligned (checked)
+// CTA-pair kernels (cta_group::2): every CTA holds HALF of each weight chunk (its 128 of the 256 output rows), so the
+// same 96 KB ring holds 6 half-chunks: a whole layer (4) stays resident for both tile slots + 2 of the next layer
+constexpr int kPairThreads = kThreads;
+constexpr int kSlots = 3;            // ring slots: one GROUP (two half-chunks) each
+constexpr int kSlotBytes = 32768;
 
 // ---- per-tile forward stash (training): bf16 SWIZZLE_128B images, 16 KB atoms -----------------------------
 //   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)

@@ -16,15 +16,15 @@ flat, packed = net._sync()
 stash = spn.ops.mlp_stash(M, spn.PREC_BF16, dev) if train else None
 for _ in range(2):
     spn.ops.mlp_forward_points(flat, packed, x6, spn.PREC_BF16, stash)
-tr = torch.zeros(3 * 12 * 2 * 16, dtype=torch.int64, device=dev)
+tr = torch.zeros(3 * 12 * 2 * 24, dtype=torch.int64, device=dev)
 L.check(L.lib().spn_tc_set_trace(L.ptr(tr)))
 spn.ops.mlp_forward_points(flat, packed, x6, spn.PREC_BF16, stash)
 torch.cuda.synchronize()
 L.lib().spn_tc_set_trace(None)
-t = tr.cpu().numpy().reshape(3, 12, 2, 16)
+t = tr.cpu().numpy().reshape(3, 12, 2, 24)
 t0 = t[t > 0].min()
 names = ["mma:act_ready", "mma:w_first", "mma:w_last", "mma:issued", "epi:acc_ready", "epi:synced", "epi:done0", "epi:done255"]
-print("round step tile | " + " ".join(f"{n:>8s}" for n in ["act_rdy", "w_first", "w_last", "issued", "acc_rdy", "-", "epi_done", "-"]) + " |  epi_len  mma_wait_w")
+print("round step tile | " + " ".join(f"{n:>8s}" for n in ["act_rdy", "lf_ok", "plf_ok", "issued", "acc_rdy", "p_accrdy", "epi_done", "p_epidone"]) + " |  epi_len  mma_wait_w")
 for it in range(3):
     for s in range(12):
         for tl in range(2):
@@ -34,5 +34,5 @@ for it in range(3):
             ww = rel[2] - rel[0]
             blk = " ".join(f"{rel[8 + i] - rel[0]:5d}" for i in range(4) if rel[8 + i] > 0)
             prod = " ".join(f"{rel[12 + i] - rel[0]:6d}" for i in range(4) if rel[12 + i] > 0)
-            print(f"{it:5d} {s:4d} {tl:4d} | " + " ".join(f"{x:8d}" for x in rel[:8]) + f" | {epi:6d} {ww:6d} | chunk ready (rel act_ready): {blk} | loads issued: {prod}")
+            print(f"{it:5d} {s:4d} {tl:4d} | " + " ".join(f"{x:8d}" for x in rel[:8]) + f" | {epi:6d} {ww:6d} | chunk ready (rel act_ready): {blk} | loads issued: {prod} | epi internals (rel acc_rdy): " + " ".join(f"{rel[16 + i] - rel[4]:5d}" for i in range(8) if rel[16 + i] > 0))
 print("cycles per pair-round:", [int(t[i + 1, 0, 0, 0] - t[i, 0, 0, 0]) for i in range(2)])
