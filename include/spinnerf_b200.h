@@ -159,6 +159,16 @@ int spn_tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int dept
  * pipeline events into stamps_dev[3 rounds][12 steps][2 tiles][24 events] (1728 int64; see tools/trace_fwd.py). NULL = off. */
 int spn_tc_set_trace(long long* stamps_dev);
 
+/* ---- a11  train-step losses (run_nerf.py:15, 1481-1521, default flags) for a chunk that concatenates the step's three
+ * ray groups: [0,n1) unmasked rays, [n1,n1+n2) masked rays of the kept view (both: img2mse of rgb_map and rgb0 against
+ * target_rgb [n1+n2,3]), [n1+n2, n1+n2+n3) inpainted-disparity rays (img2mse of disp_map and disp0 against target_disp
+ * [n3]; dropped, loss and gradient, when NaN — run_nerf.py:1520).  Writes the upstream gradients g_* ([n,3] / [n]) for
+ * spn_render_rays_bwd and out8 = {loss, psnr, the six loss terms}.  sums6_zeroed: 6 floats, zero on entry. */
+int spn_train_losses(const float* rgb_map, const float* rgb0, const float* disp_map, const float* disp0,
+                     const float* target_rgb, const float* target_disp, int n1, int n2, int n3,
+                     float* sums6_zeroed, float* g_rgb, float* g_rgb0, float* g_disp, float* g_disp0,
+                     float* out8, void* stream);
+
 /* ---- a12  Adam (run_nerf.py:433-434, 1611-1622), one flat launch --------------------------- */
 int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,
@@ -206,6 +216,9 @@ typedef struct {       /* upstream gradients (NULL = zero) and gradient outputs 
   float* grads_fine;    /* may alias grads_coarse when there is no fine net            */
   float* d_raw_scratch; /* [n, S', 4]                                                  */
   void* workspace;      /* spn_mlp_bwd_workspace_bytes(n*S')                           */
+  int detach_begin;     /* rays [detach_begin, detach_end) of the chunk are rendered with detach_weights=True */
+  int detach_end;       /* (helpers:385-388) in addition to SPN_F_DETACH_WEIGHTS (= all rays); 0,0 = none: lets the  */
+                        /* step's three render calls (run_nerf.py:1455-1470) share one chunk                        */
 } spn_render_grads;
 
 int spn_render_rays_bwd(const spn_render_cfg* cfg, const spn_render_io* io,

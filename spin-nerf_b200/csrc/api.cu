@@ -257,7 +257,7 @@ extern "C" int spn_render_rays_bwd(const spn_render_cfg* c, const spn_render_io*
   if (NI == 0) {
     SPN_CHECK_ARG(io->stash_coarse, "spn_render_rays_bwd: forward ran without a stash");
     RET_IF(composite_bwd(io->raw, io->z_vals, rays_d, c->ncols, noisy ? io->noise0 : nullptr, c->raw_noise_std, n, S,
-                         white, detach, g->g_rgb, g->g_disp, g->g_acc, g->g_weights, g->g_depth, g->d_raw_scratch, st));
+                         white, detach, g->detach_begin, g->detach_end, g->g_rgb, g->g_disp, g->g_acc, g->g_weights, g->g_depth, g->d_raw_scratch, st));
     return spn_mlp_bwd(io->params_coarse, io->packed_coarse, io->stash_coarse, g->d_raw_scratch, (int64_t)n * S,
                        g->grads_coarse, g->workspace, c->precision, stream);
   }
@@ -268,13 +268,13 @@ extern "C" int spn_render_rays_bwd(const spn_render_cfg* c, const spn_render_io*
   SPN_CHECK_ARG(gf, "spn_render_rays_bwd: null grads_fine");
   if (g->g_rgb || g->g_disp || g->g_acc || g->g_weights || g->g_depth) {
     RET_IF(composite_bwd(io->raw, io->z_vals, rays_d, c->ncols, noisy ? io->noise1 : nullptr, c->raw_noise_std, n, S2,
-                         white, detach, g->g_rgb, g->g_disp, g->g_acc, g->g_weights, g->g_depth, g->d_raw_scratch, st));
+                         white, detach, g->detach_begin, g->detach_end, g->g_rgb, g->g_disp, g->g_acc, g->g_weights, g->g_depth, g->d_raw_scratch, st));
     RET_IF(spn_mlp_bwd(pf, kf, io->stash_fine, g->d_raw_scratch, (int64_t)n * S2, gf, g->workspace, c->precision, stream));
   }
   // coarse pass: z_samples are detached (run_nerf.py:700) so only rgb0/disp0/acc0 carry gradient
   if (g->g_rgb0 || g->g_disp0 || g->g_acc0) {
     RET_IF(composite_bwd(io->raw_coarse, io->z_coarse, rays_d, c->ncols, noisy ? io->noise0 : nullptr,
-                         c->raw_noise_std, n, S, white, detach, g->g_rgb0, g->g_disp0, g->g_acc0, nullptr, nullptr,
+                         c->raw_noise_std, n, S, white, detach, g->detach_begin, g->detach_end, g->g_rgb0, g->g_disp0, g->g_acc0, nullptr, nullptr,
                          g->d_raw_scratch, st));
     RET_IF(spn_mlp_bwd(io->params_coarse, io->packed_coarse, io->stash_coarse, g->d_raw_scratch, (int64_t)n * S,
                        g->grads_coarse, g->workspace, c->precision, stream));

@@ -111,9 +111,9 @@ int composite_fwd(const float* raw, const float* z, const float* rays_d, int ld_
                   float noise_scale, int n, int S, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
                   float* weights, float* depth_map, float* alpha, cudaStream_t stream);
 int composite_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise,
-                  float noise_scale, int n, int S, int white_bkgd, int detach_weights, const float* g_rgb,
-                  const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
-                  float* d_raw, cudaStream_t stream);
+                  float noise_scale, int n, int S, int white_bkgd, int detach_weights, int detach_begin, int detach_end,
+                  const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_weights,
+                  const float* g_depth, float* d_raw, cudaStream_t stream);
 
 // ---- kernels implemented in the other translation units -------------------------------------
 // fp32 CUDA-core MLP (mlp_fp32.cu)

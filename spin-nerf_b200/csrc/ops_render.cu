@@ -227,13 +227,14 @@ raw2outputs_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__
 __global__ void __launch_bounds__(256)
 raw2outputs_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                        const float* __restrict__ rays_d, int ld_d, const float* __restrict__ noise,
-                       float noise_scale, int n, int S, int white_bkgd, int detach_weights,
+                       float noise_scale, int n, int S, int white_bkgd, int detach_all, int det0, int det1,
                        const float* __restrict__ g_rgb, const float* __restrict__ g_disp,
                        const float* __restrict__ g_acc, const float* __restrict__ g_w,
                        const float* __restrict__ g_depth, float4* __restrict__ d_raw) {
   int ray = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
   int lane = threadIdx.x % kWarp;
   if (ray >= n) return;
+  const bool detach_weights = detach_all || (ray >= det0 && ray < det1);   // helpers:385-388, per ray
   const float* d = rays_d + (int64_t)ray * ld_d;
   float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   int nch = (S + kWarp - 1) / kWarp;
@@ -559,14 +560,14 @@ extern "C" int spn_raw2outputs_bwd(const float* raw, const float* z, const float
                                    const float* noise, int n, int S, int white_bkgd, int detach_weights,
                                    const float* g_rgb, const float* g_disp, const float* g_acc,
                                    const float* g_weights, const float* g_depth, float* d_raw, void* stream) {
-  return spn::composite_bwd(raw, z, rays_d, ld_d, noise, 1.0f, n, S, white_bkgd, detach_weights, g_rgb, g_disp, g_acc,
+  return spn::composite_bwd(raw, z, rays_d, ld_d, noise, 1.0f, n, S, white_bkgd, detach_weights, 0, 0, g_rgb, g_disp, g_acc,
                             g_weights, g_depth, d_raw, as_stream(stream));
 }
 
 int spn::composite_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise,
-                       float noise_scale, int n, int S, int white_bkgd, int detach_weights, const float* g_rgb,
-                       const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
-                       float* d_raw, cudaStream_t stream) {
+                       float noise_scale, int n, int S, int white_bkgd, int detach_weights, int detach_begin,
+                       int detach_end, const float* g_rgb, const float* g_disp, const float* g_acc,
+                       const float* g_weights, const float* g_depth, float* d_raw, cudaStream_t stream) {
   if (n == 0) return SPN_OK;
   SPN_CHECK_ARG(raw && z && rays_d && d_raw, "spn_raw2outputs_bwd: null pointer");
   SPN_CHECK_ARG(n >= 0 && S >= 1 && S <= kMaxChunks * 32 && ld_d >= 3,
@@ -574,8 +575,8 @@ int spn::composite_bwd(const float* raw, const float* z, const float* rays_d, in
   SPN_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw) & 15) == 0, "spn_raw2outputs_bwd: raw/d_raw must be 16-byte aligned");
   if (n == 0) return SPN_OK;
   raw2outputs_bwd_kernel<<<blocks_for((int64_t)n * 32, 256), 256, 0, stream>>>(
-      (const float4*)raw, z, rays_d, ld_d, noise, noise_scale, n, S, white_bkgd, detach_weights, g_rgb, g_disp, g_acc,
-      g_weights, g_depth, (float4*)d_raw);
+      (const float4*)raw, z, rays_d, ld_d, noise, noise_scale, n, S, white_bkgd, detach_weights, detach_begin, detach_end,
+      g_rgb, g_disp, g_acc, g_weights, g_depth, (float4*)d_raw);
   SPN_LAUNCH_CHECK("raw2outputs_bwd_kernel");
   return SPN_OK;
 }
@@ -614,6 +615,96 @@ extern "C" int spn_resample(const float* z, const float* weights, const float* u
   resample_kernel<<<blocks_for(n, kPdfWarps), kPdfWarps * 32, 0, as_stream(stream)>>>(z, weights, u, n, S, n_imp,
                                                                                     z_out, z_samples, z_std, inds);
   SPN_LAUNCH_CHECK("resample_kernel");
+  return SPN_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// train-step losses (run_nerf.py:1481-1521, default flags) for a batch that concatenates the step's three ray
+// groups: [0,n1) unmasked rays and [n1,n1+n2) masked rays of the kept view -> img2mse(rgb, target) + img2mse(rgb0,
+// target) per group; [n1+n2, n) inpainted-disparity rays -> img2mse(disp, target) + img2mse(disp0, target), dropped
+// (loss and gradient) when NaN (`if not inp_loss.isnan()`, :1520).  Two launches: sums, then gradients + scalars.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+train_loss_sums_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ disp,
+                       const float* __restrict__ disp0, const float* __restrict__ tgt_rgb,
+                       const float* __restrict__ tgt_disp, int n1, int n2, int n3, float* __restrict__ sums) {
+  // element space: 3*(n1+n2) colour entries, then n3 disparity entries
+  const int ncol = 3 * (n1 + n2), total = ncol + n3;
+  float s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < ncol) {
+      const float t = tgt_rgb[i], a = rgb[i] - t, b = rgb0[i] - t;
+      const int k = i < 3 * n1 ? 0 : 2;
+      s[k] += a * a; s[k + 1] += b * b;
+    } else {
+      const int r = i - ncol;
+      const float t = tgt_disp[r], a = disp[n1 + n2 + r] - t, b = disp0[n1 + n2 + r] - t;
+      s[4] += a * a; s[5] += b * b;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float v = warp_sum(s[k]);
+    if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(sums + k, v);
+    if ((threadIdx.x & 31) == 0 && v != v) atomicAdd(sums + k, v);   // NaN must reach the sum
+  }
+}
+
+__global__ void __launch_bounds__(256)
+train_loss_grads_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ disp,
+                        const float* __restrict__ disp0, const float* __restrict__ tgt_rgb,
+                        const float* __restrict__ tgt_disp, int n1, int n2, int n3, const float* __restrict__ sums,
+                        float* __restrict__ g_rgb, float* __restrict__ g_rgb0, float* __restrict__ g_disp,
+                        float* __restrict__ g_disp0, float* __restrict__ out) {
+  const int n = n1 + n2 + n3, ncol = 3 * n;
+  const float ld = n3 > 0 ? sums[4] / n3 : 0.0f, ld0 = n3 > 0 ? sums[5] / n3 : 0.0f;
+  const bool bad = (ld + ld0) != (ld + ld0);
+  const float c1 = n1 > 0 ? 2.0f / (3.0f * n1) : 0.0f, c2 = n2 > 0 ? 2.0f / (3.0f * n2) : 0.0f;
+  const float c3 = (n3 > 0 && !bad) ? 2.0f / n3 : 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncol + n; i += gridDim.x * blockDim.x) {
+    if (i < ncol) {
+      float a = 0.0f, b = 0.0f;
+      if (i < 3 * (n1 + n2)) {
+        const float t = tgt_rgb[i], c = i < 3 * n1 ? c1 : c2;
+        a = c * (rgb[i] - t); b = c * (rgb0[i] - t);
+      }
+      g_rgb[i] = a; g_rgb0[i] = b;
+    } else {
+      const int r = i - ncol;
+      float a = 0.0f, b = 0.0f;
+      if (r >= n1 + n2 && c3 != 0.0f) {
+        const float t = tgt_disp[r - n1 - n2];
+        a = c3 * (disp[r] - t); b = c3 * (disp0[r] - t);
+      }
+      g_disp[r] = a; g_disp0[r] = b;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float l0 = n1 > 0 ? sums[0] / (3.0f * n1) : 0.0f, l1 = n1 > 0 ? sums[1] / (3.0f * n1) : 0.0f;
+    const float l2 = n2 > 0 ? sums[2] / (3.0f * n2) : 0.0f, l3 = n2 > 0 ? sums[3] / (3.0f * n2) : 0.0f;
+    out[0] = l0 + l1 + l2 + l3 + (bad ? 0.0f : ld + ld0);   // the step's loss
+    out[1] = -10.0f * log10f(l0);                           // psnr of the unmasked fine rgb (mse2psnr)
+    out[2] = l0; out[3] = l1; out[4] = l2; out[5] = l3; out[6] = bad ? 0.0f : ld; out[7] = bad ? 0.0f : ld0;
+  }
+}
+
+extern "C" int spn_train_losses(const float* rgb_map, const float* rgb0, const float* disp_map, const float* disp0,
+                                const float* target_rgb, const float* target_disp, int n1, int n2, int n3,
+                                float* sums6_zeroed, float* g_rgb, float* g_rgb0, float* g_disp, float* g_disp0,
+                                float* out8, void* stream) {
+  SPN_CHECK_ARG(rgb_map && rgb0 && disp_map && disp0 && sums6_zeroed && g_rgb && g_rgb0 && g_disp && g_disp0 && out8 &&
+                n1 >= 0 && n2 >= 0 && n3 >= 0 && (n1 + n2 == 0 || target_rgb) && (n3 == 0 || target_disp),
+                "spn_train_losses: bad arguments");
+  const int n = n1 + n2 + n3;
+  if (n == 0) return SPN_OK;
+  cudaStream_t st = as_stream(stream);
+  const int blocks = blocks_for((int64_t)4 * n, 256) < 296 ? blocks_for((int64_t)4 * n, 256) : 296;
+  train_loss_sums_kernel<<<blocks, 256, 0, st>>>(rgb_map, rgb0, disp_map, disp0, target_rgb, target_disp, n1, n2, n3, sums6_zeroed);
+  SPN_LAUNCH_CHECK("train_loss_sums_kernel");
+  train_loss_grads_kernel<<<blocks, 256, 0, st>>>(rgb_map, rgb0, disp_map, disp0, target_rgb, target_disp, n1, n2, n3,
+                                                 sums6_zeroed, g_rgb, g_rgb0, g_disp, g_disp0, out8);
+  SPN_LAUNCH_CHECK("train_loss_grads_kernel");
   return SPN_OK;
 }
 

@@ -76,9 +76,10 @@ def chunk_forward(opts, rays, net_c, net_f, t_rand=None, u=None, noise0=None, no
     return cfg, keep
 
 
-def chunk_backward(cfg, keep, net_c, net_f, g, gc, gf, scratch=None, ws=None):
+def chunk_backward(cfg, keep, net_c, net_f, g, gc, gf, scratch=None, ws=None, detach_range=(0, 0)):
     """spn_render_rays_bwd: accumulates d(loss)/d(params) into the flat buffers gc / gf.
-    g: dict output-name -> upstream gradient tensor (missing = zero)."""
+    g: dict output-name -> upstream gradient tensor (missing = zero).  detach_range: rays [a, b) of the chunk that the
+    caller rendered with detach_weights=True (run_nerf_helpers.py:385-388) when several render calls share the chunk."""
     dev = keep["rays"].device
     n, S2 = cfg.n_rays, cfg.n_samples + cfg.n_importance
     io, hold = _bind_io(keep, net_c, net_f)
@@ -95,6 +96,7 @@ def chunk_backward(cfg, keep, net_c, net_f, g, gc, gf, scratch=None, ws=None):
         ws = ops.mlp_bwd_workspace(n * S2, cfg.precision, dev)
     gr.grads_coarse, gr.grads_fine = ptr(gc), ptr(gf)
     gr.d_raw_scratch, gr.workspace = ptr(scratch), ptr(ws)
+    gr.detach_begin, gr.detach_end = int(detach_range[0]), int(detach_range[1])
     check(lib().spn_render_rays_bwd(C.byref(cfg), C.byref(io), C.byref(gr), stream()), "spn_render_rays_bwd")
 
 

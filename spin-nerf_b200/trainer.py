@@ -77,7 +77,45 @@ class Trainer:
 
     def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
         """One optimisation step on this rank's shard of the three ray batches.  Returns the (local) loss and
-        psnr like run_nerf.py:1481-1521 defines them for the default flags."""
+        psnr like run_nerf.py:1481-1521 defines them for the default flags.
+
+        The reference renders the three batches with three render() calls (run_nerf.py:1455-1470); rays are
+        independent, so here they are concatenated into ONE chunk: one sampling / MLP / compositing pass forward and
+        one backward over 3x the rays (fewer, fuller kernel launches).  What differs between the calls — which loss
+        a ray feeds and detach_weights=True for the masked rays — is applied per ray range (spn_train_losses,
+        spn_render_grads.detach_begin/end)."""
+        sh = self.sharder
+        rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
+        rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
+        rays_inp, depth_inp = sh.shard(rays_inp, 1), sh.shard(depth_inp)
+        n1, n2, n3 = rays_clf.shape[1], rays_s.shape[1], rays_inp.shape[1]
+        n = n1 + n2 + n3
+        P = self.shared
+        rays = P("rays_cat", (2, n, 3), torch.float32)
+        torch.cat([rays_clf, rays_s, rays_inp], 1, out=rays)
+        tgt_rgb = P("tgt_rgb", (n1 + n2, 3), torch.float32)
+        torch.cat([target_clf, target_s], 0, out=tgt_rgb)
+        cfg, k = self._forward(0, rays, False)
+        g_rgb, g_rgb0 = P("g_rgb", (n, 3), torch.float32), P("g_rgb0", (n, 3), torch.float32)
+        g_disp, g_disp0 = P("g_disp", (n,), torch.float32), P("g_disp0", (n,), torch.float32)
+        sums, out = P("loss_sums", (8,), torch.float32), P("loss_out", (8,), torch.float32)
+        sums.zero_()
+        L.check(L.lib().spn_train_losses(L.ptr(k["rgb_map"]), L.ptr(k["rgb0"]), L.ptr(k["disp_map"]), L.ptr(k["disp0"]),
+                                         L.ptr(tgt_rgb), L.ptr(L.f32(depth_inp)), n1, n2, n3, L.ptr(sums), L.ptr(g_rgb),
+                                         L.ptr(g_rgb0), L.ptr(g_disp), L.ptr(g_disp0), L.ptr(out), L.stream()),
+                "spn_train_losses")
+        for g in self.grads:
+            g.zero_()
+        gc, gf = self.grads
+        chunk_backward(cfg, k, self.net_c, self.net_f,
+                       {"rgb_map": g_rgb, "rgb0": g_rgb0, "disp_map": g_disp, "disp0": g_disp0}, gc, gf,
+                       self._scratch(cfg), self._ws(cfg), detach_range=(n1, n1 + n2))
+        self.apply_gradients()
+        res = out[:2].clone()          # `out` is a pooled buffer: hand back copies of (loss, psnr)
+        return res[0], res[1]
+
+    def step_three_calls(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
+        """The same step as three separate render calls, exactly in the reference's order (kept for parity tests)."""
         sh = self.sharder
         rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
         rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)

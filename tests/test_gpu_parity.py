@@ -459,6 +459,40 @@ def test_train_step_bf16_tracks_reference():
         opt.step()
 
 
+@pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
+def test_trainer_batched_step_equals_three_render_calls(prec_name):
+    """Trainer.step renders the step's three ray batches as ONE chunk (per-ray-range losses and detach_weights);
+    it must produce the gradients, loss and parameters of the three separate render calls of run_nerf.py:1455-1521."""
+    trainer_mod = __import__("importlib").import_module("spin-nerf_b200.trainer")
+    prec = spn.PREC_FP32 if prec_name == "fp32" else spn.PREC_BF16
+    g = load_golden("render")
+    rng = np.random.default_rng(5)
+    rays = g["rays"]                                           # [2, n, 3]
+    n = rays.shape[1]
+    sel = [rng.permutation(n)[:m] for m in (96, 64, 80)]       # three batches of different sizes
+    batches = []
+    for i, ix in enumerate(sel):
+        batches.append(T(np.ascontiguousarray(rays[:, ix])))
+        batches.append(T(rng.uniform(0, 1, (len(ix), 3) if i < 2 else (len(ix),)).astype(np.float32)))
+    out = []
+    for mode in ("batched", "three"):
+        netc, _ = make_net(11, prec, 1.0); netf, _ = make_net(12, prec, 1.0)
+        tr = trainer_mod.Trainer(netc, netf, lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                                 perturb=0.0, raw_noise_std=0.0, near=1.2, far=8.0)
+        fn = tr.step if mode == "batched" else tr.step_three_calls
+        loss, psnr = fn(*batches)
+        torch.cuda.synchronize()
+        out.append((float(loss), float(psnr), N(tr.grads[0]), N(tr.grads[1]), N(netc.flat_params()), N(netf.flat_params())))
+    a, b = out
+    assert abs(a[0] - b[0]) <= 1e-5 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-4 * abs(b[1]), (a[:2], b[:2])
+    tol = 1e-5 if prec_name == "fp32" else 2e-3              # bf16: tile boundaries move, tensor-core sums reorder
+    for ga, gb in ((a[2], b[2]), (a[3], b[3])):
+        assert np.abs(gb).max() > 0
+        assert np.abs(ga - gb).max() <= tol * np.abs(gb).max(), np.abs(ga - gb).max() / np.abs(gb).max()
+    for pa, pb in ((a[4], b[4]), (a[5], b[5])):
+        assert np.abs(pa - pb).max() <= 2e-3 * 5e-4 + (0 if prec_name == "fp32" else 1e-3)   # Adam steps are +-lr sized
+
+
 def test_render_bf16_psnr_vs_reference():
     g = load_golden("render")
     H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
