@@ -91,7 +91,7 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(spin-nerf_b200/csrc/build.sh).  There is no CPU / PyTorch fallback for this path.")
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(os.environ.get("SPN_LIB_OVERRIDE", LIB_PATH))   # override: A/B timing of experimental builds only
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)      # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args

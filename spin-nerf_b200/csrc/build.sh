@@ -2,10 +2,10 @@
 # Builds libspinnerf_b200.so (sm_100a only) in-tree next to this script's package.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libspinnerf_b200.so"
+OUT="${SPN_LIB_OUT:-$HERE/../libspinnerf_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH=(-gencode arch=compute_100a,code=sm_100a)
-FLAGS=(-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v)
+FLAGS=(-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v ${SPN_EXTRA_NVCC_FLAGS:-})
 SRCS=(api ops_render mlp_fp32 mlp_tc mlp_tc_bwd)
 mkdir -p "$HERE/obj"
 pids=()

@@ -37,14 +37,14 @@ static int check_arch_bwd() {
   return SPN_OK;
 }
 
-static inline int64_t even_tiles(int64_t m) { return (m + 2 * kTileM - 1) / (2 * kTileM) * 2; }
+static inline int64_t quad_tiles(int64_t m) { return (m + 4 * kTileM - 1) / (4 * kTileM) * 4; }   // a CTA pair works on 4 tiles
 constexpr int kWgMaxCtas = 192;   // >= SM count of any sm_100 part
 size_t mlp_tc_bwd_ws_bytes(int64_t m) {
-  return (size_t)even_tiles(m) * kDstashTileBytes + (size_t)kWgMaxCtas * 256 * 256 * sizeof(float) + 256;
+  return (size_t)quad_tiles(m) * kDstashTileBytes + (size_t)kWgMaxCtas * 256 * 256 * sizeof(float) + 256;
 }
 
 // =====================================================================================================
-// dgrad
+// dgrad: CTA pairs (cta_group::2), same skeleton as the forward kernel (mlp_tc.cu: ring, barriers, roles)
 // =====================================================================================================
 constexpr int kDgSteps = 9;
 __constant__ int c_dg_chunks[kDgSteps] = {2, 4, 4, 4, 4, 4, 4, 4, 4};
@@ -59,109 +59,154 @@ struct DgradParams {
   const float* d_raw;
   uint8_t* dstash;
   int64_t m;
-  int num_pairs;
-  int piece;        // bytes per cp.async.bulk of the weight producer
+  int num_quads;
 };
 
-// 16 columns of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask (16 bits) -> bf16 -> A operand of the next GEMM
-__device__ __forceinline__ void dg_cols16(const uint32_t (&v)[16], int col0, uint32_t mb, float dalpha, bool add_alpha,
-                                          const float* __restrict__ cst, uint8_t* act, int r) {
+// 32 accumulator columns of a dgrad epilogue: (+ d_sigma * Wa) -> ReLU mask (bit = column) -> bf16 -> A operand of the
+// next GEMM.   wa_a: shared address of this thread's first bf16 sigma weight    row_a / rx: as in the forward epilogue
+template <bool kAlpha>
+__device__ __forceinline__ void dg_cols32(const uint32_t (&v)[32], const int cl, const uint32_t mb, const float dalpha,
+                                          const uint32_t wa_a, const uint32_t row_a, const uint32_t rx) {
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int col = col0 + g * 8;
+  for (int g = 0; g < 4; ++g) {
+    const int c = cl + g * 8;
     float h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = __uint_as_float(v[g * 8 + e]);
-    if (add_alpha) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(cst + C_WA + col + 4));
-      h[0] = fmaf(dalpha, w0.x, h[0]); h[1] = fmaf(dalpha, w0.y, h[1]); h[2] = fmaf(dalpha, w0.z, h[2]); h[3] = fmaf(dalpha, w0.w, h[3]);
-      h[4] = fmaf(dalpha, w1.x, h[4]); h[5] = fmaf(dalpha, w1.y, h[5]); h[6] = fmaf(dalpha, w1.z, h[6]); h[7] = fmaf(dalpha, w1.w, h[7]);
+    if (kAlpha) {
+      const uint4 wq = lds128u(wa_a + c * 2);
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        h[e] = fmaf(dalpha, __uint_as_float(ww[e / 2] << 16), h[e]);
+        h[e + 1] = fmaf(dalpha, __uint_as_float(ww[e / 2] & 0xffff0000u), h[e + 1]);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) h[e] = ((mb >> (g * 8 + e)) & 1u) ? h[e] : 0.f;
-    const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-    *reinterpret_cast<uint4*>(act + (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
+    sts128(row_a + (uint32_t)(c / 64) * kAtomBytes + ((uint32_t)(((c % 64) / 8) << 4) ^ rx), pack_bf16(h[0], h[1]),
+           pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParams p) {
+template <bool kAlpha>
+__device__ __forceinline__ void dg_layer(const uint32_t tmem_a, const uint32_t (&mw)[4], const float dalpha, const uint32_t wa_a,
+                                         const uint32_t row_a, const uint32_t rx) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(tmem_a, va);
+  tmem_ld32(tmem_a + 32, vb);
+  tmem_ld_wait_dep(va);
+  tmem_ld_wait_dep(vb);
+  dg_cols32<kAlpha>(va, 0, mw[0], dalpha, wa_a, row_a, rx);
+  tmem_ld32(tmem_a + 64, va);
+  dg_cols32<kAlpha>(vb, 32, mw[1], dalpha, wa_a, row_a, rx);
+  tmem_ld32(tmem_a + 96, vb);
+  tmem_ld_wait_dep(va);
+  tmem_ld_wait_dep(vb);
+  dg_cols32<kAlpha>(va, 64, mw[2], dalpha, wa_a, row_a, rx);
+  dg_cols32<kAlpha>(vb, 96, mw[3], dalpha, wa_a, row_a, rx);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp_dgrad_kernel(const DgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
   if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack
-  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 16;
+  // barriers as in mlp_fwd_kernel: group_full[2][4] (step counter % 4), empty[3], acc_full[2], act_ready[2]
+  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 64;
+  const uint32_t bar_acc = bar_empty + 8 * kSlots, bar_act = bar_acc + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
+  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
+  const uint32_t wr_s = sbase + SM_BIAS;        // rgb-head weights [3][128] fp32 (the bias rows are unused here)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, kEpiThreads); }
+    for (int s = 0; s < kSlots; ++s) mbar_init(bar_empty + 8 * s, 1);
+    for (int b = 0; b < 8; ++b) mbar_init(bar_full + 8 * b, rank == 0 ? 2 : 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 2 * kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc2(smem_u32(tmem_ptr_smem), 512); tmem_relinquish2(); }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
+    const int i = threadIdx.x - 64;
+    const __nv_bfloat16 w = __float2bfloat16_rn(__ldg(cst + C_WA + i));          // the forward's bf16 sigma weights
+    sts16(sbase + SM_WA + 2 * i, *reinterpret_cast<const uint16_t*>(&w));
+    sts32f(wr_s + 4 * i, __ldg(cst + C_WR + i));
+    if (i < 128) sts32f(wr_s + 4 * (256 + i), __ldg(cst + C_WR + 256 + i));
+  }
   tcgen05_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
-  const int my_pairs = (p.num_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+  const int my_rounds = (p.num_quads - cid + ncl - 1) / ncl;
 
   if (warp == 0) {
-    // ---- weight producer (transposed images): 16 KB pieces, one issuing lane per (ring stage, piece) — see mlp_tc.cu
-    const uint32_t piece = (uint32_t)p.piece;
-    const int npieces = (int)(kChunkBig / piece);
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < my_pairs; ++it) {
+    // ---- weight producer: this CTA's half (128 of 256 rows) of every transposed chunk; groups of two chunks per ring slot
+    uint32_t stage = 0, phase = 0, gs = 0;
+    for (int it = 0; it < my_rounds; ++it) {
       const uint8_t* src = p.packed + kFwdBytes;
-      for (int s = 0; s < kDgSteps; ++s) {
-        for (int t = 0; t < 2; ++t) {
-          const uint8_t* sp = src;
-          for (int c = 0; c < c_dg_chunks[s]; ++c) {
-            if (lane == 0) {
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(bar_full + 8 * stage, kChunkBig);
+      for (int s = 0; s < kDgSteps; ++s, ++gs) {
+        const int nch = c_dg_chunks[s];
+        for (int g = 0; 2 * g < nch; ++g) {
+          const int sub = lane >= kSlots ? 1 : 0;
+          if (lane == (int)stage || lane == (int)stage + kSlots) {
+            const uint32_t gbar = bar_full + 8 * (gs & 3) + 32 * g;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);       // both lanes, every release (see mlp_fwd_kernel)
+            if (sub == 0) {
+              mbar_arrive_expect_tx(gbar, 2u * (kChunkBig / 2));
+              if (g == 0 && nch <= 2) mbar_arrive(gbar + 32);
             }
-            __syncwarp();
-            const int pi = lane - (int)stage * npieces;
-            if (pi >= 0 && pi < npieces)
-              bulk_g2s(sbase + SM_RING + stage * kChunkBig + pi * piece, sp + pi * piece, piece, bar_full + 8 * stage);
-            sp += kChunkBig;
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            bulk_g2s(sbase + SM_RING + stage * kSlotBytes + sub * (kSlotBytes / 2),
+                     src + (size_t)(2 * g + sub) * kChunkBig + (size_t)rank * (kChunkBig / 2), kChunkBig / 2, gbar);
           }
+          if (++stage == kSlots) { stage = 0; phase ^= 1; }
         }
-        src += (size_t)c_dg_chunks[s] * kChunkBig;
+        src += (size_t)nch * kChunkBig;
       }
     }
+  } else if (warp == 1 && rank != 0) {
+    if (lane == 0) {   // ---- peer: relay "my halves of this group have landed" to the leader's group barrier
+      const uint32_t full_leader = mapa_cluster(bar_full, 0);
+      uint32_t gs = 0;
+      for (int it = 0; it < my_rounds; ++it)
+        for (int s = 0; s < kDgSteps; ++s, ++gs)
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(bar_full + 32 * g + 8 * (gs & 3), (gs >> 2) & 1u);
+            mbar_arrive_cluster(full_leader + 32 * g + 8 * (gs & 3));
+          }
+    }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer
-      uint32_t stage = 0, phase = 0;
+    if (lane == 0) {   // ---- leader: MMA issuer for the pair
+      uint32_t grp = 0, gs = 0;
       uint32_t act_phase[2] = {0, 0};
-      const uint32_t idesc = make_idesc(kTileM, 256, 0, 0);
-      for (int it = 0; it < my_pairs; ++it) {
-        for (int s = 0; s < kDgSteps; ++s) {
+      const uint32_t idesc = make_idesc(2 * kTileM, 256, 0, 0);
+      for (int it = 0; it < my_rounds; ++it) {
+        for (int s = 0; s < kDgSteps; ++s, ++gs) {
           const int nch = c_dg_chunks[s];
+          const uint32_t lph = (gs >> 2) & 1u, gbar = bar_full + 8 * (gs & 3);
+          mbar_wait_cluster(gbar, lph);
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(bar_act + 8 * t, act_phase[t]);
+            mbar_wait_cluster(bar_act + 8 * t, act_phase[t]);
             act_phase[t] ^= 1;
             tcgen05_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             uint32_t accumulate = 0;
             for (int c = 0; c < nch; ++c) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              tcgen05_fence_after_sync();
+              const uint32_t stage = (grp + (uint32_t)(c >> 1)) % kSlots;
+              if (t == 0 && c == 2) { mbar_wait_cluster(gbar + 32, lph); tcgen05_fence_after_sync(); }
               const uint64_t a_desc = make_smem_desc(sbase + SM_ACT + t * kActBytes + c * kAtomBytes, 16, 1024);
-              const uint64_t b_desc = make_smem_desc(sbase + SM_RING + stage * kChunkBig, 16, 1024);
+              const uint64_t b_desc = make_smem_desc(sbase + SM_RING + stage * kSlotBytes + (c & 1) * (kSlotBytes / 2), 16, 1024);
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
                 accumulate = 1;
               }
-              umma_commit(bar_empty + 8 * stage);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (t == 1 && ((c & 1) || c == nch - 1)) umma_commit_2cta(bar_empty + 8 * stage, 3);
             }
-            umma_commit(bar_acc + 8 * t);
+            umma_commit_2cta(bar_acc + 8 * t, 3);
           }
+          grp += (uint32_t)((nch + 1) >> 1);
         }
       }
     }
@@ -172,51 +217,61 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
     const int cg = (ew >> 2) & 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    uint8_t* act = smem + SM_ACT + t * kActBytes;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    const uint32_t act_a = sbase + SM_ACT + t * kActBytes;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    const uint32_t row_a = act_a + (uint32_t)cg * 2u * kAtomBytes + (uint32_t)r * 128u;
+    const uint32_t wa_a = sbase + SM_WA + (uint32_t)cg * 256u;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u + (uint32_t)cg * 128u;
+    const uint32_t act_leader = mapa_cluster(bar_act + 8 * t, 0);
+    const bool store_lane = lane == 0 && cg == 0;             // issues this warp's 16 KB dstash stores
     uint32_t acc_phase = 0;
-    for (int it = 0; it < my_pairs; ++it) {
-      const int64_t tile = 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + t;
+    for (int it = 0; it < my_rounds; ++it) {
+      const int64_t tile = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank + t;
       const int64_t row = tile * kTileM + r;
       const bool live = row < p.m;
       const uint8_t* stash_tile = p.stash + (size_t)tile * kStashTileBytes;
       uint8_t* dst_tile = p.dstash + (size_t)tile * kDstashTileBytes;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(stash_tile + kStashMaskOff);
       // prologue: d_hv = (d_rgb . Wr) * (hv > 0)   [128 wide, 64 columns per half]  -> A atoms 0-1 and dstash atoms 0-1
-      float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0 && cg == 0) bulk_wait_read0();   // previous tile's last dstash stores have left shared memory
+      const float4 dr = live ? *reinterpret_cast<const float4*>(p.d_raw + row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint2 mk = *reinterpret_cast<const uint2*>(masks + (8 * 128 + r) * 8 + cg * 2);
+      named_bar_sync(1 + t, kEpiThreads);      // the previous round's last dstash store was issued ...
+      if (store_lane) bulk_wait_read0();       // ... and has finished reading the tile (all four issuing lanes wait)
       named_bar_sync(1 + t, kEpiThreads);
       {
-        const uint2 mk = *reinterpret_cast<const uint2*>(masks + (8 * 128 + r) * 8 + cg * 2);
         const uint32_t mw2[2] = {mk.x, mk.y};
-#pragma unroll 1
+#pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
-          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const int col = cg * 64 + cb * 32 + j;
-            float v0 = dr.x * __ldg(cst + C_WR + col) + dr.y * __ldg(cst + C_WR + 128 + col) + dr.z * __ldg(cst + C_WR + 256 + col);
-            float v1 = dr.x * __ldg(cst + C_WR + col + 1) + dr.y * __ldg(cst + C_WR + 129 + col) + dr.z * __ldg(cst + C_WR + 257 + col);
-            v0 = ((mw2[cb] >> j) & 1u) ? v0 : 0.f;
-            v1 = ((mw2[cb] >> (j + 1)) & 1u) ? v1 : 0.f;
-            pk[j / 2] = pack_bf16(v0, v1);
-          }
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int col = cg * 64 + cb * 32 + g8 * 8;       // column of d_hv (0..127)
+            float v[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = cg * 64 + cb * 32 + g * 8;
-            const uint32_t off = (uint32_t)(col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8);
-            *reinterpret_cast<uint4*>(act + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int e = 0; e < 8; e += 4) {
+              const float4 w0 = lds128f(wr_s + 4 * (col + e)), w1 = lds128f(wr_s + 4 * (128 + col + e)),
+                           w2 = lds128f(wr_s + 4 * (256 + col + e));
+              v[e + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+              v[e + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+              v[e + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+              v[e + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = ((mw2[cb] >> (g8 * 8 + e)) & 1u) ? v[e] : 0.f;
+            sts128(act_a + (uint32_t)(col / 64) * kAtomBytes + sw128_off((uint32_t)r, (uint32_t)((col % 64) / 8)),
+                   pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_act + 8 * t);
-        named_bar_sync(1 + t, kEpiThreads);      // tile rows complete -> stream them to the dstash
-        if (lane == 0 && cg == 0 && q < 2) {     // one 16 KB atom per warp: bulk-copy issue is serialised per thread
-          bulk_s2g(dst_tile + (size_t)(DA_HV + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
-          bulk_commit();
         }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(act_leader);
+      int pending_atom = DA_HV, pending_n = 2;                  // d_hv: atoms 0-1 of the tile
       for (int s = 0; s < kDgSteps; ++s) {
+        named_bar_sync(1 + t, kEpiThreads);                     // the whole group has written the previous output
+        if (store_lane && q < pending_n) {                      // one 16 KB atom per warp: bulk-copy issue is serialised per thread
+          bulk_s2g(dst_tile + (size_t)(pending_atom + q) * kAtomBytes, act_a + q * kAtomBytes, kAtomBytes);
+          bulk_commit();
+        }
         // the step's ReLU mask words are fetched while its MMAs are still running (no L1 left: every load is an L2 trip)
         const int mslot = c_dg_mask[s];
         uint32_t mw[4] = {~0u, ~0u, ~0u, ~0u};
@@ -224,44 +279,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
           const uint4 m0 = *reinterpret_cast<const uint4*>(masks + (mslot * 128 + r) * 8 + cg * 4);
           mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
         }
+        if (store_lane && q < pending_n) bulk_wait_read0();     // the store has finished READING the tile we overwrite
+        named_bar_sync(1 + t, kEpiThreads);
         mbar_wait(bar_acc + 8 * t, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after_sync();
-        if (lane == 0 && cg == 0) bulk_wait_read0();   // the previous stores have finished reading the tile we overwrite
-        named_bar_sync(1 + t, kEpiThreads);
-        const float dalpha = (s == 1) ? dr.w : 0.f;     // d_h7 += d_sigma * Wa  (alpha_linear, helpers:113)
-        const int dst_atom = c_dg_dst[s];
-        const bool last = s == kDgSteps - 1;
-        const int c0 = cg * 128;
-        uint32_t va[16], vb[16];
-        tmem_ld16(tmem_lane + c0, va);
-#pragma unroll
-        for (int sb = 0; sb < 8; sb += 2) {      // 16-column TMEM loads, double-buffered
-          tmem_ld_wait_dep16(va);
-          tmem_ld16(tmem_lane + c0 + (sb + 1) * 16, vb);
-          dg_cols16(va, c0 + sb * 16, mw[sb / 2] & 0xffffu, dalpha, s == 1, cst, act, r);
-          tmem_ld_wait_dep16(vb);
-          if (sb + 2 < 8) tmem_ld16(tmem_lane + c0 + (sb + 2) * 16, va);
-          dg_cols16(vb, c0 + (sb + 1) * 16, mw[sb / 2] >> 16, dalpha, s == 1, cst, act, r);
-        }
+        if (s == 1) dg_layer<true>(tmem_lane, mw, dr.w, wa_a, row_a, rx);   // d_h7 += d_sigma * Wa (alpha_linear, helpers:113)
+        else dg_layer<false>(tmem_lane, mw, 0.f, wa_a, row_a, rx);
         tcgen05_fence_before_sync();
         fence_proxy_async_smem();
-        if (!last) mbar_arrive(bar_act + 8 * t);
-        named_bar_sync(1 + t, kEpiThreads);
-        if (lane == 0 && cg == 0) {
-          bulk_s2g(dst_tile + (size_t)(dst_atom + q) * kAtomBytes, smem_u32(act) + q * kAtomBytes, kAtomBytes);
-          bulk_commit();
-        }
+        __syncwarp();
+        if (s != kDgSteps - 1 && lane == 0) mbar_arrive_cluster(act_leader);
+        pending_atom = c_dg_dst[s]; pending_n = 4;
       }
-      if (lane == 0 && cg == 0) bulk_wait0();    // dstash complete before the kernel can exit
+      // the last layer's output (d_h0) is streamed out at the top of the next round / below
+      named_bar_sync(1 + t, kEpiThreads);
+      if (store_lane) {
+        bulk_s2g(dst_tile + (size_t)(pending_atom + q) * kAtomBytes, act_a + q * kAtomBytes, kAtomBytes);
+        bulk_commit();
+      }
     }
+    if (store_lane) bulk_wait0();    // dstash complete before the kernel can exit
   }
+  __syncwarp();
   tcgen05_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
-    __syncwarp();
     tcgen05_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -269,8 +314,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_kernel(const DgradParam
 // wgrad
 // =====================================================================================================
 constexpr int kWgUnits = 12;
-constexpr int kWgStages = 6;
-constexpr int kWgSlabRows = 32;                 // samples per pipeline stage
+#ifndef SPN_WG_SLAB_ROWS
+#define SPN_WG_SLAB_ROWS 64   // 8 KB bulk pieces: 2.54 -> 2.18 ms per 2^20 samples vs 32-row slabs (tools/bench_bwd.py)
+#endif
+constexpr int kWgSlabRows = SPN_WG_SLAB_ROWS;   // samples per pipeline stage
+constexpr int kWgStages = 192 / kWgSlabRows;    // 192 KB ring
 constexpr int kWgSlabBytes = kWgSlabRows * 128; // one atom's slab: 4 KB
 constexpr int kWgStageBytes = 8 * kWgSlabBytes; // 4 A slabs + 4 B slabs = 32 KB
 constexpr int kWgThreads = 192;
@@ -364,8 +412,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
       // ---- producer: 32-sample slabs of dpre (A) and layer input (B).  Each of the <= 8 slab copies of a stage is
       //      issued by its own lane (one thread retires at most one cp.async.bulk per ~700 cycles, tools/bulk_rate.py)
       for (int64_t sl = 0; sl < nslabs; ++sl) {
-        const int64_t tile = t0 + sl / 4;
-        const int j = (int)(sl % 4);
+        const int64_t tile = t0 + sl / (kTileM / kWgSlabRows);
+        const int j = (int)(sl % (kTileM / kWgSlabRows));
         if (lane == 0) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (p.debug & 4) mbar_arrive(bar_full + 8 * stage);
@@ -422,18 +470,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
         mbar_wait(bar_full + 8 * stage, phase);
         if (do_bias && !(p.debug & 2)) {
           const uint32_t abase = sbase + stage * kWgStageBytes + (j >> 3) * kWgSlabBytes;
-          uint4 w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t addr = abase + sw128_off((uint32_t)(rg * 8 + i), (uint32_t)(j & 7));
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(addr));
-          }
+          for (int sub = 0; sub < kWgSlabRows / 32; ++sub) {
+            uint4 w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            bs[0] += __uint_as_float(w[i].x << 16); bs[1] += __uint_as_float(w[i].x & 0xffff0000u);
-            bs[2] += __uint_as_float(w[i].y << 16); bs[3] += __uint_as_float(w[i].y & 0xffff0000u);
-            bs[4] += __uint_as_float(w[i].z << 16); bs[5] += __uint_as_float(w[i].z & 0xffff0000u);
-            bs[6] += __uint_as_float(w[i].w << 16); bs[7] += __uint_as_float(w[i].w & 0xffff0000u);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t addr = abase + sw128_off((uint32_t)(sub * 32 + rg * 8 + i), (uint32_t)(j & 7));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(addr));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              bs[0] += __uint_as_float(w[i].x << 16); bs[1] += __uint_as_float(w[i].x & 0xffff0000u);
+              bs[2] += __uint_as_float(w[i].y << 16); bs[3] += __uint_as_float(w[i].y & 0xffff0000u);
+              bs[4] += __uint_as_float(w[i].z << 16); bs[5] += __uint_as_float(w[i].z & 0xffff0000u);
+              bs[6] += __uint_as_float(w[i].w << 16); bs[7] += __uint_as_float(w[i].w & 0xffff0000u);
+            }
           }
         }
         mbar_arrive(bar_empty + 8 * stage);
@@ -568,10 +619,11 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   // 1. dgrad chain
   DgradParams dp;
   dp.packed = (const uint8_t*)packed; dp.stash = (const uint8_t*)stash; dp.d_raw = d_raw;
-  dp.dstash = (uint8_t*)ws; dp.m = m; dp.num_pairs = (int)((tiles + 1) / 2); dp.piece = weight_piece_bytes();
-  int grid = dp.num_pairs < sm_count() ? dp.num_pairs : sm_count();
+  dp.dstash = (uint8_t*)ws; dp.m = m; dp.num_quads = (int)((tiles + 3) / 4);
+  const int pairs = sm_count() / 2;
+  int grid = 2 * (dp.num_quads < pairs ? dp.num_quads : pairs);
   prof_begin(PROF_MLP_DGRAD, st);
-  mlp_dgrad_kernel<<<grid, kThreads, kSmemBytes, st>>>(dp);
+  mlp_dgrad_kernel<<<grid, kPairThreads, kSmemBytes, st>>>(dp);
   prof_end(PROF_MLP_DGRAD, st);
   SPN_LAUNCH_CHECK("mlp_dgrad_kernel");
   // 2. weight / bias gradients of the ten wide layers
@@ -599,7 +651,7 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
     ++assigned;
   }
   const int wgrid = assigned;
-  wp.partial = reinterpret_cast<float*>((uint8_t*)ws + (size_t)even_tiles(m) * kDstashTileBytes);
+  wp.partial = reinterpret_cast<float*>((uint8_t*)ws + (size_t)quad_tiles(m) * kDstashTileBytes);
   static const int wg_debug = getenv("SPN_WG_DEBUG") ? atoi(getenv("SPN_WG_DEBUG")) : 0;
   wp.debug = wg_debug;
   prof_begin(PROF_MLP_WGRAD, st);
