@@ -206,13 +206,17 @@ def main():
 
     flush = torch.empty(64 * 1024 * 1024, device=dev)                         # 256 MB > 126 MB L2
 
+    def pool_step():
+        """device-resident sampler: draw the step's ray indices, gather + assemble the batch in one kernel"""
+        return tr.step_from_pool(pool, rgb_pool, disp_pool, torch.randint(0, M, (3, global_n), device=dev, generator=g))
+
     def run_steps(k, batch_fn, timed):
         ms, evs = 0.0, []
         for _ in range(k):
             flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            loss, psnr = tr.step(*batch_fn())
+            loss, psnr = tr.step(*batch_fn()) if batch_fn is not None else pool_step()
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -220,13 +224,13 @@ def main():
 
     barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
     clocks = ClockSampler(local); clocks.start()         # nvidia-smi needs ~1 s to start streaming samples
-    run_steps(args.warmup, device_batches, False)
+    run_steps(args.warmup, None, False)
     barrier(); torch.cuda.synchronize()
     L = spn._lib.lib()
     L.spn_profile_enable(1); L.spn_launch_count(1)
     clocks.rows.clear()                                   # keep only samples taken during the timed region
     t_wall = time.perf_counter()
-    times, loss = run_steps(args.steps, device_batches, True)
+    times, loss = run_steps(args.steps, None, True)
     torch.cuda.synchronize(); barrier()
     wall = time.perf_counter() - t_wall
     clk = clocks.stop()

@@ -73,6 +73,14 @@ int spn_ndc_rays(int n, int H, int W, float focal, float near_plane, const float
  * [o(3) d(3) near far viewdir(3)], viewdir = d/|d| taken BEFORE the optional NDC map. */
 int spn_build_ray_batch(int n, const float* rays_o, const float* rays_d, float near_, float far_,
                         int ndc, int H, int W, float focal, float* rays, void* stream);
+/* Batch assembly from a device-resident ray pool (what RayDataset.__getitem__ + DataLoader
+ * collation, DS_NeRF/data.py:4-15 / run_nerf.py:1367-1413, and render()'s ray matrix produce for the sampled rays):
+ * row i of rays [n,11] is pool ray idx[i] (int64) laid out like spn_build_ray_batch; the first n_rgb rays also gather
+ * their colour target rgb_pool[idx[i]] -> rgb_out [n_rgb,3], the remaining ones their inpainted-disparity target
+ * disp_pool[idx[i]] -> disp_out [n - n_rgb] (either pool may be NULL). */
+int spn_gather_ray_batch(int n, const float* pool_o, const float* pool_d, const int64_t* idx, float near_, float far_,
+                         int ndc, int H, int W, float focal, float* rays, const float* rgb_pool, float* rgb_out,
+                         int n_rgb, const float* disp_pool, float* disp_out, void* stream);
 
 /* ---- a5  positional encoding (helpers:22-70) -------------------------------------------- */
 /* x [m,3] -> out [m, 3+6*n_freqs] = [x, sin(2^k x), cos(2^k x)...]. */

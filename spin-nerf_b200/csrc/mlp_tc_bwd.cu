@@ -661,7 +661,8 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   prof_end(PROF_MLP_WGRAD, st);
   SPN_LAUNCH_CHECK("mlp_wgrad_reduce_kernel");
   // 3. heads
-  int hgrid = (int)(tiles < 8192 ? tiles : 8192);    // one tile per block: latency hidden by occupancy
+  const int hmax = 8 * sm_count();                    // 8 resident blocks per SM; every block ends with 643 atomics
+  int hgrid = (int)(tiles < hmax ? tiles : hmax);
   mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, d_raw, m, tiles, grads + po.off[T_WR],
                                                 grads + po.off[T_BR], grads + po.off[T_WA], grads + po.off[T_BA]);
   SPN_LAUNCH_CHECK("mlp_heads_wgrad_kernel");

@@ -95,6 +95,36 @@ __global__ void build_ray_batch_kernel(int n, const float* __restrict__ ro,
   r[6] = near_; r[7] = far_;
 }
 
+// batch assembly from a device-resident ray pool: what RayDataset.__getitem__ + DataLoader collation + render()'s ray
+// matrix (data.py:4-15, run_nerf.py:126-153, 1367-1413) produce for N_rand sampled rays, in one launch
+__global__ void gather_ray_batch_kernel(int n, const float* __restrict__ pool_o, const float* __restrict__ pool_d,
+                                        const int64_t* __restrict__ idx, float near_, float far_, int ndc, int H, int W,
+                                        float focal, float* __restrict__ rays, const float* __restrict__ rgb_pool,
+                                        float* __restrict__ rgb_out, int n_rgb, const float* __restrict__ disp_pool,
+                                        float* __restrict__ disp_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t j = idx[i];
+  float o[3] = {pool_o[3 * j], pool_o[3 * j + 1], pool_o[3 * j + 2]};
+  float d[3] = {pool_d[3 * j], pool_d[3 * j + 1], pool_d[3 * j + 2]};
+  float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  float* r = rays + (int64_t)i * 11;
+  r[8] = d[0] / nrm; r[9] = d[1] / nrm; r[10] = d[2] / nrm;
+  if (ndc) {
+    float a[3], b[3];
+    ndc_one(H, W, focal, 1.0f, o, d, a, b);
+    for (int k = 0; k < 3; ++k) { o[k] = a[k]; d[k] = b[k]; }
+  }
+  r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
+  r[3] = d[0]; r[4] = d[1]; r[5] = d[2];
+  r[6] = near_; r[7] = far_;
+  if (i < n_rgb) {
+    if (rgb_pool) { rgb_out[3 * i] = rgb_pool[3 * j]; rgb_out[3 * i + 1] = rgb_pool[3 * j + 1]; rgb_out[3 * i + 2] = rgb_pool[3 * j + 2]; }
+  } else if (disp_pool) {
+    disp_out[i - n_rgb] = disp_pool[j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // a5 positional encoding (standalone op; the MLP kernels encode in-kernel)
 // ------------------------------------------------------------------------------------------
@@ -511,6 +541,19 @@ extern "C" int spn_build_ray_batch(int n, const float* rays_o, const float* rays
   build_ray_batch_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(n, rays_o, rays_d, near_, far_, ndc, H,
                                                                             W, focal, rays);
   SPN_LAUNCH_CHECK("build_ray_batch_kernel");
+  return SPN_OK;
+}
+
+extern "C" int spn_gather_ray_batch(int n, const float* pool_o, const float* pool_d, const int64_t* idx, float near_,
+                                    float far_, int ndc, int H, int W, float focal, float* rays, const float* rgb_pool,
+                                    float* rgb_out, int n_rgb, const float* disp_pool, float* disp_out, void* stream) {
+  SPN_CHECK_ARG(n >= 0 && pool_o && pool_d && idx && rays && n_rgb >= 0 && n_rgb <= n && (!rgb_pool || rgb_out || n_rgb == 0) &&
+                (!disp_pool || disp_out || n_rgb == n), "spn_gather_ray_batch: bad arguments");
+  if (n == 0) return SPN_OK;
+  gather_ray_batch_kernel<<<blocks_for(n, 128), 128, 0, as_stream(stream)>>>(n, pool_o, pool_d, idx, near_, far_, ndc, H, W,
+                                                                             focal, rays, rgb_pool, rgb_out, n_rgb,
+                                                                             disp_pool, disp_out);
+  SPN_LAUNCH_CHECK("gather_ray_batch_kernel");
   return SPN_OK;
 }
 

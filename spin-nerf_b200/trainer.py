@@ -58,11 +58,13 @@ class Trainer:
         self.shared = BufferPool(dev)
 
     # ---------------------------------------------------------------------------------------
-    def _forward(self, idx, rays_od, detach_weights):
-        """rays_od [2,n,3] (origin, direction) -> chunk state; random draws made on the device."""
-        o, d = rays_od[0], rays_od[1]
-        H, W, f = self.hwf if self.hwf is not None else (0, 0, 1.0)
-        rb = ops.build_ray_batch(o, d, self.near, self.far, self.ndc, H, W, f)
+    def _forward(self, idx, rays_od, detach_weights, rb=None):
+        """rays_od [2,n,3] (origin, direction) or a ready ray matrix rb [n,11] -> chunk state; random draws made on
+        the device."""
+        if rb is None:
+            o, d = rays_od[0], rays_od[1]
+            H, W, f = self.hwf if self.hwf is not None else (0, 0, 1.0)
+            rb = ops.build_ray_batch(o, d, self.near, self.far, self.ndc, H, W, f)
         n = rb.shape[0]
         S, NI = self.cfg["N_samples"], self.cfg["N_importance"]
         opts = dict(self.cfg, detach_weights=detach_weights)
@@ -96,12 +98,38 @@ class Trainer:
         tgt_rgb = P("tgt_rgb", (n1 + n2, 3), torch.float32)
         torch.cat([target_clf, target_s], 0, out=tgt_rgb)
         cfg, k = self._forward(0, rays, False)
+        return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3)
+
+    def step_from_pool(self, pool_od, rgb_pool, disp_pool, idx):
+        """The same step fed by a device-resident ray pool: pool_od [2,M,3] all rays of the
+        scene, rgb_pool [M,3] / disp_pool [M] their colour / inpainted-disparity targets, idx [3,N] int64 the rays
+        sampled for the three groups (unmasked, masked, inpainted) of this step.  One gather kernel assembles this
+        rank's ray matrix and targets (instead of the reference's per-ray Dataset/DataLoader path)."""
+        lo, hi = self.sharder.bounds(idx.shape[1])
+        m = hi - lo
+        ids = idx if (lo == 0 and hi == idx.shape[1]) else idx[:, lo:hi].contiguous()
+        ids = ids.reshape(-1)
+        n = 3 * m
+        P = self.shared
+        rb = P("rays_gathered", (n, 11), torch.float32)
+        tgt_rgb, tgt_disp = P("tgt_rgb", (2 * m, 3), torch.float32), P("tgt_disp", (m,), torch.float32)
+        H, W, f = self.hwf if self.hwf is not None else (0, 0, 1.0)
+        L.check(L.lib().spn_gather_ray_batch(n, L.ptr(pool_od[0]), L.ptr(pool_od[1]), L.ptr(ids), self.near, self.far,
+                                             int(self.ndc), int(H), int(W), float(f), L.ptr(rb), L.ptr(rgb_pool),
+                                             L.ptr(tgt_rgb), 2 * m, L.ptr(disp_pool), L.ptr(tgt_disp), L.stream()),
+                "spn_gather_ray_batch")
+        cfg, k = self._forward(0, None, False, rb=rb)
+        return self._finish_step(cfg, k, tgt_rgb, tgt_disp, m, m, m)
+
+    def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3):
+        n = n1 + n2 + n3
+        P = self.shared
         g_rgb, g_rgb0 = P("g_rgb", (n, 3), torch.float32), P("g_rgb0", (n, 3), torch.float32)
         g_disp, g_disp0 = P("g_disp", (n,), torch.float32), P("g_disp0", (n,), torch.float32)
         sums, out = P("loss_sums", (8,), torch.float32), P("loss_out", (8,), torch.float32)
         sums.zero_()
         L.check(L.lib().spn_train_losses(L.ptr(k["rgb_map"]), L.ptr(k["rgb0"]), L.ptr(k["disp_map"]), L.ptr(k["disp0"]),
-                                         L.ptr(tgt_rgb), L.ptr(L.f32(depth_inp)), n1, n2, n3, L.ptr(sums), L.ptr(g_rgb),
+                                         L.ptr(tgt_rgb), L.ptr(depth_inp), n1, n2, n3, L.ptr(sums), L.ptr(g_rgb),
                                          L.ptr(g_rgb0), L.ptr(g_disp), L.ptr(g_disp0), L.ptr(out), L.stream()),
                 "spn_train_losses")
         for g in self.grads:

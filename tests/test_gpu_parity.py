@@ -493,6 +493,31 @@ def test_trainer_batched_step_equals_three_render_calls(prec_name):
         assert np.abs(pa - pb).max() <= 2e-3 * 5e-4 + (0 if prec_name == "fp32" else 1e-3)   # Adam steps are +-lr sized
 
 
+def test_trainer_step_from_pool_equals_explicit_batches():
+    """The device-resident sampler path (one gather kernel) feeds the step the same rays / targets as explicit batches."""
+    trainer_mod = __import__("importlib").import_module("spin-nerf_b200.trainer")
+    g = load_golden("render")
+    rng = np.random.default_rng(9)
+    pool = T(np.ascontiguousarray(g["rays"]))                     # [2, M, 3]
+    M = pool.shape[1]
+    rgb_pool = T(rng.uniform(0, 1, (M, 3)).astype(np.float32)); disp_pool = T(rng.uniform(0, 1, M).astype(np.float32))
+    idx = torch.from_numpy(rng.integers(0, M, (3, 72))).to(DEV)
+    res = []
+    for mode in ("pool", "explicit"):
+        netc, _ = make_net(11, spn.PREC_FP32, 1.0); netf, _ = make_net(12, spn.PREC_FP32, 1.0)
+        tr = trainer_mod.Trainer(netc, netf, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.0,
+                                 raw_noise_std=0.0, near=1.2, far=8.0)
+        if mode == "pool":
+            loss, _ = tr.step_from_pool(pool, rgb_pool, disp_pool, idx)
+        else:
+            loss, _ = tr.step(pool[:, idx[0]], rgb_pool[idx[0]], pool[:, idx[1]], rgb_pool[idx[1]], pool[:, idx[2]], disp_pool[idx[2]])
+        torch.cuda.synchronize()
+        res.append((float(loss), N(tr.grads[0]), N(tr.grads[1])))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
+    for a, b in ((res[0][1], res[1][1]), (res[0][2], res[1][2])):     # same rays, same kernels: only atomic-add order differs
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+
+
 def test_render_bf16_psnr_vs_reference():
     g = load_golden("render")
     H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
