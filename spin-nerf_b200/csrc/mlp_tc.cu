@@ -247,8 +247,16 @@ __device__ __forceinline__ void store_enc_chunks(const uint32_t (&w)[NW], int j0
   }
 }
 
+// ReLU mask of 32 columns, built from the 16 packed post-ReLU bf16 pairs in column order: a non-negative bf16 is non-zero
+// iff adding 0x7FFF carries into bit 15, so (w + 0x7FFF7FFF) & 0x80008000 flags both halves at once and shifting the
+// accumulator right by one per pair leaves pair i's flags at bits i (column 2i) and 16+i (column 2i+1): 3 instructions
+// per pair instead of a compare + select + or per element.  relu_mask_bit(c) is where column c of the block ends up.
+__device__ __forceinline__ uint32_t relu_mask_push(uint32_t acc, uint32_t packed_pair) {
+  return (acc >> 1) | ((packed_pair + 0x7FFF7FFFu) & 0x80008000u);
+}
+
 // 32 accumulator columns of a hidden layer: h = acc + bias (ReLU), bf16, swizzled store into the A tile; returns the 32
-// ReLU mask bits (bit = column).  MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
+// ReLU mask bits (layout: relu_mask_push).  MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
 //   bias_a: shared address of this thread's first bias entry (column cl = 0)    wa_a: bf16 sigma weights, same origin
 //   row_a:  shared address of (this tile, this column half, row r, chunk 0)     rx: (r & 7) << 4
 template <bool kTrain, int MODE>
@@ -267,10 +275,6 @@ __device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const in
     const float2 h45 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])), make_float2(b1.x, b1.y));
     const float2 h67 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])), make_float2(b1.z, b1.w));
     float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
-    if (kTrain && MODE != 2) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
-    }
     if (MODE == 1) {
       const uint4 wq = lds128u(wa_a + c * 2);       // 8 bf16 sigma weights
       const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
@@ -285,6 +289,10 @@ __device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const in
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       o[e] = (MODE == 0) ? pack_relu_bf16(h[2 * e], h[2 * e + 1]) : pack_bf16(h[2 * e], h[2 * e + 1]);
+    if (kTrain && MODE != 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mb = relu_mask_push(mb, o[e]);
+    }
     sts128(row_a + (uint32_t)(c / 64) * kAtomBytes + ((uint32_t)(((c % 64) / 8) << 4) ^ rx), o[0], o[1], o[2], o[3]);
   }
   return mb;
@@ -340,9 +348,8 @@ __device__ __forceinline__ uint32_t epi_final32(const uint32_t (&v)[32], const i
       rgb[2] = fmaf(h[e], r2.x, fmaf(h[e + 1], r2.y, fmaf(h[e + 2], r2.z, fmaf(h[e + 3], r2.w, rgb[2]))));
     }
     if (kTrain) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) mb |= (h[e] > 0.f ? 1u : 0u) << (g * 8 + e);
       const uint4 v4 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+      mb = relu_mask_push(relu_mask_push(relu_mask_push(relu_mask_push(mb, v4.x), v4.y), v4.z), v4.w);
       *reinterpret_cast<uint4*>(stash_tile + (size_t)(SA_HV + col / 64) * kAtomBytes + sw128_off(r, (col % 64) / 8)) = v4;
     }
   }

@@ -48,7 +48,9 @@ constexpr int kSlotBytes = 32768;
 //   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)
 //   atoms 33-36 feature                          atoms 37-38   hv (128 wide)
 //   atom 39     gamma(viewdir) (27 + pad)
-// followed by ReLU masks: 9 slots (h0..h7, hv) x 128 rows x 8 words
+// followed by ReLU masks: 9 slots (h0..h7, hv) x 128 rows x 8 words; word w covers columns 32w..32w+31 with column
+// 32w + c at bit relu_mask_bit(c) (pairs are pushed as packed bf16x2 words, see relu_mask_push in mlp_tc.cu)
+__host__ __device__ constexpr int relu_mask_bit(int c) { return ((c & 1) << 4) | (c >> 1); }
 constexpr int kStashAtoms = 40;
 constexpr int SA_ENC = 0, SA_H0 = 1, SA_FEAT = 33, SA_HV = 37, SA_DENC = 39;
 constexpr size_t kStashMaskOff = (size_t)kStashAtoms * kAtomBytes;

@@ -83,7 +83,7 @@ __device__ __forceinline__ void dg_cols32(const uint32_t (&v)[32], const int cl,
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = ((mb >> (g * 8 + e)) & 1u) ? h[e] : 0.f;
+    for (int e = 0; e < 8; ++e) h[e] = ((mb >> relu_mask_bit(g * 8 + e)) & 1u) ? h[e] : 0.f;
     sts128(row_a + (uint32_t)(c / 64) * kAtomBytes + ((uint32_t)(((c % 64) / 8) << 4) ^ rx), pack_bf16(h[0], h[1]),
            pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
   }
@@ -256,7 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
               v[e + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = ((mw2[cb] >> (g8 * 8 + e)) & 1u) ? v[e] : 0.f;
+            for (int e = 0; e < 8; ++e) v[e] = ((mw2[cb] >> relu_mask_bit(g8 * 8 + e)) & 1u) ? v[e] : 0.f;
             sts128(act_a + (uint32_t)(col / 64) * kAtomBytes + sw128_off((uint32_t)r, (uint32_t)((col % 64) / 8)),
                    pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
