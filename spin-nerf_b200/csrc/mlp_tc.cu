@@ -629,10 +629,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
         if (epi == EPI_RELU) epi_layer<kTrain, 0>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
         else if (epi == EPI_RELU_ALPHA) epi_layer<kTrain, 1>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
         else epi_layer<kTrain, 2>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
-        if (kTrain && c_step_mask_slot[s] >= 0) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
-          *reinterpret_cast<uint4*>(mrow) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-        }
         tcgen05_fence_before_sync();
         if (etr) etr[22] = clock64();
         fence_proxy_async_smem();
@@ -640,6 +636,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(act_leader);
         if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
+        // the mask words go out AFTER the hand-over: a global store in front of it sat ~900 cycles on the critical path
+        if (kTrain && c_step_mask_slot[s] >= 0) {
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
+          *reinterpret_cast<uint4*>(mrow) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+        }
         if (kTrain) pending_atom = c_step_stash_atom[s];
       }
     }
