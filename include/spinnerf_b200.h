@@ -181,6 +181,13 @@ int spn_train_losses(const float* rgb_map, const float* rgb0, const float* disp_
 int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                   void* stream);
+/* The same update with the step counter and learning-rate schedule on the device, so that a whole train step can be
+ * captured once and replayed as a CUDA graph.  state4 = {step, lr/bias_correction1, sqrt(bias_correction2), lr} (floats,
+ * zero-initialised).  spn_adam_tick advances it once per optimisation step: step += 1, lr = lr0 * decay_base^((step-1) /
+ * decay_steps) (run_nerf.py:1616-1622: decay_base 0.1, decay_steps lrate_decay*1000); spn_adam_step_dev applies it. */
+int spn_adam_tick(float* state4, float lr0, float decay_base, float decay_steps, float beta1, float beta2, void* stream);
+int spn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* state4, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- a1-a3  render_rays, whole chunk (run_nerf.py:593-737) --------------------------------- */
 typedef struct {

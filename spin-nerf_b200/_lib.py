@@ -75,6 +75,8 @@ _SIGS = {
     "spn_gather_ray_batch": (C.c_int, [C.c_int, c_fp, c_fp, c_fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float,
                                        c_fp, c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp]),
     "spn_train_losses": (C.c_int, [c_fp] * 6 + [C.c_int] * 3 + [c_fp] * 7),
+    "spn_adam_tick": (C.c_int, [c_fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_fp]),
+    "spn_adam_step_dev": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_float, C.c_float, C.c_float, C.c_float, c_fp]),
     "spn_adam_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, c_fp]),
     "spn_render_rays_fwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), c_fp]),
     "spn_render_rays_bwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), C.POINTER(RenderGrads), c_fp]),

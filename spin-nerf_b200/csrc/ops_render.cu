@@ -504,6 +504,32 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+// Adam with the step counter and schedule resident on the device, so a whole train step can be replayed as a CUDA graph:
+// state = {step, lr / bias_correction1, sqrt(bias_correction2), lr}; adam_tick advances it once per step.
+__global__ void adam_tick_kernel(float* __restrict__ state, float lr0, float decay_base, float decay_steps, float b1,
+                                 float b2) {
+  const float k = state[0] + 1.0f;                                  // 1-based step about to be applied
+  const float lr = lr0 * powf(decay_base, (k - 1.0f) / decay_steps);  // run_nerf.py:1616-1622
+  state[0] = k;
+  state[1] = lr / (1.0f - powf(b1, k));
+  state[2] = sqrtf(1.0f - powf(b2, k));
+  state[3] = lr;
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1, float b2,
+                                float eps, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_bc1 = state[1], bc2_sqrt = state[2];
+  float gi = g[i] * gscale;
+  float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+  float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - lr_bc1 * (mi / denom);
+}
+
 }  // namespace spn
 
 // ============================================================================================
@@ -748,6 +774,25 @@ extern "C" int spn_train_losses(const float* rgb_map, const float* rgb0, const f
   train_loss_grads_kernel<<<blocks, 256, 0, st>>>(rgb_map, rgb0, disp_map, disp0, target_rgb, target_disp, n1, n2, n3,
                                                  sums6_zeroed, g_rgb, g_rgb0, g_disp, g_disp0, out8);
   SPN_LAUNCH_CHECK("train_loss_grads_kernel");
+  return SPN_OK;
+}
+
+extern "C" int spn_adam_tick(float* state4, float lr0, float decay_base, float decay_steps, float beta1, float beta2,
+                             void* stream) {
+  SPN_CHECK_ARG(state4 && decay_steps > 0.f, "spn_adam_tick: bad arguments");
+  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(state4, lr0, decay_base, decay_steps, beta1, beta2);
+  SPN_LAUNCH_CHECK("adam_tick_kernel");
+  return SPN_OK;
+}
+
+extern "C" int spn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 const float* state4, float beta1, float beta2, float eps, float grad_scale,
+                                 void* stream) {
+  SPN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && state4 && n >= 0, "spn_adam_step_dev: bad arguments");
+  if (n == 0) return SPN_OK;
+  adam_dev_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, state4, beta1,
+                                                                     beta2, eps, grad_scale);
+  SPN_LAUNCH_CHECK("adam_dev_kernel");
   return SPN_OK;
 }
 

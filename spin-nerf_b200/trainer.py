@@ -56,6 +56,8 @@ class Trainer:
         self.global_step = 0
         self.pools = [BufferPool(dev)] * 3      # each render is consumed (backward) before the next starts
         self.shared = BufferPool(dev)
+        self.adam_state = None                  # device-resident {step, lr/bc1, sqrt(bc2), lr}: CUDA-graph mode
+        self._graph = None
 
     # ---------------------------------------------------------------------------------------
     def _forward(self, idx, rays_od, detach_weights, rb=None):
@@ -91,6 +93,8 @@ class Trainer:
         rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
         rays_inp, depth_inp = sh.shard(rays_inp, 1), sh.shard(depth_inp)
         n1, n2, n3 = rays_clf.shape[1], rays_s.shape[1], rays_inp.shape[1]
+        if target_clf.shape[0] != n1 or target_s.shape[0] != n2 or depth_inp.shape[0] != n3:
+            raise RuntimeError("Trainer.step: every ray batch needs one target per ray")
         n = n1 + n2 + n3
         P = self.shared
         rays = P("rays_cat", (2, n, 3), torch.float32)
@@ -191,12 +195,54 @@ class Trainer:
     # ---------------------------------------------------------------------------------------
     def apply_gradients(self):
         """NCCL all-reduce (mean over ranks) of the two flat gradient vectors, then one Adam launch per network;
-        learning-rate schedule of run_nerf.py:1616-1622."""
+        learning-rate schedule of run_nerf.py:1616-1622.  With `self.adam_state` set (CUDA-graph mode) the step counter
+        and schedule live on the device (spn_adam_tick / spn_adam_step_dev) so the launches are replayable."""
         scale = allreduce_sum_(self.grads, self.pg) if self.sharder.world > 1 else 1.0
         self.global_step += 1
+        if self.adam_state is not None:
+            L.check(L.lib().spn_adam_tick(L.ptr(self.adam_state), self.lr0, 0.1, float(self.lrate_decay * 1000),
+                                          self.betas[0], self.betas[1], L.stream()), "spn_adam_tick")
         lr = self.lr0 * (0.1 ** ((self.global_step - 1) / (self.lrate_decay * 1000)))
         for net, g, m, v in zip((self.net_c, self.net_f), self.grads, self.m, self.v):
             if net is None:
                 continue
-            ops.adam_step(net.flat_params(), g, m, v, self.global_step, lr, self.betas, self.eps, grad_scale=scale)
+            if self.adam_state is not None:
+                L.check(L.lib().spn_adam_step_dev(L.ptr(net.flat_params()), L.ptr(g), L.ptr(m), L.ptr(v), g.numel(),
+                                                  L.ptr(self.adam_state), self.betas[0], self.betas[1], self.eps,
+                                                  float(scale), L.stream()), "spn_adam_step_dev")
+            else:
+                ops.adam_step(net.flat_params(), g, m, v, self.global_step, lr, self.betas, self.eps, grad_scale=scale)
             net.mark_params_changed()
+
+    # ---------------------------------------------------------------------------------------
+    def step_graphed(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
+        """`step` replayed as ONE CUDA graph (the whole step is ~45 small and 6 large launches; replaying it removes the
+        launch latency a caller that reads the loss back every step would otherwise expose).  Inputs may live on the
+        host (pinned) or the device: they are copied into static device buffers, then the graph is replayed.  The
+        first call runs eagerly (allocates every pooled buffer), the second captures, later ones replay; shapes must
+        not change.  Returns (loss, psnr) as views of static buffers (valid until the next call)."""
+        ins = (rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp)
+        if self._graph is None:
+            self._static_in = [torch.empty(t.shape, dtype=torch.float32, device=self.device) for t in ins]
+            if self.adam_state is None:
+                self.adam_state = torch.zeros(4, device=self.device)
+                self.adam_state[0] = float(self.global_step)
+            self._graph = "warm"
+        for s, t in zip(self._static_in, ins):
+            s.copy_(t, non_blocking=True)
+        if self._graph == "warm":                      # eager pass: sizes every pooled buffer, sets kernel attributes
+            out = self.step(*self._static_in)
+            self._graph = "capture"
+            return out
+        if self._graph == "capture":
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.lib().spn_launch_count(0)
+            with torch.cuda.graph(graph):
+                self._static_out = self.step(*self._static_in)
+            self.graph_launches = int(L.lib().spn_launch_count(0) - n0)   # our kernels per replay
+            self._graph = graph
+            self.global_step -= 1                      # capture only recorded the step, it did not run
+        self._graph.replay()
+        self.global_step += 1
+        return self._static_out

@@ -493,6 +493,42 @@ def test_trainer_batched_step_equals_three_render_calls(prec_name):
         assert np.abs(pa - pb).max() <= 2e-3 * 5e-4 + (0 if prec_name == "fp32" else 1e-3)   # Adam steps are +-lr sized
 
 
+def test_trainer_graphed_steps_equal_eager_steps():
+    """Trainer.step_graphed (eager pass, capture, replays with the Adam schedule on the device) walks the same parameter
+    trajectory as Trainer.step with the host-side schedule."""
+    trainer_mod = __import__("importlib").import_module("spin-nerf_b200.trainer")
+    g = load_golden("render")
+    rng = np.random.default_rng(3)
+    rays = g["rays"]
+    n = rays.shape[1]
+    steps = []
+    for _ in range(5):
+        b = []
+        for i in range(3):
+            ix = rng.permutation(n)[:40]
+            b.append(torch.from_numpy(np.ascontiguousarray(rays[:, ix])).pin_memory())
+            b.append(torch.from_numpy(rng.uniform(0, 1, (len(ix), 3) if i < 2 else (len(ix),)).astype(np.float32)).pin_memory())
+        steps.append(b)
+    res = []
+    for mode in ("graph", "eager"):
+        netc, _ = make_net(11, spn.PREC_BF16, 1.0); netf, _ = make_net(12, spn.PREC_BF16, 1.0)
+        tr = trainer_mod.Trainer(netc, netf, lr=5e-4, lrate_decay=1, N_samples=64, N_importance=64, lindisp=True,
+                                 white_bkgd=True, perturb=0.0, raw_noise_std=0.0, near=1.2, far=8.0)
+        losses = []
+        for b in steps:
+            if mode == "graph":
+                loss, _ = tr.step_graphed(*b)
+            else:
+                loss, _ = tr.step(*[t.to(DEV) for t in b])
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        res.append((losses, N(netc.flat_params()), N(netf.flat_params()), tr.global_step))
+    assert res[0][3] == res[1][3] == 5
+    assert np.allclose(res[0][0], res[1][0], rtol=2e-3), (res[0][0], res[1][0])
+    for a, b in ((res[0][1], res[1][1]), (res[0][2], res[1][2])):
+        assert np.abs(a - b).max() <= 1.5e-3          # 5 Adam steps of <= 5e-4 each; bf16 tensor-core sums may reorder
+
+
 def test_trainer_step_from_pool_equals_explicit_batches():
     """The device-resident sampler path (one gather kernel) feeds the step the same rays / targets as explicit batches."""
     trainer_mod = __import__("importlib").import_module("spin-nerf_b200.trainer")
