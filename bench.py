@@ -298,6 +298,16 @@ def main():
         if n_l and ms_l > 0:
             kern[name] = {"launches_per_step": n_l / args.steps, "ms_per_step": ms_l / args.steps,
                           "tflops": evals_per_rank_step * flop * args.steps / (ms_l * 1e-3) / 1e12}
+    # per-kernel roofline: forward / dgrad are bound by the tensor pipe, wgrad by HBM (it streams every stash and dstash
+    # tile once: 76 atoms of 16 KB per 128-sample tile = 9.73 KB per MLP evaluation)
+    hbm_peak = float(peaks.get("hbm_gbs", 6400.0))
+    wg_bytes_per_eval = 76 * 16384 / 128.0
+    for name, k in kern.items():
+        if name == "mlp_wgrad":
+            gbs = evals_per_rank_step * wg_bytes_per_eval / (k["ms_per_step"] * 1e-3) / 1e9
+            k.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak)
+        else:
+            k.update(bound="tensor", achieved=k["tflops"], peak=peak, unit="TFLOP/s", frac=k["tflops"] / peak)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     traffic = None
     try:
@@ -306,8 +316,13 @@ def main():
         pass
     roofline = None
     if dom:
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                    "frac": kern[dom]["tflops"] / peak, "traffic": traffic, "peak_source": peak_src, "kernels": kern,
+        d = kern[dom]
+        roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": traffic,
+                    "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if d["bound"] == "hbm" else "bf16_tflops_sustained (kernel timed inside a long step)"))
+                                   if peaks else "fallback (B200_PROFILING.md)",
+                    "algorithmic_units": "wgrad: 76 x 16 KB stash/dstash atoms per 128-sample tile; fwd/dgrad: 1 186 816 / 1 115 392 FLOP per MLP evaluation",
+                    "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
     cpu = None
     if not args.no_cpu_baseline:

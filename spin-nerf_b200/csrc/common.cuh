@@ -127,6 +127,7 @@ int mlp_fp32_bwd(const float* params, const void* stash, const float* d_raw, int
 size_t mlp_tc_packed_bytes();
 int weight_piece_bytes();
 void tc_set_trace(long long* dev);
+long long* tc_get_trace();
 size_t mlp_tc_stash_bytes(int64_t m);
 size_t mlp_tc_bwd_ws_bytes(int64_t m);
 int mlp_tc_pack(const float* params, void* packed, cudaStream_t st);

@@ -30,6 +30,7 @@ size_t mlp_tc_packed_bytes() { return kPackedBytes; }
 // diagnostic timeline buffer (device pointer, kTraceSlots int64): see tools/trace_fwd.py
 static long long* g_trace = nullptr;
 void tc_set_trace(long long* dev) { g_trace = dev; }
+long long* tc_get_trace() { return g_trace; }
 constexpr int kTraceRounds = 3, kTraceEvents = 24;
 constexpr int kTraceSlots = kTraceRounds * 12 * 2 * kTraceEvents;
 __device__ __forceinline__ long long gtimer_ns() {

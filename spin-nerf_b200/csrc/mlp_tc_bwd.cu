@@ -334,7 +334,7 @@ struct WgUnit {
   int w_off;       // float offset of dW[0][0] in the flat gradient
   int ld;          // row stride of dW
   int b_off;       // float offset of the bias gradient, -1 if another unit owns it
-  int cost;        // relative tensor work per tile (1/8 of a 256x256x128 GEMM)
+  int cost;        // relative CTA time per tile (138 = a 256x256 unit)
 };
 struct WgTable { WgUnit u[kWgUnits]; int total_cost; };
 
@@ -346,16 +346,17 @@ static WgTable build_wg_table() {
   auto DH = [&](int i) { return DA_H7 + 4 * (7 - i); };
   auto H = [&](int i) { return SA_H0 + 4 * i; };
   int n = 0;
-  // cost = measured per-slab time (HBM bytes + the ~1000-cycle copy round dominate; the MMAs are a minor part), /8 of a big unit
-  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 5};
-  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, H(i - 1), 256, 256, W(i), kW, B(i), 8};
-  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 5};
-  t.u[n++] = WgUnit{DH(5), 256, H(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 8};
-  t.u[n++] = WgUnit{DH(6), 256, H(5), 256, 256, W(6), kW, B(6), 8};
-  t.u[n++] = WgUnit{DH(7), 256, H(6), 256, 256, W(7), kW, B(7), 8};
-  t.u[n++] = WgUnit{DA_FEAT, 256, H(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 8};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 6};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 4};
+  // cost = measured CTA-cycles per tile (tools/trace_wgrad.py, 64-sample slabs): HBM bytes plus the per-slab copy round —
+  // the narrow units are slower than their byte share — relative to 138 for a 256x256 unit
+  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 115};
+  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, H(i - 1), 256, 256, W(i), kW, B(i), 138};
+  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 104};
+  t.u[n++] = WgUnit{DH(5), 256, H(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 138};
+  t.u[n++] = WgUnit{DH(6), 256, H(5), 256, 256, W(6), kW, B(6), 138};
+  t.u[n++] = WgUnit{DH(7), 256, H(6), 256, 256, W(7), kW, B(7), 138};
+  t.u[n++] = WgUnit{DA_FEAT, 256, H(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 138};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 113};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 88};
   t.total_cost = 0;
   for (int i = 0; i < kWgUnits; ++i) t.total_cost += t.u[i].cost;
   return t;
@@ -369,6 +370,7 @@ struct WgradParams {
   WgTable tab;
   int cta_begin[kWgUnits + 1];   // CTAs [cta_begin[u], cta_begin[u+1]) split unit u's tiles evenly
   float* partial;                // [gridDim.x][256][256] fp32 per-CTA weight-gradient partials
+  long long* cta_cycles;         // diagnostic (spn_tc_set_trace): [2*cta] = unit, [2*cta+1] = cycles of the CTA's segment
   int debug;                     // SPN_WG_DEBUG bit0: skip MMAs, bit1: skip column sums, bit2: skip the copies (timing experiments)
 };
 
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
     const int a_atoms = u.m_out / 64, b_atoms = u.n_in / 64;
     const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * kWgSlabBytes;
     const int64_t nslabs = (t1 - t0) * (kTileM / kWgSlabRows);
+    const long long seg_t0 = clock64();
 
     if (warp == 0) {
       // ---- producer: 32-sample slabs of dpre (A) and layer input (B).  Each of the <= 8 slab copies of a stage is
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
       }
       tcgen05_fence_before_sync();
       mbar_arrive(bar_acc_empty);
+      if (p.cta_cycles && threadIdx.x == 64) { p.cta_cycles[2 * blockIdx.x] = ui; p.cta_cycles[2 * blockIdx.x + 1] = clock64() - seg_t0; }
     }
     seg_phase ^= 1;
   }
@@ -629,31 +633,38 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   // 2. weight / bias gradients of the ten wide layers
   WgradParams wp;
   wp.stash = (const uint8_t*)stash; wp.dstash = (const uint8_t*)ws; wp.grads = grads; wp.tiles = tiles; wp.tab = wg_tab;
-  // CTAs per unit proportional to tensor cost (>= 1, <= tiles); every CTA owns exactly one (unit, tile range)
+  // Every CTA owns exactly one (unit, tile range).  CTAs are handed out greedily to the unit whose CTAs would otherwise
+  // run longest (cost / CTAs), which minimises the slowest CTA; a unit never gets more CTAs than tiles.
   int target = sm_count();
-  if ((int64_t)wg_tab.total_cost * tiles / 16 < target) target = (int)((int64_t)wg_tab.total_cost * tiles / 16);
-  if (target < kWgUnits) target = kWgUnits;
+  {
+    const int64_t enough = (int64_t)wg_tab.total_cost * tiles / (2 * 138);   // ~2 tiles of a big unit per CTA at least
+    if (enough < target) target = (int)enough;
+    if (target < kWgUnits) target = kWgUnits;
+  }
+  int per_unit[kWgUnits];
+  for (int ui = 0; ui < kWgUnits; ++ui) per_unit[ui] = 1;
+  for (int assigned_n = kWgUnits; assigned_n < target; ++assigned_n) {
+    int best = -1;
+    double worst = -1.0;
+    for (int ui = 0; ui < kWgUnits; ++ui) {
+      if (per_unit[ui] >= tiles) continue;
+      const double tpc = (double)wg_tab.u[ui].cost / per_unit[ui];
+      if (tpc > worst) { worst = tpc; best = ui; }
+    }
+    if (best < 0) break;
+    ++per_unit[best];
+  }
   int assigned = 0;
   wp.cta_begin[0] = 0;
   for (int ui = 0; ui < kWgUnits; ++ui) {
-    int g = (int)((int64_t)target * wg_tab.u[ui].cost / wg_tab.total_cost);
-    if (g < 1) g = 1;
-    if (g > tiles) g = (int)tiles;
-    assigned += g;
+    assigned += per_unit[ui];
     wp.cta_begin[ui + 1] = assigned;
-  }
-  // hand left-over SMs to the big units
-  for (int ui = 0; assigned < sm_count() && ui < kWgUnits; ++ui) {
-    if (wg_tab.u[ui].cost < 8) continue;
-    int have = wp.cta_begin[ui + 1] - wp.cta_begin[ui];
-    if (have >= tiles) continue;
-    for (int k = ui + 1; k <= kWgUnits; ++k) wp.cta_begin[k] += 1;
-    ++assigned;
   }
   const int wgrid = assigned;
   wp.partial = reinterpret_cast<float*>((uint8_t*)ws + (size_t)quad_tiles(m) * kDstashTileBytes);
   static const int wg_debug = getenv("SPN_WG_DEBUG") ? atoi(getenv("SPN_WG_DEBUG")) : 0;
   wp.debug = wg_debug;
+  wp.cta_cycles = tc_get_trace();
   prof_begin(PROF_MLP_WGRAD, st);
   mlp_wgrad_kernel<<<wgrid, kWgThreads, kWgSmemBytes, st>>>(wp);
   SPN_LAUNCH_CHECK("mlp_wgrad_kernel");
