@@ -549,15 +549,21 @@ __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const WgradParams
 // =====================================================================================================
 // rgb / sigma heads: dWr[3,128] += d_rgb^T hv,  dbr,  dWa[256] += d_sigma h7,  dba
 // =====================================================================================================
-__global__ void __launch_bounds__(256) mlp_heads_wgrad_kernel(const uint8_t* __restrict__ stash,
+// 8 warps per block, warp w owns rows 16w..16w+15 of a tile; lane l reads the 16-byte chunk (8 features) l of the 256-wide
+// h7 row (atom l / 8, chunk l % 8) and, for l < 16, chunk l of the 128-wide hv row: every load instruction of a warp
+// covers whole 128-byte lines of the swizzled stash atoms.  Partials live in registers across the block's tiles and are
+// combined through shared memory once, then 643 atomics per block.
+__global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* __restrict__ stash,
                                                               const float* __restrict__ d_raw, int64_t m,
                                                               int64_t tiles, float* __restrict__ g_wr,
                                                               float* __restrict__ g_br, float* __restrict__ g_wa,
                                                               float* __restrict__ g_ba) {
   __shared__ float4 s_d[kTileM];
-  const int tid = threadIdx.x;
-  // threads 0..127: column pair of h7 (256 wide); threads 128..191: column pair of hv (128 wide)
-  float a0 = 0.f, a1 = 0.f, r0[3] = {0, 0, 0}, r1[3] = {0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  __shared__ float s_red[8][32][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float wa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float wr[3][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  float sb[4] = {0, 0, 0, 0};
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
     if (tid < kTileM) {
@@ -566,40 +572,71 @@ __global__ void __launch_bounds__(256) mlp_heads_wgrad_kernel(const uint8_t* __r
     }
     __syncthreads();
     const uint8_t* st = stash + (size_t)tile * kStashTileBytes;
-    if (tid < 128) {
-      const int c = 2 * tid;
-      const uint8_t* base = st + (size_t)(SA_H0 + 28 + c / 64) * kAtomBytes + (c % 8) * 2;
-      const uint32_t c16 = (uint32_t)(c % 64) / 8;
-#pragma unroll 4
-      for (int rr = 0; rr < kTileM; ++rr) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + sw128_off(rr, c16)));
-        const float da = s_d[rr].w;
-        a0 = fmaf(da, __uint_as_float(w << 16), a0);
-        a1 = fmaf(da, __uint_as_float(w & 0xffff0000u), a1);
+    const uint8_t* h7 = st + (size_t)(SA_H0 + 28 + (lane >> 3)) * kAtomBytes;
+    const uint8_t* hv = st + (size_t)(SA_HV + ((lane & 15) >> 3)) * kAtomBytes;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {       // 8 rows in flight per lane: 12 x 16 B loads, ~100 registers
+      uint4 q7[8], qv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = (uint32_t)(warp * 16 + half * 8 + i);
+        q7[i] = __ldg(reinterpret_cast<const uint4*>(h7 + sw128_off(rr, (uint32_t)(lane & 7))));
+        if (lane < 16) qv[i] = __ldg(reinterpret_cast<const uint4*>(hv + sw128_off(rr, (uint32_t)(lane & 7))));
       }
-    } else if (tid < 192) {
-      const int c = 2 * (tid - 128);
-      const uint8_t* base = st + (size_t)(SA_HV + c / 64) * kAtomBytes + (c % 8) * 2;
-      const uint32_t c16 = (uint32_t)(c % 64) / 8;
-#pragma unroll 4
-      for (int rr = 0; rr < kTileM; ++rr) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + sw128_off(rr, c16)));
-        const float h0 = __uint_as_float(w << 16), h1 = __uint_as_float(w & 0xffff0000u);
-        const float4 d = s_d[rr];
-        r0[0] = fmaf(d.x, h0, r0[0]); r0[1] = fmaf(d.y, h0, r0[1]); r0[2] = fmaf(d.z, h0, r0[2]);
-        r1[0] = fmaf(d.x, h1, r1[0]); r1[1] = fmaf(d.y, h1, r1[1]); r1[2] = fmaf(d.z, h1, r1[2]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 d = s_d[warp * 16 + half * 8 + i];
+        const uint32_t w7[4] = {q7[i].x, q7[i].y, q7[i].z, q7[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          wa[2 * e] = fmaf(d.w, __uint_as_float(w7[e] << 16), wa[2 * e]);
+          wa[2 * e + 1] = fmaf(d.w, __uint_as_float(w7[e] & 0xffff0000u), wa[2 * e + 1]);
+        }
+        if (lane < 16) {
+          const uint32_t wv[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h0 = __uint_as_float(wv[e] << 16), h1 = __uint_as_float(wv[e] & 0xffff0000u);
+            wr[0][2 * e] = fmaf(d.x, h0, wr[0][2 * e]); wr[0][2 * e + 1] = fmaf(d.x, h1, wr[0][2 * e + 1]);
+            wr[1][2 * e] = fmaf(d.y, h0, wr[1][2 * e]); wr[1][2 * e + 1] = fmaf(d.y, h1, wr[1][2 * e + 1]);
+            wr[2][2 * e] = fmaf(d.z, h0, wr[2][2 * e]); wr[2][2 * e + 1] = fmaf(d.z, h1, wr[2][2 * e + 1]);
+          }
+        }
+        if (lane == 31) { sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
       }
-    } else if (tid == 192) {
-      for (int rr = 0; rr < kTileM; ++rr) { const float4 d = s_d[rr]; sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
     }
   }
-  if (tid < 128) {
-    atomicAdd(g_wa + 2 * tid, a0); atomicAdd(g_wa + 2 * tid + 1, a1);
-  } else if (tid < 192) {
-    const int c = 2 * (tid - 128);
-    for (int k = 0; k < 3; ++k) { atomicAdd(g_wr + k * kWV + c, r0[k]); atomicAdd(g_wr + k * kWV + c + 1, r1[k]); }
-  } else if (tid == 192) {
-    atomicAdd(g_br, sb[0]); atomicAdd(g_br + 1, sb[1]); atomicAdd(g_br + 2, sb[2]); atomicAdd(g_ba, sb[3]);
+  // block reduction over the 8 warps, one quantity at a time through the same shared buffer
+  auto reduce8 = [&](const float (&v)[8], float* dst, int n_lanes) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_red[warp][lane][e] = v[e];
+    __syncthreads();
+    if (warp == 0 && lane < n_lanes) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_red[w][lane][e];
+        atomicAdd(dst + 8 * lane + e, acc);
+      }
+    }
+  };
+  reduce8(wa, g_wa, 32);                         // d alpha_linear.weight [256]
+  reduce8(wr[0], g_wr, 16);                      // d rgb_linear.weight [3][128]
+  reduce8(wr[1], g_wr + kWV, 16);
+  reduce8(wr[2], g_wr + 2 * kWV, 16);
+  {
+    const float v[8] = {sb[0], sb[1], sb[2], sb[3], 0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_red[warp][lane][e] = v[e];
+    __syncthreads();
+    if (tid < 4) {
+      float acc = 0.f;
+      for (int w = 0; w < 8; ++w) acc += s_red[w][31][tid];
+      atomicAdd(tid < 3 ? g_br + tid : g_ba, acc);
+    }
   }
 }
 
@@ -672,7 +709,7 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   prof_end(PROF_MLP_WGRAD, st);
   SPN_LAUNCH_CHECK("mlp_wgrad_reduce_kernel");
   // 3. heads
-  const int hmax = 8 * sm_count();                    // 8 resident blocks per SM; every block ends with 643 atomics
+  const int hmax = 4 * sm_count();                    // 4 resident blocks per SM; every block ends with 643 atomics
   int hgrid = (int)(tiles < hmax ? tiles : hmax);
   mlp_heads_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, d_raw, m, tiles, grads + po.off[T_WR],
                                                 grads + po.off[T_BR], grads + po.off[T_WA], grads + po.off[T_BA]);

@@ -459,6 +459,36 @@ def test_train_step_bf16_tracks_reference():
         opt.step()
 
 
+def test_mlp_bf16_full_size_is_chunk_invariant():
+    """BASELINE size (3 x 1024 rays x 128 fine samples = 393 216 evaluations, many rounds of every CTA pair): a sample's
+    output must not depend on which tile / CTA / round processed it, and the weight gradient of the whole batch must be
+    the sum of the gradients of its parts (size-independent properties; the oracle is too slow at this size)."""
+    net, p = make_net(11, spn.PREC_BF16)
+    M = 3 * 1024 * 128
+    gen = torch.Generator(device=DEV); gen.manual_seed(7)
+    x6 = torch.randn(M, 6, device=DEV, generator=gen)
+    x6[:, 3:] = x6[:, 3:] / x6[:, 3:].norm(dim=1, keepdim=True)
+    draw = torch.randn(M, 4, device=DEV, generator=gen) / M
+    flat, packed = net._sync()
+    cut = 1000 * 128 + 77                                    # ragged split: tiles of the parts do not line up with the whole
+    outs, grads = [], []
+    for lo, hi in ((0, M), (0, cut), (cut, M)):
+        n = hi - lo
+        stash = ops.mlp_stash(n, spn.PREC_BF16, DEV)
+        raw, _ = ops.mlp_forward_points(flat, packed, x6[lo:hi].contiguous(), spn.PREC_BF16, stash)
+        g = torch.zeros(spn.MLP_NPARAMS, device=DEV)
+        ops.mlp_backward(flat, packed, stash, draw[lo:hi].contiguous(), g, spn.PREC_BF16,
+                         workspace=ops.mlp_bwd_workspace(n, spn.PREC_BF16, DEV))
+        outs.append(raw); grads.append(g)
+        del stash
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], torch.cat([outs[1], outs[2]], 0))          # bit-exact, row by row
+    gsum = grads[1] + grads[2]
+    scale = grads[0].abs().max()
+    assert scale > 0 and (grads[0] - gsum).abs().max() <= 2e-3 * scale, float((grads[0] - gsum).abs().max() / scale)
+
+
 @pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
 def test_trainer_batched_step_equals_three_render_calls(prec_name):
     """Trainer.step renders the step's three ray batches as ONE chunk (per-ray-range losses and detach_weights);
