@@ -126,6 +126,11 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cpu_rays
+    # bounded sample: one probe step sizes the per-step ray count so that warmup + steps end within ~4 minutes
+    _, probe = cpu_train_steps(n, 1, 0)
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    while n > 8 and probe * (n / args.cpu_rays) > budget:
+        n //= 2
     rps, sec = cpu_train_steps(n, args.steps, args.warmup)
     cores = os.cpu_count()
     line = {"impl": "reference", "metric": "rays/sec (train-step)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
@@ -147,6 +152,9 @@ def workload_config(n_gpus, n_rand):
 
 
 # ------------------------------------------------------------------------------------------------
+PARTIAL = {}     # rank 0's result line as far as it is known; the watchdog prints it if a later phase hangs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,7 +165,23 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--cpu_rays", type=int, default=128, help="rays per render call in the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--deadline", type=float, default=420.0,
+                    help="hard wall-clock limit in seconds: a watchdog thread ends the process (exit code 3) if the run has not "
+                         "finished by then, so a hung collective or kernel can never hold the GPU box")
     args = ap.parse_args()
+    if args.impl == "reference":
+        args.deadline = max(args.deadline, 1200.0)       # host-only run: nothing to protect but the caller's patience
+    if args.deadline > 0:
+        import threading
+
+        def _watchdog():
+            time.sleep(args.deadline)
+            sys.stderr.write(f"bench.py: deadline of {args.deadline:.0f} s exceeded, aborting\n"); sys.stderr.flush()
+            if PARTIAL and int(os.environ.get("RANK", "0")) == 0:       # report what was measured before the hang
+                print(json.dumps(dict(PARTIAL, aborted=f"deadline {args.deadline:.0f} s exceeded after the device-timed region")),
+                      flush=True)
+            os._exit(3)
+        threading.Thread(target=_watchdog, daemon=True).start()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -248,6 +272,10 @@ def main():
         step_ms = float(t.item())
     rays_per_step = RENDERS_PER_STEP * global_n
     value = rays_per_step * args.steps / (step_ms * 1e-3)
+    PARTIAL.update({"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
+                    "config": workload_config(world, n_rand), "gpu_launches": launches, "e2e": None})
 
     # ---- e2e: the public train-step API fed from pinned HOST memory, loss read back each step
     host = [tuple(t.cpu().pin_memory() for t in device_batches()) for _ in range(max(args.warmup, 3) + args.steps)]
@@ -263,7 +291,10 @@ def main():
             flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            loss, psnr = tr.step_graphed(*host_batches())     # H2D copies + one CUDA-graph replay of the whole step
+            if world == 1:
+                loss, psnr = tr.step_graphed(*host_batches())     # H2D copies + one CUDA-graph replay of the whole step
+            else:   # multi-GPU: eager launches (the step contains an NCCL all-reduce; its graph capture is not validated)
+                loss, psnr = tr.step(*[t.to(dev, non_blocking=True) for t in host_batches()])
             _ = float(loss)                      # D2H of the step's result (synchronises)
             e1.record()
             evs.append((e0, e1))

@@ -125,7 +125,6 @@ int mlp_fp32_bwd(const float* params, const void* stash, const float* d_raw, int
                  float* grads, void* ws, cudaStream_t st);
 // tcgen05 MLP (mlp_tc.cu)
 size_t mlp_tc_packed_bytes();
-int weight_piece_bytes();
 void tc_set_trace(long long* dev);
 long long* tc_get_trace();
 size_t mlp_tc_stash_bytes(int64_t m);

@@ -1,20 +1,21 @@
 // NeRF MLP (DS_NeRF/run_nerf_helpers.py:74-127) fused with sampling-point generation and positional
 // encoding (run_nerf.py:56-71, 670; helpers:22-70) on the 5th-generation tensor cores (tcgen05).
 //
-// One persistent CTA per SM, 320 threads:
-//   warp 0      weight producer: streams pre-swizzled bf16 weight chunks (32 KB = [256 out x 64 in]) from
-//               L2/HBM into a 3-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarrier tx counts
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256|128, K=16), accumulators in TMEM
-//   warps 2-5   epilogue / prologue of tile A (rows 0..127 -> TMEM lanes 0..127)
-//   warps 6-9   epilogue / prologue of tile B
-// Two 128-sample tiles are in flight per CTA and ping-pong on the tensor pipe: while tile A's epilogue turns
-// its fp32 accumulator (TMEM, 256 columns) into the next layer's bf16 A-operand (bias, ReLU, cast, 128B-swizzled
-// store to shared memory, in place), tile B's layer runs on the tensor cores, and vice versa.  Activations
-// never leave the SM; HBM sees 24 B in + 16 B out per sample (plus the bf16 stash in training).
+// Persistent CTA PAIRS (thread-block clusters of 2 on neighbouring SMs, cta_group::2 MMAs), 576 threads per CTA:
+//   warp 0      weight producer: this CTA's HALF (its 128 of 256 output rows) of every pre-swizzled bf16 weight chunk,
+//               cp.async.bulk (TMA engine) into a 3-slot ring of two-chunk groups, mbarrier tx counts
+//   warp 1      leader CTA: one lane issues the pair's tcgen05.mma (M = 256 = one tile slot of both CTAs, N = 256|128,
+//               K = 16) and the multicast commits; peer CTA: relays "my weight halves have landed" to the leader
+//   warps 2-9   epilogue / prologue of tile slot 0 (rows 0..127 -> TMEM lanes 0..127, 2 column halves x 4 lane quarters)
+//   warps 10-17 epilogue / prologue of tile slot 1
+// Two 128-sample tiles per CTA ping-pong on the tensor pipe: while slot 0's epilogue turns its fp32 accumulator (TMEM,
+// 256 columns) into the next layer's bf16 A operand (bias, ReLU, cast, 128B-swizzled store to shared memory, in place),
+// slot 1's layer runs on the tensor cores, and vice versa.  Activations never leave the SM; HBM sees 24 B in + 16 B out
+// per sample (plus the bf16 stash in training).  See the comment above mlp_fwd_kernel for the barrier protocol.
 //
 // The 63-wide skip input of layer 5 and the 27-wide view encoding of the views layer are applied as a
 // second accumulating pass (K=64 / K=32) after the 256-wide pass, so the 128x256 activation tile can be
-// updated in place; the encodings stay packed in registers in between.
+// updated in place; the encodings are re-derived from the 3-D point while the previous pass runs.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -26,31 +27,16 @@ using namespace tc;
 
 size_t mlp_tc_packed_bytes() { return kPackedBytes; }
 
-// bytes per bulk copy of the weight producers (SPN_W_PIECE = 4096 | 8192 | 16384 for timing experiments)
 // diagnostic timeline buffer (device pointer, kTraceSlots int64): see tools/trace_fwd.py
 static long long* g_trace = nullptr;
 void tc_set_trace(long long* dev) { g_trace = dev; }
 long long* tc_get_trace() { return g_trace; }
 constexpr int kTraceRounds = 3, kTraceEvents = 24;
 constexpr int kTraceSlots = kTraceRounds * 12 * 2 * kTraceEvents;
-__device__ __forceinline__ long long gtimer_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 __device__ __forceinline__ void trace_stamp(long long* tr, int it, int s, int t, int e) {
   if (it < kTraceRounds) tr[((it * 12 + s) * 2 + t) * kTraceEvents + e] = clock64();
 }
 
-int weight_piece_bytes() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("SPN_W_PIECE");
-    v = e ? atoi(e) : 16384;
-    if (v != 4096 && v != 8192 && v != 16384) v = 16384;
-  }
-  return v;
-}
 
 struct ChunkDesc {
   int src_off;   // float offset of the tensor inside the flat parameter vector (+ n0 for transposed chunks)
@@ -172,7 +158,6 @@ struct FwdParams {
   float* raw;
   uint8_t* stash;   // nullable
   int num_quads;    // groups of 4 tiles: one round of a CTA pair (2 tile slots per CTA)
-  int prefetch;     // SPN_W_PREFETCH (experiment): L2-prefetch the next layer's chunks
   long long* trace; // diagnostic (spn_tc_set_trace): clock64 stamps of CTA 0's pipeline events, NULL = off
 };
 
@@ -681,7 +666,6 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   int64_t tiles = (m + kTileM - 1) / kTileM;
   p.num_quads = (int)((tiles + 3) / 4);
   p.trace = g_trace;
-  { static int pf = getenv("SPN_W_PREFETCH") ? atoi(getenv("SPN_W_PREFETCH")) : 0; p.prefetch = pf; }
   const int pairs = sm_count() / 2;
   int grid = 2 * (p.num_quads < pairs ? p.num_quads : pairs);
   auto kern = stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>;
