@@ -172,8 +172,6 @@ def main():
     if args.impl == "reference":
         args.deadline = max(args.deadline, 1200.0)       # host-only run: nothing to protect but the caller's patience
     if args.deadline > 0:
-        import threading
-
         def _watchdog():
             time.sleep(args.deadline)
             sys.stderr.write(f"bench.py: deadline of {args.deadline:.0f} s exceeded, aborting\n"); sys.stderr.flush()
