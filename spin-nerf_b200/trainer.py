@@ -222,6 +222,9 @@ class Trainer:
         first call runs eagerly (allocates every pooled buffer), the second captures, later ones replay; shapes must
         not change.  Returns (loss, psnr) as views of static buffers (valid until the next call)."""
         ins = (rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp)
+        if self.sharder.world > 1:
+            raise NotImplementedError("Trainer.step_graphed: graph capture of the step's NCCL all-reduce is not validated; "
+                                      "use Trainer.step / step_from_pool on multi-GPU runs")
         if self._graph is None:
             self._static_in = [torch.empty(t.shape, dtype=torch.float32, device=self.device) for t in ins]
             if self.adam_state is None:
