@@ -80,3 +80,49 @@ def train_step(rb, target, tdisp, pc, pf, st_c, st_f, lr, n_samples=64, n_import
         for k in p:
             p[k], st.m[k], st.v[k] = O.adam_step(p[k], g[k], st.m[k], st.v[k], st.step, lr)
     return box["loss"], gc, gf
+
+
+def spin_step_grads(batches, pc, pf, one_chunk, n_samples=64, n_importance=64, lindisp=True, white_bkgd=True):
+    """Loss and parameter gradients of the SPIn-NeRF step (run_nerf.py:1455-1521, default flags) for
+    batches = [(rb_unmasked, rgb_target), (rb_masked, rgb_target), (rb_inpainted, disp_target)]:
+      one_chunk=False: three render calls as in the reference — MSE on rgb/rgb0 for the first two (the second with
+                       detach_weights=True), MSE on disp/disp0 for the third — gradients summed;
+      one_chunk=True:  the three ray batches concatenated into one render call, every loss term and detach_weights
+                       applied to its ray range (what spin-nerf_b200/trainer.py:Trainer.step launches on the GPU).
+    Deterministic sampling (perturb=0, no noise).  Returns (loss, grads_coarse, grads_fine)."""
+    (rb1, t1), (rb2, t2), (rb3, t3) = batches
+    n1, n2, n3 = len(rb1), len(rb2), len(rb3)
+    if not one_chunk:
+        total, gc_sum, gf_sum = 0.0, None, None
+        for i, (rb, tgt) in enumerate(batches):
+            box = {}
+
+            def g_out(o, i=i, tgt=tgt, box=box):
+                a, b = ("rgb_map", "rgb0") if i < 2 else ("disp_map", "disp0")
+                la, ga = mse_grad(o[a], tgt); lb, gb = mse_grad(o[b], tgt)
+                box["loss"] = la + lb
+                return {a: ga, b: gb}
+            _, gc, gf = render_with_grads(rb, pc, pf, n_samples, n_importance, lindisp, white_bkgd, g_out,
+                                          detach_weights=(i == 1))
+            total += box["loss"]
+            gc_sum = gc if gc_sum is None else {k: gc_sum[k] + gc[k] for k in gc}
+            gf_sum = gf if gf_sum is None else {k: gf_sum[k] + gf[k] for k in gf}
+        return total, gc_sum, gf_sum
+    rb = np.concatenate([rb1, rb2, rb3], 0)
+    box = {}
+
+    def g_out(o):
+        g = {k: np.zeros_like(o[k]) for k in ("rgb_map", "rgb0", "disp_map", "disp0")}
+        loss = 0.0
+        for lo, hi, tgt, keys in ((0, n1, t1, ("rgb_map", "rgb0")), (n1, n1 + n2, t2, ("rgb_map", "rgb0")),
+                                  (n1 + n2, n1 + n2 + n3, t3, ("disp_map", "disp0"))):
+            for k in keys:
+                l, gk = mse_grad(o[k][lo:hi], tgt)
+                loss += l
+                g[k][lo:hi] = gk
+        box["loss"] = loss
+        return g
+    detach = np.zeros(n1 + n2 + n3, bool)
+    detach[n1:n1 + n2] = True
+    _, gc, gf = render_with_grads(rb, pc, pf, n_samples, n_importance, lindisp, white_bkgd, g_out, detach_weights=detach)
+    return box["loss"], gc, gf

@@ -159,3 +159,28 @@ def test_train_step_oracle_matches_reference_autograd():
     for nm, p in (("c", pc), ("f", pf)):
         for k, v in p.items():
             close_mostly(v.reshape(-1)[::997], tr[f"p_sub__{nm}__{k}"], rtol=0, atol=2e-4, max_frac=0.03, hard=1.0)
+
+
+def test_one_chunk_step_equals_three_render_calls():
+    """The reformulation the GPU trainer relies on (rays are independent; losses and detach_weights per ray range): in the
+    numpy oracle the gradients of one concatenated render equal the summed gradients of the reference's three calls."""
+    from oracle import train_oracle as TO
+    g = load_golden("render")
+    rng = np.random.default_rng(1)
+    rays = g["rays"]
+    n = rays.shape[1]
+    batches = []
+    for i, m in enumerate((10, 7, 9)):
+        ix = rng.permutation(n)[:m]
+        rb = O.make_ray_batch(rays[0][ix], rays[1][ix], 1.2, 8.0)
+        batches.append((rb, rng.uniform(0, 1, (len(ix), 3) if i < 2 else (len(ix),)).astype(np.float32)))
+    pc, pf = O.init_params(11), O.init_params(12)
+    for p in (pc, pf):
+        p["alpha_linear.bias"] = p["alpha_linear.bias"] + np.float32(1.0)
+    l3, gc3, gf3 = TO.spin_step_grads(batches, pc, pf, one_chunk=False)
+    l1, gc1, gf1 = TO.spin_step_grads(batches, pc, pf, one_chunk=True)
+    assert abs(l1 - l3) <= 1e-6 * abs(l3)
+    for a, b in ((gc1, gc3), (gf1, gf3)):
+        for k in a:
+            scale = np.abs(b[k]).max()
+            assert np.abs(a[k] - b[k]).max() <= 2e-5 * max(scale, 1e-12), k
