@@ -347,8 +347,9 @@ __device__ __forceinline__ uint32_t epi_final32(const uint32_t (&v)[32], const i
 // half of the weight chunk from shared memory (128 of the 256 output rows) and loads only that half from L2: per-SM
 // shared-memory traffic per layer drops from 336 KB to 224 KB (operand reads 192 -> 128, weight writes 80 -> 32), which
 // is what bounded the single-CTA version (tools/trace_fwd.py: MMAs ran at ~190 instead of 128 cycles with the
-// 128 B/cycle/SM shared-memory pipe saturated).  With 16 KB half-chunks the 96 KB ring has 6 slots: a layer's four
-// chunks are loaded ONCE per round and stay resident for both tile slots, two slots prefetch the next layer.
+// 128 B/cycle/SM shared-memory pipe saturated).  With 16 KB half-chunks the 96 KB ring holds 6 of them: a layer's four
+// chunks are loaded ONCE per round and stay resident for both tile slots, the rest prefetches the next layer (see the
+// ring / barrier comment inside the kernel; tests/test_ring_protocol_model.py is an executable model of the protocol).
 //   leader CTA (cluster rank 0): warp 1 lane 0 issues the MMAs and the multicast commits (ring slot free / accumulator
 //     ready arrive on the same barrier offsets in both CTAs)
 //   peer CTA: warp 1 lane 0 relays "my halves of this weight group have landed" to the leader's group barrier
