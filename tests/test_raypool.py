@@ -1,0 +1,94 @@
+"""Ray pools (spin-nerf_b200/raypool.py) against a restatement of the array pipeline of
+DS_NeRF/run_nerf.py:1225-1318 on a synthetic scene; get_rays_np itself is checked against the imported reference where
+/root/reference exists.  CPU only."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sio = importlib.import_module("spin-nerf_b200.scene_io")
+rp = importlib.import_module("spin-nerf_b200.raypool")
+HAVE_REF = os.path.isfile("/root/reference/DS_NeRF/run_nerf_helpers.py")
+
+
+def reference_arrays(images, poses, hwf, masks, depths, i_train, prepare, train_gt):
+    """run_nerf.py:1228-1318 restated with the reference's array shapes: [N, ro+rd+rgb, H, W, 3] stacks with the label as a
+    4th component, transposed to [N,H,W,3,4], training views only, flattened; then the three boolean selections."""
+    H, W, focal = hwf
+    rays = np.stack([np.stack(rp.camera_rays(H, W, focal, p), 0) for p in poses[:, :3, :4]], 0)          # [N,2,H,W,3]
+
+    def with_label(label):
+        lab = np.repeat(label[:, None, :, :, None], 3, axis=1)                                             # [N,3,H,W,1]
+        a = np.concatenate([np.concatenate([rays, images[:, None]], 1), lab], -1)                          # [N,3,H,W,4]
+        a = np.transpose(a, [0, 2, 3, 1, 4])
+        return np.stack([a[i] for i in i_train], 0).reshape(-1, 3, 4).astype(np.float32)
+    rays_rgb, rays_inp = with_label(masks), with_label(depths)
+    clf = rays_rgb.reshape(-1, 3, 4) if (train_gt or prepare) else rays_rgb[rays_rgb[:, :, 3] == 0].reshape(-1, 3, 4)
+    inp = rays_inp[rays_rgb[:, :, 3] != 0].reshape(-1, 3, 4)
+    rgb = rays_rgb if prepare else rays_rgb[rays_rgb[:, :, 3] == 1].reshape(-1, 3, 4)
+    return clf, inp, rgb
+
+
+@pytest.mark.parametrize("prepare,train_gt,lpips", [(False, False, True), (False, False, False), (False, True, True), (True, False, True)])
+def test_pools_reproduce_the_reference_arrays(prepare, train_gt, lpips, tmp_path):
+    sio.synthetic_scene(str(tmp_path), n_views=8, hw=(20, 28), factor=2, seed=6, n_unlabelled=1)
+    images, poses, bds, render_poses, i_test, masks, depths, _ = sio.load_scene(str(tmp_path), factor=2, lpips=lpips, prepare=prepare)
+    hwf = (int(poses[0, 0, 4]), int(poses[0, 1, 4]), poses[0, 2, 4])
+    i_train = [i for i in range(len(images)) if i != i_test]
+    pools = rp.build_ray_pools(images, poses, hwf, masks, depths, i_train, prepare=prepare, train_gt=train_gt)
+    clf, inp, rgb = reference_arrays(images, poses, hwf, masks, depths, i_train, prepare, train_gt)
+    for idx, ref, fourth in ((pools.idx_clf, clf, pools.label), (pools.idx_inp, inp, pools.disp), (pools.idx_rgb, rgb, pools.label)):
+        assert len(idx) == len(ref)
+        assert np.array_equal(pools.o[idx], ref[:, 0, :3]) and np.array_equal(pools.d[idx], ref[:, 1, :3])
+        assert np.array_equal(pools.rgb[idx], ref[:, 2, :3])
+        assert np.array_equal(fourth[idx], ref[:, 0, 3]) and np.array_equal(fourth[idx], ref[:, 2, 3])
+    if not prepare and not train_gt:
+        assert len(pools.idx_clf) + len(pools.idx_inp) == len(pools.label)            # a pixel is either background or not
+        if lpips:                                                                     # only one view keeps label +1 (load_llff.py:161)
+            per_view = len(pools.label) // len(i_train)
+            assert len(np.unique(pools.idx_rgb // per_view)) == 1
+
+
+def test_sampling_draws_each_group_from_its_own_set(tmp_path):
+    sio.synthetic_scene(str(tmp_path), n_views=8, hw=(20, 28), factor=2, seed=8, n_unlabelled=1)
+    images, poses, bds, _, i_test, masks, depths, _ = sio.load_scene(str(tmp_path), factor=2, lpips=True)
+    hwf = (int(poses[0, 0, 4]), int(poses[0, 1, 4]), poses[0, 2, 4])
+    kept = 8 - 5                                    # the view that keeps label +1 under --lpips (load_llff.py:161)
+    i_train = [i for i in range(8) if i != i_test or i == kept]
+    pools = rp.build_ray_pools(images, poses, hwf, masks, depths, i_train)
+    idx = pools.sample_indices(64, np.random.default_rng(0))
+    assert idx.shape == (3, 64)
+    assert np.all(pools.label[idx[0]] == 0) and np.all(pools.label[idx[1]] == 1) and np.all(pools.label[idx[2]] != 0)
+    assert len(np.unique(idx[0])) == 64                                                # without replacement while the set is large enough
+
+
+def test_device_side_index_draw_respects_the_groups(tmp_path):
+    import torch
+    sio.synthetic_scene(str(tmp_path), n_views=8, hw=(20, 28), factor=2, seed=8, n_unlabelled=1)
+    images, poses, bds, _, i_test, masks, depths, _ = sio.load_scene(str(tmp_path), factor=2, lpips=True)
+    hwf = (int(poses[0, 0, 4]), int(poses[0, 1, 4]), poses[0, 2, 4])
+    pools = rp.build_ray_pools(images, poses, hwf, masks, depths, list(range(8)))
+    dev = pools.to("cpu")
+    assert dev["pool_od"].shape == (2, len(pools.label), 3) and dev["idx_clf"].dtype == torch.int64
+    g = torch.Generator(); g.manual_seed(0)
+    idx = rp.draw_step_indices(dev, 256, g)
+    assert idx.shape == (3, 256)
+    lab = torch.from_numpy(pools.label)
+    assert bool((lab[idx[0]] == 0).all()) and bool((lab[idx[1]] == 1).all()) and bool((lab[idx[2]] != 0).all())
+    assert torch.equal(dev["rgb"][idx[0]], torch.from_numpy(pools.rgb)[idx[0]])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="the reference checkout only exists in the build container")
+def test_camera_rays_match_reference_get_rays_np():
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    H, _ = ref_loader.load()
+    rng = np.random.default_rng(0)
+    c2w = rng.normal(size=(3, 4)).astype(np.float32)
+    o, d = rp.camera_rays(30, 41, 37.5, c2w)
+    ro, rd = H.get_rays_np(30, 41, 37.5, c2w)
+    assert np.array_equal(o, ro) and np.array_equal(d, rd)
