@@ -40,9 +40,18 @@ def flatten_rays(rays):
 
 
 def reference_loader():
-    sys.path.insert(0, os.path.join(ROOT, "spin-nerf_b200", "compat"))
-    sys.path.insert(0, "/root/reference/DS_NeRF")
-    return importlib.import_module("load_llff")
+    """The unmodified DS_NeRF/load_llff.py with the cv2-backed imageio stand-in of spin-nerf_b200/compat (this image has no
+    imageio; other tests may have left an empty stub module under that name)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("imageio", os.path.join(ROOT, "spin-nerf_b200", "compat", "imageio.py"))
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    sys.modules["imageio"] = shim
+    if "/root/reference/DS_NeRF" not in sys.path:
+        sys.path.insert(0, "/root/reference/DS_NeRF")
+    mod = importlib.import_module("load_llff")
+    mod.imageio = shim
+    return mod
 
 
 def run_reference(ref, scene_dir, kw):
