@@ -173,6 +173,13 @@ def workload_config(n_gpus, n_rand):
 
 # ------------------------------------------------------------------------------------------------
 PARTIAL = {}     # rank 0's result line as far as it is known; the watchdog prints it if a later phase hangs
+T_START = time.perf_counter()
+
+
+def phase(msg):
+    """stderr breadcrumb (rank 0 only): if a run ever stalls, the log says in which phase"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench +{time.perf_counter() - T_START:6.1f}s] {msg}\n"); sys.stderr.flush()
 
 
 def main():
@@ -206,7 +213,6 @@ def main():
 
     import torch
     spn = importlib.import_module("spin-nerf_b200")
-    from oracle import nerf_oracle as O            # weights init + cpu_baseline leg only
     trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,16 +220,23 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # One 4.8 MB all-reduce per step is latency-bound either way, so the in-switch (NVLS) algorithm buys nothing here;
+        # its multicast set-up is the most fragile part of NCCL initialisation inside containers, and an unexplained
+        # 8-GPU hang cost this project a round's GPU budget.  Off unless the caller asks for it; collectives that stall
+        # abort the job after 3 minutes instead of torch's default 10.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        phase(f"init_process_group nccl world={world}")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     prec = spn.PREC_BF16 if args.precision == "bf16" else spn.PREC_FP32
 
     # ---- model: reference-shaped coarse + fine networks, seeded init (identical on every rank)
     nets = []
     for seed in (1, 2):
         net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
-        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.init_params(seed).items()})
-        net = net.to(dev); net.precision = prec
+        net = net.seeded_init_(seed).to(dev); net.precision = prec
         nets.append(net)
     n_rand = args.n_rand
     sharder = trainer_mod.RaySharder(rank, world)
@@ -266,12 +279,14 @@ def main():
 
     barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
     clocks = ClockSampler(local); clocks.start()         # nvidia-smi needs ~1 s to start streaming samples
+    phase(f"scene resident ({M} rays); {args.warmup} warm-up steps")
     run_steps(args.warmup, None, False)
     barrier(); torch.cuda.synchronize()
     L = spn._lib.lib()
     L.spn_profile_enable(1); L.spn_launch_count(1)
     clocks.rows.clear()                                   # keep only samples taken during the timed region
     t_wall = time.perf_counter()
+    phase(f"{args.steps} timed steps")
     times, loss = run_steps(args.steps, None, True)
     torch.cuda.synchronize(); barrier()
     wall = time.perf_counter() - t_wall
@@ -295,6 +310,7 @@ def main():
                     "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
                     "config": workload_config(world, n_rand), "gpu_launches": launches, "e2e": None})
 
+    phase(f"device-timed value = {value:.0f} rays/s; e2e pass from pinned host batches")
     # ---- e2e: the public train-step API fed from pinned HOST memory, loss read back each step
     host = [tuple(t.cpu().pin_memory() for t in device_batches()) for _ in range(max(args.warmup, 3) + args.steps)]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -326,6 +342,7 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = rays_per_step * args.steps / (e2e_ms * 1e-3)
 
+    phase("e2e done")
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -374,7 +391,8 @@ def main():
                     "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
+        phase("cpu_baseline sample (oracle port on the host cores)")
         t0 = time.perf_counter()
         cores, limits = cpu_threads_best()
         with (limits(limits=cores) if limits else __import__("contextlib").nullcontext()):

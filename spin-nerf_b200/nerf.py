@@ -147,6 +147,20 @@ class NeRF(nn.Module):
         raw = _MLPFunction.apply(self, need_grad, x6, *params)
         return raw.reshape(*sh[:-1], 4)
 
+    def seeded_init_(self, seed, scale=1.0):
+        """nn.Linear-style uniform init U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (what helpers:86-102 get from torch's default
+        initialiser) drawn from a numpy PCG64 stream in registration order, so that every rank, every machine and the
+        test-side checker derive the same synthetic weights from a seed without shipping them.  Returns self."""
+        import numpy as np
+        rng = np.random.default_rng(seed)
+        with torch.no_grad():
+            for p in self._flat_params():          # weight then bias of each Linear, both bounded by the layer's fan-in
+                if p.dim() == 2:
+                    bound = scale / np.sqrt(p.shape[1])
+                p.copy_(torch.from_numpy(rng.uniform(-bound, bound, size=tuple(p.shape)).astype(np.float32)))
+        self.mark_params_changed()
+        return self
+
     def load_weights_from_keras(self, weights):
         """helpers:129-156."""
         import numpy as np

@@ -50,7 +50,11 @@ class Trainer:
         dev = net_c.flat_params().device
         self.device = dev
         z = lambda: torch.zeros(L.MLP_NPARAMS, device=dev)
-        self.grads = [z(), z()]
+        # both networks' flat gradients live in ONE buffer (the fine network's vector starts at the next 512-byte boundary,
+        # i.e. with the alignment of a fresh allocation): one memset and one all-reduce per step
+        stride = (L.MLP_NPARAMS + 127) // 128 * 128
+        self.grad_all = torch.zeros(2 * stride, device=dev)
+        self.grads = [self.grad_all[:L.MLP_NPARAMS], self.grad_all[stride:stride + L.MLP_NPARAMS]]
         self.m = [z(), z()]
         self.v = [z(), z()]
         self.global_step = 0
@@ -136,8 +140,7 @@ class Trainer:
                                          L.ptr(tgt_rgb), L.ptr(depth_inp), n1, n2, n3, L.ptr(sums), L.ptr(g_rgb),
                                          L.ptr(g_rgb0), L.ptr(g_disp), L.ptr(g_disp0), L.ptr(out), L.stream()),
                 "spn_train_losses")
-        for g in self.grads:
-            g.zero_()
+        self.grad_all.zero_()
         gc, gf = self.grads
         chunk_backward(cfg, k, self.net_c, self.net_f,
                        {"rgb_map": g_rgb, "rgb0": g_rgb0, "disp_map": g_disp, "disp0": g_disp0}, gc, gf,
@@ -152,8 +155,7 @@ class Trainer:
         rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
         rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
         rays_inp, depth_inp = sh.shard(rays_inp, 1), sh.shard(depth_inp)
-        for g in self.grads:
-            g.zero_()
+        self.grad_all.zero_()
         gc, gf = self.grads
         mse_g = lambda x, t: (2.0 / x.numel()) * (x - t)
         losses = []
@@ -197,7 +199,7 @@ class Trainer:
         """NCCL all-reduce (mean over ranks) of the two flat gradient vectors, then one Adam launch per network;
         learning-rate schedule of run_nerf.py:1616-1622.  With `self.adam_state` set (CUDA-graph mode) the step counter
         and schedule live on the device (spn_adam_tick / spn_adam_step_dev) so the launches are replayable."""
-        scale = allreduce_sum_(self.grads, self.pg) if self.sharder.world > 1 else 1.0
+        scale = allreduce_sum_([self.grad_all], self.pg) if self.sharder.world > 1 else 1.0
         self.global_step += 1
         if self.adam_state is not None:
             L.check(L.lib().spn_adam_tick(L.ptr(self.adam_state), self.lr0, 0.1, float(self.lrate_decay * 1000),

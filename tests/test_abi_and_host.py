@@ -55,6 +55,16 @@ def test_nerf_module_is_reference_shaped_and_flat():
         net(torch.zeros(3, 6))                                                      # CPU tensor: loud, no fallback
 
 
+def test_seeded_init_is_the_checkers_weight_stream():
+    """bench.py / tools derive their synthetic weights inside the product package (no oracle import on the product
+    path); the tests' checker derives the same ones from the same seed."""
+    net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True).seeded_init_(7)
+    ref = O.init_params(7)
+    sd = net.state_dict()
+    assert all(np.array_equal(sd[k].numpy(), ref[k]) for k in ref)
+    np.testing.assert_array_equal(net.flat_params().numpy(), np.concatenate([ref[k].reshape(-1) for k, _ in O.PARAM_SHAPES]))
+
+
 def test_nerf_rgb_state_dict_has_no_alpha_linear():
     a = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     m = spn.NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, alpha_model=a)

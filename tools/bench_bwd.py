@@ -6,13 +6,12 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import nerf_oracle as O
 
 spn = importlib.import_module("spin-nerf_b200")
 L = spn._lib
 dev = "cuda"
 net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
-net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.init_params(1).items()}); net = net.to(dev)
+net = net.seeded_init_(1).to(dev)
 flat, packed = net._sync()
 for M in [int(a) for a in sys.argv[1:]] or [8192, 65536, 131072, 1048576]:
     x6 = torch.randn(M, 6, device=dev); draw = torch.randn(M, 4, device=dev)
