@@ -9,8 +9,10 @@ from . import _lib
 from ._lib import PREC_BF16, PREC_FP32, LIB_PATH, MLP_NPARAMS
 from . import ops
 from .nerf import NeRF, NeRF_RGB, default_precision, set_default_precision
-from .render import render, render_rays, batchify_rays, render_path, render_rays_composed
+from .render import render, render_rays, batchify_rays, render_path, render_path_sharded, render_rays_composed
+from . import frame_io, lpips_patch
 
-__all__ = ["ops", "NeRF", "NeRF_RGB", "render", "render_rays", "batchify_rays", "render_path", "PREC_BF16",
+__all__ = ["ops", "NeRF", "NeRF_RGB", "render", "render_rays", "batchify_rays", "render_path", "render_path_sharded",
+           "frame_io", "lpips_patch", "PREC_BF16",
            "PREC_FP32", "set_default_precision", "default_precision"]
 __version__ = "0.1.0"

@@ -15,6 +15,7 @@ import torch
 from . import _lib as L
 from . import ops
 from ._lib import check, f32, lib, ptr, stream
+from .frame_io import FrameWriter, dump_frame, to8b
 from .nerf import NeRF, NeRF_RGB
 
 _DIFF = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0")
@@ -243,6 +244,10 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
     if not use_viewdirs:
         raise NotImplementedError("spinnerf_b200 implements the use_viewdirs=True path")
     if c2w is not None:
+        c2w = torch.as_tensor(c2w)
+        if not c2w.is_cuda:     # the reference keeps its poses on the default (CUDA) device; a host pose is 48 bytes to move
+            net = kwargs.get("network_fn") or kwargs.get("network_fine")
+            c2w = c2w.to(next(net.parameters()).device)
         rays_o, rays_d = ops.get_rays(H, W, focal, c2w, patch)
     else:
         rays_o, rays_d = rays
@@ -269,25 +274,27 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
 
-def to8b(x):
-    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
-
-
 def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
                 disp_require_grad=False, need_alpha=False, rgb_require_grad=False, detach_weights=False,
                 patch_len=None, masks=None):
     """run_nerf.py:168-307: per-pose render loop (rays generated on the device from c2w), optional
-    LPIPS patch sampling inside the mask bbox (:197-211), optional per-frame dumps (:231-295)."""
+    LPIPS patch sampling inside the mask bbox (:197-211), optional per-frame dumps (:231-295).
+
+    Without gradients (video / test renders) frames leave through frame_io.FrameWriter: device->host copies on a side
+    stream into double-buffered pinned memory and file writes on a worker thread, overlapping the next frame's kernels
+     — the reference blocks on `.cpu()` and on the files after every frame (:221-295)."""
     H, W, focal = hwf
     if render_factor != 0:
         H = H // render_factor; W = W // render_factor; focal = focal / render_factor
     H, W = int(H), int(W)
     if savedir is not None:
         np.savetxt(os.path.join(savedir, 'intrinsics.txt'), np.array([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1]]))
+    with_grad = disp_require_grad or rgb_require_grad
+    writer = None if with_grad else FrameWriter(savedir, gt_imgs, need_alpha)
     rgbs, disps, Xs, Ys = [], [], [], []
     for i, c2w in enumerate(render_poses):
         c2w = torch.as_tensor(c2w)
-        if disp_require_grad or rgb_require_grad:
+        if with_grad:
             patch = None
             if patch_len is not None:
                 masked = np.where(masks[i] != 0)
@@ -298,14 +305,21 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
             rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
                                                    need_alpha=need_alpha, detach_weights=detach_weights, patch=patch,
                                                    **render_kwargs)
+            disps.append(disp if disp_require_grad else disp.detach().cpu().numpy())
+            rgbs.append(rgb if rgb_require_grad else rgb.detach().cpu().numpy())
+            if savedir is not None:
+                N = lambda t: t.detach().cpu().numpy()
+                dump_frame(savedir, i, N(rgb), None if gt_imgs is None else gt_imgs[i], N(depth), N(disp),
+                           N(extras['weights']), N(extras['z_vals']), N(extras['alpha']) if need_alpha else None, N(c2w))
         else:
             with torch.no_grad():
                 rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
                                                        need_alpha=need_alpha, **render_kwargs)
-        disps.append(disp if disp_require_grad else disp.detach().cpu().numpy())
-        rgbs.append(rgb if rgb_require_grad else rgb.detach().cpu().numpy())
-        if savedir is not None:
-            _dump_frame(savedir, i, rgbs[-1], gt_imgs, depth, disp, extras, need_alpha, c2w)
+            writer.submit(i, c2w, dict(rgb=rgb, disp=disp, depth=depth, weights=extras['weights'], z_vals=extras['z_vals'],
+                                       alpha=extras.get('alpha')))
+    if writer is not None:
+        rgbs, disps = writer.close()
+        return rgbs, disps, (Xs, Ys)
     disps = torch.stack(disps, 0) if disp_require_grad else np.stack(disps, 0)
     rgbs = torch.stack(rgbs, 0) if rgb_require_grad else np.stack(rgbs, 0)
     return rgbs, disps, (Xs, Ys)
@@ -336,25 +350,3 @@ def render_path_sharded(render_poses, hwf, chunk, render_kwargs, render_factor=0
         for j, i in enumerate(idx):
             out_rgb[i], out_disp[i] = r_[j], d_[j]
     return out_rgb, out_disp
-
-
-def _dump_frame(savedir, i, rgb, gt_imgs, depth, disp, extras, need_alpha, c2w):
-    import cv2
-    sub = lambda d: os.path.join(savedir, d)
-    for d in ['rgb', 'depth', 'disp', 'weight', 'images', 'z', 'pose'] + (['alpha'] if need_alpha else []):
-        os.makedirs(sub(d), exist_ok=True)
-    rgb_np = rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb
-    rgb8 = to8b(np.nan_to_num(rgb_np))
-    cv2.imwrite(os.path.join(sub('rgb'), '{:06d}.png'.format(i)), rgb8[..., ::-1])
-    if gt_imgs is not None:
-        gt = gt_imgs[i]
-        gt = gt.detach().cpu().numpy() if torch.is_tensor(gt) else gt
-        cv2.imwrite(os.path.join(sub('images'), '{:06d}.png'.format(i)), to8b(gt)[..., ::-1])
-    np.save(os.path.join(sub('depth'), '{:06d}.npy'.format(i)), depth.detach().cpu().numpy())
-    np.save(os.path.join(sub('disp'), '{:06d}.npy'.format(i)), disp.detach().cpu().numpy())
-    np.save(os.path.join(sub('weight'), '{:06d}.npy'.format(i)), extras['weights'].detach().cpu().numpy())
-    np.save(os.path.join(sub('z'), '{:06d}.npy'.format(i)), extras['z_vals'].detach().cpu().numpy())
-    if need_alpha:
-        np.save(os.path.join(sub('alpha'), '{:06d}.npy'.format(i)), extras['alpha'].detach().cpu().numpy())
-    pose = np.concatenate([c2w[:3, :4].detach().cpu().numpy(), np.array([[0, 0, 0, 1]])], axis=0)
-    np.savetxt(os.path.join(sub('pose'), '{:06d}.txt'.format(i)), pose)

@@ -64,9 +64,9 @@ class Trainer:
         self._graph = None
 
     # ---------------------------------------------------------------------------------------
-    def _forward(self, idx, rays_od, detach_weights, rb=None):
+    def _forward(self, idx, rays_od, detach_weights, rb=None, test_kwargs=False):
         """rays_od [2,n,3] (origin, direction) or a ready ray matrix rb [n,11] -> chunk state; random draws made on
-        the device."""
+        the device.  test_kwargs: render like render_kwargs_test (perturb=False, raw_noise_std=0, run_nerf.py:485-488)."""
         if rb is None:
             o, d = rays_od[0], rays_od[1]
             H, W, f = self.hwf if self.hwf is not None else (0, 0, 1.0)
@@ -74,6 +74,8 @@ class Trainer:
         n = rb.shape[0]
         S, NI = self.cfg["N_samples"], self.cfg["N_importance"]
         opts = dict(self.cfg, detach_weights=detach_weights)
+        if test_kwargs:
+            opts.update(perturb=False, raw_noise_std=0.0)
         t_rand = u = n0 = n1 = None
         if opts["perturb"]:
             t_rand = torch.rand(n, S, device=self.device)
@@ -83,7 +85,7 @@ class Trainer:
             n1 = torch.randn(n, S + NI, device=self.device) if NI else None
         return chunk_forward(opts, rb, self.net_c, self.net_f, t_rand, u, n0, n1, train=True, pool=self.pools[idx])
 
-    def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
+    def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp, _apply=True):
         """One optimisation step on this rank's shard of the three ray batches.  Returns the (local) loss and
         psnr like run_nerf.py:1481-1521 defines them for the default flags.
 
@@ -106,9 +108,9 @@ class Trainer:
         tgt_rgb = P("tgt_rgb", (n1 + n2, 3), torch.float32)
         torch.cat([target_clf, target_s], 0, out=tgt_rgb)
         cfg, k = self._forward(0, rays, False)
-        return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3)
+        return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3, _apply)
 
-    def step_from_pool(self, pool_od, rgb_pool, disp_pool, idx):
+    def step_from_pool(self, pool_od, rgb_pool, disp_pool, idx, _apply=True):
         """The same step fed by a device-resident ray pool: pool_od [2,M,3] all rays of the
         scene, rgb_pool [M,3] / disp_pool [M] their colour / inpainted-disparity targets, idx [3,N] int64 the rays
         sampled for the three groups (unmasked, masked, inpainted) of this step.  One gather kernel assembles this
@@ -127,9 +129,9 @@ class Trainer:
                                              L.ptr(tgt_rgb), 2 * m, L.ptr(disp_pool), L.ptr(tgt_disp), L.stream()),
                 "spn_gather_ray_batch")
         cfg, k = self._forward(0, None, False, rb=rb)
-        return self._finish_step(cfg, k, tgt_rgb, tgt_disp, m, m, m)
+        return self._finish_step(cfg, k, tgt_rgb, tgt_disp, m, m, m, _apply)
 
-    def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3):
+    def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3, apply=True):
         n = n1 + n2 + n3
         P = self.shared
         g_rgb, g_rgb0 = P("g_rgb", (n, 3), torch.float32), P("g_rgb0", (n, 3), torch.float32)
@@ -145,9 +147,61 @@ class Trainer:
         chunk_backward(cfg, k, self.net_c, self.net_f,
                        {"rgb_map": g_rgb, "rgb0": g_rgb0, "disp_map": g_disp, "disp0": g_disp0}, gc, gf,
                        self._scratch(cfg), self._ws(cfg), detach_range=(n1, n1 + n2))
-        self.apply_gradients()
+        if apply:
+            self.apply_gradients()
         res = out[:2].clone()          # `out` is a pooled buffer: hand back copies of (loss, psnr)
         return res[0], res[1]
+
+    # ---------------------------------------------------------------------------------------
+    # perceptual-loss branch (run_nerf.py:1523-1561, `--lpips`)
+    def lpips_patch_backward(self, poses, patches, targets, lpips_fn, hwf_s, batch_size=None, weight=0.01):
+        """Renders this rank's share of the step's LPIPS patches and accumulates d(lpips term)/d(params) into the flat
+        gradient buffers; returns this rank's part of the term  sum_i LPIPS(pred_i, target_i).mean() / batch_size / 100
+        (run_nerf.py:1551-1559) as a device scalar.  Call between `step(..., _apply=False)` and `apply_gradients()`
+        (what `step_with_lpips` does).
+
+        poses [B,3,4|5] camera-to-world; patches: B windows (X, Y, len0, len1) on the down-scaled grid hwf_s = (H_s, W_s,
+        focal_s) (lpips_patch.patch_geometry / draw_origins); targets: B tensors [1,3,h,w] in [-1,1]
+        (lpips_patch.PatchSampler.target_patches); lpips_fn(pred, target) any differentiable torch callable.
+
+        Like the reference the patches are rendered with the TEST kwargs and detach_weights=True (:1541-1549), but the
+        rays of each window are generated on the device from c2w (spn_get_rays' patch window) instead of slicing a
+        full-frame ray grid (run_nerf.py:119-123), all B patches share ONE ray chunk, and the chunk runs through the
+        fused forward / backward without autograd: torch autograd only sees LPIPS itself (d term / d rgb).
+        Multi-GPU: whole patches are dealt round-robin to the ranks (LPIPS needs a complete patch on one device); each
+        rank's term is scaled by the world size so that the gradient mean over ranks is the global term's gradient."""
+        B = len(patches)
+        batch_size = B if batch_size is None else int(batch_size)
+        Hs, Ws, fs = hwf_s
+        mine = list(range(self.sharder.rank, B, self.sharder.world))
+        if not mine:
+            return torch.zeros((), device=self.device)
+        ros, rds, shapes = [], [], []
+        for i in mine:
+            ro, rd = ops.get_rays(Hs, Ws, fs, torch.as_tensor(poses[i], device=self.device)[:3, :4], patch=patches[i])
+            ros.append(ro.reshape(-1, 3)); rds.append(rd.reshape(-1, 3)); shapes.append(tuple(ro.shape[:2]))
+        rb = ops.build_ray_batch(torch.cat(ros), torch.cat(rds), self.near, self.far, self.ndc, Hs, Ws, fs)
+        cfg, k = self._forward(0, None, True, rb=rb, test_kwargs=True)
+        rgb = k["rgb_map"].detach().clone().requires_grad_(True)        # [n,3]: the only tensor torch autograd sees
+        term, off = 0.0, 0
+        for i, (h, w) in zip(mine, shapes):
+            pred = ((rgb[off:off + h * w].view(h, w, 3) - 0.5) * 2).permute(2, 0, 1)[None, ...]      # :1552
+            term = term + lpips_fn(pred, targets[i].to(self.device)).mean()
+            off += h * w
+        term = term * (float(weight) / batch_size)
+        g_rgb, = torch.autograd.grad(term * float(self.sharder.world), rgb)
+        gc, gf = self.grads
+        chunk_backward(cfg, k, self.net_c, self.net_f, {"rgb_map": g_rgb.contiguous()}, gc, gf,
+                       self._scratch(cfg), self._ws(cfg))
+        return term.detach()
+
+    def step_with_lpips(self, batch, poses, patches, targets, lpips_fn, hwf_s, batch_size=None, from_pool=False):
+        """The `--lpips` train step (iterations > 300, run_nerf.py:1523): `batch` = the six tensors of `step` (or the
+        four arguments of `step_from_pool` with from_pool=True), then the patch branch, then ONE optimiser step."""
+        loss, psnr = (self.step_from_pool if from_pool else self.step)(*batch, _apply=False)
+        lp = self.lpips_patch_backward(poses, patches, targets, lpips_fn, hwf_s, batch_size)
+        self.apply_gradients()
+        return loss + lp, psnr
 
     def step_three_calls(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
         """The same step as three separate render calls, exactly in the reference's order (kept for parity tests)."""

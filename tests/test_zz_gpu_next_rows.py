@@ -1,0 +1,165 @@
+"""GPU checks of the rows SURVEY.md section 8 marks "next": the LPIPS-patch branch of the train step (f2) and the frame
+path of render_path (a10 / f4).  Both are compositions of kernels whose numerics tests/test_gpu_parity.py pins against the
+reference; what is checked here is the composition: the fused no-autograd patch step against the same computation through
+the autograd render() API, and the asynchronous frame sink against plain per-frame renders.  Needs a B200: pytest -m gpu"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+spn = importlib.import_module("spin-nerf_b200")
+DEV = "cuda"
+HWF = (24, 32, 28.8)
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def make_net(seed, precision):
+    p = O.init_params(seed)
+    p["alpha_linear.bias"] = p["alpha_linear.bias"] + np.float32(1.0)
+    net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+    net = net.to(DEV)
+    net.precision = precision
+    return net
+
+
+def poses(n, seed=0):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 3, 5), np.float32)
+    for i in range(n):
+        out[i, :, :3] = np.eye(3)
+        out[i, :, 3] = [0.1 * i, -0.2 + 0.05 * i, 0.0]
+        out[i, :, :3] += rng.standard_normal((3, 3)).astype(np.float32) * 0.02
+    return out
+
+
+def render_kwargs(netc, netf):
+    return dict(network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64, N_importance=64, lindisp=True,
+                white_bkgd=True, perturb=0., raw_noise_std=0., use_viewdirs=True, ndc=False, near=1.2, far=8.0)
+
+
+def trainer(prec, perturb):
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    netc, netf = make_net(11, prec), make_net(12, prec)
+    tr = trainer_mod.Trainer(netc, netf, lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                             perturb=perturb, raw_noise_std=perturb, near=1.2, far=8.0, hwf=HWF)
+    return tr, netc, netf
+
+
+def lpips_net():
+    return importlib.import_module("spin-nerf_b200.compat.lpips").LPIPS().to(DEV)
+
+
+PATCHES = [(2, 3, 6, 7), (10, 20, 6, 7), (20, 28, 6, 7)]        # the last one sticks out of the 24x32 frame: 4x4
+SHAPES = [(6, 7), (6, 7), (4, 4)]
+
+
+def patch_targets(seed=1):
+    rng = np.random.default_rng(seed)
+    return [T(rng.uniform(-1, 1, (1, 3, h, w)).astype(np.float32)) for h, w in SHAPES]
+
+
+def test_lpips_patch_backward_matches_autograd_render():
+    """Trainer.lpips_patch_backward (one fused chunk for all patches, no autograd around the renderer) against the
+    reference's formulation (run_nerf.py:1541-1559): one render(c2w=..., patch=..., detach_weights=True) per view with
+    the test kwargs, LPIPS per patch, sum / batch_size / 100, backward through autograd."""
+    P = poses(3)
+    lp = lpips_net()
+    tgts = patch_targets()
+    tr, netc, netf = trainer(spn.PREC_FP32, 1.0)        # the trainer's own kwargs are the noisy TRAIN ones: must not leak
+    term = tr.lpips_patch_backward(P, PATCHES, tgts, lp, HWF)
+    torch.cuda.synchronize()
+    g_c, g_f = N(tr.grads[0]).copy(), N(tr.grads[1]).copy()
+
+    netc2, netf2 = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    kw = render_kwargs(netc2, netf2)
+    total = 0
+    for pose, patch, tgt, shp in zip(P, PATCHES, tgts, SHAPES):
+        rgb = spn.render(*HWF, chunk=32768, c2w=T(pose[:3, :4]), patch=patch, detach_weights=True, retraw=True, **kw)[0]
+        assert tuple(rgb.shape) == shp + (3,)
+        total = total + lp(((rgb - 0.5) * 2).permute(2, 0, 1)[None, ...], tgt).mean()
+    total = total / 3 / 100
+    total.backward()
+    torch.cuda.synchronize()
+    flat = lambda net: np.concatenate([(N(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)).reshape(-1)
+                                       for p in net._flat_params()])
+    r_c, r_f = flat(netc2), flat(netf2)
+    total = float(total.detach())
+    assert abs(float(term) - total) <= 1e-5 * abs(total), (float(term), total)
+    assert np.abs(r_f).max() > 0
+    assert np.abs(g_f - r_f).max() <= 1e-4 * np.abs(r_f).max(), np.abs(g_f - r_f).max() / np.abs(r_f).max()
+    # weights are detached and z_samples carry no gradient: the coarse network gets none from this term (both ways)
+    assert np.abs(g_c).max() == 0 and np.abs(r_c).max() <= 1e-10
+
+
+@pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
+def test_step_with_lpips_is_step_plus_patch_gradients(prec_name):
+    prec = spn.PREC_FP32 if prec_name == "fp32" else spn.PREC_BF16
+    rng = np.random.default_rng(4)
+    ro, rd = O.get_rays(24, 32, 28.8, poses(1)[0, :, :4])
+    rays = np.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    batch = []
+    for i, m in enumerate((96, 64, 80)):
+        ix = rng.permutation(rays.shape[1])[:m]
+        batch.append(T(rays[:, ix]))
+        batch.append(T(rng.uniform(0, 1, (m, 3) if i < 2 else (m,)).astype(np.float32)))
+    P, lp, tgts = poses(3), lpips_net(), patch_targets()
+
+    tr_a, _, _ = trainer(prec, 0.0)
+    loss_a, _ = tr_a.step(*batch, _apply=False)
+    tr_b, _, _ = trainer(prec, 0.0)
+    term_b = tr_b.lpips_patch_backward(P, PATCHES, tgts, lp, HWF)
+    tr_c, netc, netf = trainer(prec, 0.0)
+    before = N(netf.flat_params()).copy()
+    loss_c, _ = tr_c.step_with_lpips(batch, P, PATCHES, tgts, lp, HWF)
+    torch.cuda.synchronize()
+    assert tr_a.global_step == 0 and tr_b.global_step == 0 and tr_c.global_step == 1
+    assert abs(float(loss_c) - float(loss_a) - float(term_b)) <= 1e-5 * abs(float(loss_c))
+    tol = 1e-4 if prec_name == "fp32" else 2e-3
+    for k in (0, 1):
+        want = N(tr_a.grads[k]) + N(tr_b.grads[k])
+        assert np.abs(want).max() > 0
+        assert np.abs(N(tr_c.grads[k]) - want).max() <= tol * np.abs(want).max()
+    step = np.abs(N(netf.flat_params()) - before)
+    assert 0 < step.max() <= 5e-4 * 1.01               # one Adam step: |delta| <= lr
+
+
+def test_render_path_frames_and_dumps(tmp_path):
+    """render_path (run_nerf.py:168-307) through the asynchronous frame sink: the returned stacks and the dumped arrays are
+    the per-frame render() outputs, in order, for more frames than staging buffers and several chunks per frame."""
+    netc, netf = make_net(11, spn.PREC_BF16), make_net(12, spn.PREC_BF16)
+    kw = render_kwargs(netc, netf)
+    P = poses(5)
+    gt = np.random.default_rng(2).uniform(0, 1, (5, 24, 32, 3)).astype(np.float32)
+    d = str(tmp_path)
+    rgbs, disps, (Xs, Ys) = spn.render_path(P, list(HWF), 200, kw, gt_imgs=gt, savedir=d, need_alpha=True)
+    assert rgbs.shape == (5, 24, 32, 3) and disps.shape == (5, 24, 32) and rgbs.dtype == np.float32 and Xs == [] and Ys == []
+    for i in range(5):
+        with torch.no_grad():
+            rgb, disp, acc, depth, ex = spn.render(*HWF, chunk=200, c2w=T(P[i, :3, :4]), retraw=True, need_alpha=True, **kw)
+        np.testing.assert_allclose(rgbs[i], N(rgb), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(disps[i], N(disp), rtol=1e-6, atol=1e-6)
+        name = "{:06d}".format(i)
+        for sub, ref in (("depth", depth), ("disp", disp), ("weight", ex["weights"]), ("z", ex["z_vals"]), ("alpha", ex["alpha"])):
+            a = np.load(os.path.join(d, sub, name + ".npy"))
+            assert a.shape == tuple(ref.shape)
+            np.testing.assert_allclose(a, N(ref), rtol=1e-6, atol=1e-6)
+        assert os.path.isfile(os.path.join(d, "rgb", name + ".png")) and os.path.isfile(os.path.join(d, "images", name + ".png"))
+        pose = np.loadtxt(os.path.join(d, "pose", name + ".txt"))
+        np.testing.assert_allclose(pose[:3], P[i, :3, :4], rtol=1e-6)
+    # half-resolution pass without dumps (render_factor, run_nerf.py:172-176)
+    rgbs2, disps2, _ = spn.render_path(P[:2], list(HWF), 32768, kw, render_factor=2)
+    assert rgbs2.shape == (2, 12, 16, 3) and np.isfinite(rgbs2).all()
