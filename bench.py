@@ -171,6 +171,190 @@ def workload_config(n_gpus, n_rand):
             "l2": "ray pool 548 MB + per-step activation stash > 126 MB L2; L2 flushed (256 MB write) between timed steps"}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# the other two GPU configurations of BASELINE.json (not the headline line; same JSON contract)
+# ------------------------------------------------------------------------------------------------
+def _init_dist():
+    import torch
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    return rank, world, local, dev
+
+
+def _max_over_ranks(x, dev, world):
+    import torch
+    if world == 1:
+        return float(x)
+    t = torch.tensor([float(x)], device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _kernel_profile(L, steps):
+    import ctypes
+    prof = {}
+    for kind, name in ((0, "mlp_fwd"), (1, "mlp_dgrad"), (2, "mlp_wgrad")):
+        n_l, ms_l = ctypes.c_int(), ctypes.c_float()
+        L.spn_profile_read(kind, ctypes.byref(n_l), ctypes.byref(ms_l))
+        if n_l.value and ms_l.value > 0:
+            prof[name] = {"launches_per_step": n_l.value / steps, "ms_per_step": ms_l.value / steps}
+    return prof
+
+
+def run_other_workload(args):
+    import torch
+    spn = importlib.import_module("spin-nerf_b200")
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    rank, world, local, dev = _init_dist()
+    prec = spn.PREC_BF16 if args.precision == "bf16" else spn.PREC_FP32
+    nets = []
+    for seed in (1, 2):
+        net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net = net.seeded_init_(seed).to(dev); net.precision = prec
+        nets.append(net)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    L = spn._lib.lib()
+    clocks = ClockSampler(local); clocks.start()
+    all_poses = poses(N_VIEWS)
+
+    if args.workload == "render":
+        # ---- configs[4]: one full-resolution frame per step and GPU through render() in chunks of 32768 rays (run_nerf.py:767)
+        kw = dict(network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=64, N_importance=64, lindisp=True,
+                  white_bkgd=True, perturb=0., raw_noise_std=0., use_viewdirs=True, ndc=False, near=NEAR, far=FAR)
+        rays_per_step = H * W * world
+
+        def frames(k, first):
+            evs = []
+            for i in range(k):
+                flush.fill_(1.0)
+                c2w = torch.from_numpy(all_poses[(first + i * world + rank) % N_VIEWS]).to(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                with torch.no_grad():
+                    rgb, disp, acc, depth, _ = spn.render(H, W, FOCAL, chunk=32768, c2w=c2w, **kw)
+                e1.record(); evs.append((e0, e1))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs), rgb
+        phase(f"render workload: {args.warmup} warm-up frames"); frames(args.warmup, 0)
+        barrier(); torch.cuda.synchronize()
+        L.spn_profile_enable(1); L.spn_launch_count(1); clocks.rows.clear()
+        ms, rgb = frames(args.steps, args.warmup)
+        torch.cuda.synchronize(); barrier()
+        clk = clocks.stop(); launches = int(L.spn_launch_count(0)); prof = _kernel_profile(L, args.steps); L.spn_profile_enable(0)
+        ms = _max_over_ranks(ms, dev, world)
+        value = rays_per_step * args.steps / (ms * 1e-3)
+        # e2e: the public video API with host poses in and host frames out (frames sharded over the ranks, gathered over NVLink)
+        vid_poses = [all_poses[i % N_VIEWS] for i in range(args.steps * world)]
+        spn.render_path_sharded(vid_poses[:world], [H, W, FOCAL], 32768, kw)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rgbs, disps = spn.render_path_sharded(vid_poses, [H, W, FOCAL], 32768, kw)
+        torch.cuda.synchronize(); barrier()
+        e2e_ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, dev, world)
+        flop = FLOP_FWD * EVALS_PER_RAY * H * W
+        dom = prof.get("mlp_fwd")
+        tfl = flop / (dom["ms_per_step"] * 1e-3) / 1e12 if dom else None
+        line = {"metric": "rays/sec (render_path)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
+                "config": {"workload": "full-resolution 1008x756 novel-view frames (render_path), coarse+fine 64+64 samples, chunks of "
+                                       "32768 rays, one frame per step and GPU, frames sharded round-robin (BASELINE configs[4])",
+                           "frames_per_step": world, "parallelism": f"frame-dp{world}",
+                           "l2": "per-frame outputs 0.8 GB > 126 MB L2; L2 flushed (256 MB write) between timed frames"},
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": H * W * len(vid_poses) / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 48 * world,
+                        "d2h_bytes_per_step": H * W * 16 * world, "ms_per_step": e2e_ms / args.steps,
+                        "note": "render_path_sharded: host poses in, gathered host RGB+disparity video out; timed with the host clock "
+                                "around the call (it ends in a device->host copy), max over ranks"},
+                "roofline": {"kernel": "mlp_fwd", "bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s",
+                             "frac": tfl / peak if tfl else None, "traffic": None, "kernels": prof},
+                "cpu_baseline": None, "frames_per_sec": world * args.steps / (ms * 1e-3),
+                "finite": bool(np.isfinite(rgbs).all()) if rgbs is not None else None}
+    else:
+        # ---- configs[2]: --lpips step: 3 x N_rand=4096 rays + 4 patches of 47x63 at render factor 2 per step and GPU
+        lp_mod = importlib.import_module("spin-nerf_b200.lpips_patch")
+        lpips = importlib.import_module("spin-nerf_b200.compat.lpips").LPIPS().to(dev)     # fixed-input stand-in (no lpips package)
+        n_rand = 4096 if args.n_rand == 1024 else args.n_rand
+        tr = trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                                 perturb=1.0, raw_noise_std=1.0, near=NEAR, far=FAR, ndc=False, hwf=(H, W, FOCAL),
+                                 sharder=trainer_mod.RaySharder(rank, world))
+        g = torch.Generator(device=dev); g.manual_seed(0)
+        ro_all, rd_all = [], []
+        for c2w in all_poses:
+            ro, rd = spn.ops.get_rays(H, W, FOCAL, torch.from_numpy(c2w).to(dev))
+            ro_all.append(ro.reshape(-1, 3)); rd_all.append(rd.reshape(-1, 3))
+        pool = torch.stack([torch.cat(ro_all), torch.cat(rd_all)], 0)
+        M = pool.shape[1]
+        rgb_pool = torch.rand(M, 3, device=dev, generator=g); disp_pool = torch.rand(M, device=dev, generator=g)
+        Hs, Ws, fs, plen = lp_mod.patch_geometry([H, W, FOCAL], 2, 8)
+        B = 4 * world
+        tgt_frames = torch.rand(N_VIEWS, 3, Hs, Ws, device=dev, generator=g) * 2 - 1
+        rnd = __import__("random").Random(0)
+        n_patch_rays = 4 * plen[0] * plen[1]
+        rays_per_step = (RENDERS_PER_STEP * n_rand + n_patch_rays) * world
+
+        def one_step():
+            idx = torch.randint(0, M, (3, n_rand * world), device=dev, generator=g)
+            views = [rnd.randrange(N_VIEWS) for _ in range(B)]
+            patches = [(rnd.randint(0, Hs - plen[0]), rnd.randint(0, Ws - plen[1]), plen[0], plen[1]) for _ in range(B)]
+            tg = [lp_mod.crop(tgt_frames, v, p[0], p[1], plen) for v, p in zip(views, patches)]
+            return tr.step_with_lpips((pool, rgb_pool, disp_pool, idx), [all_poses[v] for v in views], patches, tg, lpips,
+                                      (Hs, Ws, fs), from_pool=True)
+
+        def steps(k):
+            evs = []
+            for _ in range(k):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); loss, _ = one_step(); e1.record(); evs.append((e0, e1))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs), loss
+        phase(f"train_lpips workload: {args.warmup} warm-up steps"); steps(args.warmup)
+        barrier(); torch.cuda.synchronize()
+        L.spn_profile_enable(1); L.spn_launch_count(1); clocks.rows.clear()
+        ms, loss = steps(args.steps)
+        torch.cuda.synchronize(); barrier()
+        clk = clocks.stop(); launches = int(L.spn_launch_count(0)); prof = _kernel_profile(L, args.steps); L.spn_profile_enable(0)
+        ms = _max_over_ranks(ms, dev, world)
+        value = rays_per_step * args.steps / (ms * 1e-3)
+        evals = (RENDERS_PER_STEP * n_rand + n_patch_rays) * EVALS_PER_RAY
+        dom = max(prof, key=lambda k: prof[k]["ms_per_step"]) if prof else None
+        line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
+                "config": {"workload": f"--lpips train step: 3 x N_rand={n_rand} rays + 4 LPIPS patches of {plen[0]}x{plen[1]} rays at render "
+                                       "factor 2 per step and GPU, LPIPS = frozen stand-in conv stack (fixed input), statue-shaped synthetic "
+                                       "scene (BASELINE configs[2])",
+                           "n_rand_per_gpu": n_rand, "patch_rays_per_gpu": n_patch_rays, "parallelism": f"ray-dp{world}",
+                           "l2": "activation stash > 126 MB L2; L2 flushed (256 MB write) between timed steps"},
+                "clocks": clk, "gpu_launches": launches, "e2e": None,
+                "roofline": {"kernel": dom, "kernels": prof, "bound": "tensor", "peak": peak, "unit": "TFLOP/s", "traffic": None,
+                             "achieved": None, "frac": None,
+                             "step_mlp_flop_frac_of_peak": evals * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12 / peak},
+                "cpu_baseline": None, "final_loss": float(loss)}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------
 PARTIAL = {}     # rank 0's result line as far as it is known; the watchdog prints it if a later phase hangs
 T_START = time.perf_counter()
@@ -192,6 +376,10 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--cpu_rays", type=int, default=128, help="rays per render call in the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "train_lpips", "render"],
+                    help="train = BASELINE configs[1] (the headline line, default); train_lpips = configs[2] (N_rand=4096 + 4 LPIPS "
+                         "patches of 47x63 per step and GPU); render = configs[4] (full 1008x756 frames through render_path, one "
+                         "frame per step and GPU)")
     ap.add_argument("--deadline", type=float, default=420.0,
                     help="hard wall-clock limit in seconds: a watchdog thread ends the process (exit code 3) if the run has not "
                          "finished by then, so a hung collective or kernel can never hold the GPU box")
@@ -210,6 +398,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+
+    if args.workload != "train":
+        return run_other_workload(args)
 
     import torch
     spn = importlib.import_module("spin-nerf_b200")

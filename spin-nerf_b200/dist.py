@@ -51,3 +51,26 @@ def allreduce_sum_(flat_grads, group=None):
 def frames_for_rank(n_frames, rank, world):
     """render_path sharding (config 5): frames round-robin over ranks."""
     return list(range(rank, n_frames, world))
+
+
+def gather_frames(local, n_frames, rank, world, group=None, dst=None):
+    """local: this rank's frames [ceil(n_frames / world), ...] in its round-robin order (frame rank + j*world at row j,
+    unused tail rows arbitrary) -> all n_frames in frame order on every rank (dst=None) or on rank dst only (others get
+    None).  One all-gather / gather of equally sized blocks; the interleave back to frame order is a view transpose."""
+    per = (n_frames + world - 1) // world
+    if local.shape[0] != per:
+        raise RuntimeError(f"gather_frames: expected {per} local frame rows, got {local.shape[0]}")
+    if world == 1:
+        return local[:n_frames]
+    if dst is None:
+        full = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)       # rank-major concatenation
+        full = full.view((world,) + tuple(local.shape))
+    else:
+        parts = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+        dist.gather(local.contiguous(), parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+        full = torch.stack(parts, 0)
+    # full[r, j] is frame r + j*world  ->  [j, r] flattened is frame order
+    return full.transpose(0, 1).reshape((per * world,) + tuple(local.shape[1:]))[:n_frames]

@@ -325,28 +325,34 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
     return rgbs, disps, (Xs, Ys)
 
 
-def render_path_sharded(render_poses, hwf, chunk, render_kwargs, render_factor=0, group=None):
-    """Config 5 (BASELINE.json): novel-view video over several GPUs.  Frames are independent, so rank r renders
-    frames r, r+W, ... (spin-nerf_b200/dist.py:frames_for_rank) with the same `render_path` code and the frames are
-    gathered to every rank (12.2 MB per 1008x756 RGBD frame).  Single process: identical to render_path."""
+def render_path_sharded(render_poses, hwf, chunk, render_kwargs, render_factor=0, group=None, dst=None):
+    """Config 5 (BASELINE.json): novel-view video over several GPUs.  Frames are independent, so rank r renders frames
+    r, r+W, ... (dist.frames_for_rank) and keeps them ON THE DEVICE as [rgb | disp] rows; one collective
+    (dist.gather_frames: all-gather over NVLink, 12.2 MB per 1008x756 frame) assembles the video, then ONE device->host
+    copy hands it over — the reference's per-frame `.cpu()` (run_nerf.py:221-229) happens once per video.
+    dst=None: every rank returns the whole video; dst=r: only rank r does (the others return None, None).
+    Single process: the same code without the collective."""
     import torch.distributed as dist
-    from .dist import frames_for_rank
+    from .dist import frames_for_rank, gather_frames
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    mine = frames_for_rank(len(render_poses), rank, world)
-    poses = [render_poses[i] for i in mine]
-    if poses:
-        rgbs, disps, _ = render_path(poses, hwf, chunk, render_kwargs, render_factor=render_factor)
-    else:
-        H, W = (int(hwf[0]) // max(render_factor, 1), int(hwf[1]) // max(render_factor, 1))
-        rgbs, disps = np.zeros((0, H, W, 3), np.float32), np.zeros((0, H, W), np.float32)
-    if world == 1:
-        return rgbs, disps
-    parts = [None] * world
-    dist.all_gather_object(parts, (mine, rgbs, disps), group=group)
+    H, W, focal = hwf
+    if render_factor != 0:
+        H = H // render_factor; W = W // render_factor; focal = focal / render_factor
+    H, W = int(H), int(W)
     n = len(render_poses)
-    out_rgb = np.zeros((n,) + rgbs.shape[1:], np.float32); out_disp = np.zeros((n,) + disps.shape[1:], np.float32)
-    for idx, r_, d_ in parts:
-        for j, i in enumerate(idx):
-            out_rgb[i], out_disp[i] = r_[j], d_[j]
-    return out_rgb, out_disp
+    mine = frames_for_rank(n, rank, world)
+    net = render_kwargs.get("network_fn") or render_kwargs.get("network_fine")
+    dev = next(net.parameters()).device
+    local = torch.zeros((len(frames_for_rank(n, 0, world)), H, W, 4), device=dev)      # rank 0 has the most frames
+    with torch.no_grad():
+        for j, i in enumerate(mine):
+            c2w = torch.as_tensor(render_poses[i])
+            rgb, disp, _, _, _ = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
+            local[j, ..., :3] = rgb
+            local[j, ..., 3] = disp
+    video = gather_frames(local, n, rank, world, group, dst)
+    if video is None:
+        return None, None
+    video = video.cpu().numpy()
+    return np.ascontiguousarray(video[..., :3]), np.ascontiguousarray(video[..., 3])

@@ -54,6 +54,37 @@ def _worker(rank, world, port, out):
     torch.distributed.destroy_process_group()
 
 
+def _frames_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = dist_mod.init_from_env("gloo")
+    n = 7                                                    # not a multiple of the world size: rank 1 has a spare row
+    mine = dist_mod.frames_for_rank(n, r, w)
+    per = (n + w - 1) // w
+    local = torch.full((per, 2, 3, 4), -1.0)
+    for j, i in enumerate(mine):
+        local[j] = float(i) + torch.arange(24.0).reshape(2, 3, 4) / 64
+    every = dist_mod.gather_frames(local, n, r, w)
+    only0 = dist_mod.gather_frames(local, n, r, w, dst=0)
+    assert (only0 is None) == (r != 0)
+    if r == 0:
+        np.save(out, torch.stack([every, only0]).numpy())
+    else:
+        assert every.shape[0] == n
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_frame_gather_restores_frame_order(tmp_path):
+    """render_path_sharded's collective (config 5): round-robin frames come back in frame order, on all ranks or on one."""
+    out = str(tmp_path / "frames.npy")
+    mp.spawn(_frames_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    want = np.arange(7.0)[:, None, None, None] + np.arange(24.0).reshape(2, 3, 4) / 64
+    np.testing.assert_array_equal(got[0], want.astype(np.float32)); np.testing.assert_array_equal(got[1], want.astype(np.float32))
+    one = torch.arange(5.0)[:, None].repeat(1, 3)
+    assert torch.equal(dist_mod.gather_frames(one, 5, 0, 1), one)
+
+
 def test_sharder_partitions_exactly():
     for n in (1, 7, 1024, 8192):
         for w in (1, 2, 3, 8):
