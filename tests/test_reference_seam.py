@@ -1,0 +1,30 @@
+"""The reference's own trainer, unmodified, over our drop-in `run_nerf_helpers`: see
+tests/seam_driver.py.  Needs the reference checkout (build container); skipped where it is absent (GPU box)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/DS_NeRF/run_nerf.py"), reason="reference checkout not present")
+@pytest.mark.timeout(600)
+def test_unmodified_reference_trainer_runs_over_the_dropin():
+    iters = 2
+    env = dict(os.environ, PYTHONSAFEPATH="1", OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "seam_driver.py"), str(iters)], capture_output=True,
+                       text=True, env=env, timeout=580)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1]
+    res = json.loads(line[5:])
+    assert res["helpers_file"] == os.path.join(ROOT, "spin-nerf_b200", "dropin", "run_nerf_helpers.py")
+    assert res["run_nerf_file"] == "/root/reference/DS_NeRF/run_nerf.py"
+    assert res["nerf_class_module"].endswith("nerf") and "spin-nerf_b200" in res["nerf_class_module"]
+    # one reference train step = three render() calls (run_nerf.py:1455-1470), each coarse + fine, then autograd backward
+    render = ["spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points", "spn_raw2outputs_fwd"]
+    step = render * 3 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * 6
+    assert res["calls"] == step * iters, res["calls"]
+    assert p.stdout.count("[TRAIN] Iter:") == iters          # the trainer's own progress line (run_nerf.py:1699-1701)
