@@ -44,7 +44,8 @@ def main():
     torch.autograd.set_detect_anomaly(False)                # values are garbage here; anomaly mode would trip on NaNs
     run_nerf.train()
     print("SEAM " + json.dumps({"helpers_file": helpers.__file__, "run_nerf_file": run_nerf.__file__,
-                                "nerf_class_module": run_nerf.NeRF.__module__, "calls": rec.names()}))
+                                "nerf_class_module": run_nerf.NeRF.__module__, "data_file": sys.modules["data"].__file__,
+                                "load_llff_file": sys.modules["load_llff"].__file__, "calls": rec.names()}))
 
 
 if __name__ == "__main__":

@@ -92,3 +92,46 @@ def test_camera_rays_match_reference_get_rays_np():
     o, d = rp.camera_rays(30, 41, 37.5, c2w)
     ro, rd = H.get_rays_np(30, 41, 37.5, c2w)
     assert np.array_equal(o, ro) and np.array_equal(d, rd)
+
+
+def test_dropin_raydataset_batches_equal_the_references():
+    """dropin/data.py: same batches as DS_NeRF/data.py under the trainer's DataLoader construction (run_nerf.py:1340-1348),
+    fetched with one gather per batch instead of N_rand __getitem__ calls."""
+    import importlib.util
+    import time
+    import torch
+    from torch.utils.data import DataLoader
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("spn_dropin_data", os.path.join(root, "spin-nerf_b200", "dropin", "data.py"))
+    ours = importlib.util.module_from_spec(spec); spec.loader.exec_module(ours)
+
+    class RefRayDataset(torch.utils.data.Dataset):           # DS_NeRF/data.py:4-15 restated (3 lines of behaviour)
+        def __init__(self, ray_data):
+            self.rayData, self.length = ray_data, ray_data.shape[0]
+
+        def __len__(self):
+            return self.length
+
+        def __getitem__(self, index):
+            return torch.Tensor(self.rayData[index])
+    ref_cls = RefRayDataset
+    if os.path.isfile("/root/reference/DS_NeRF/data.py"):    # the real one where the reference checkout exists
+        spec = importlib.util.spec_from_file_location("spn_ref_data", "/root/reference/DS_NeRF/data.py")
+        ref_mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref_mod)
+        ref_cls = ref_mod.RayDataset
+    rng = np.random.default_rng(0)
+    for dtype, shape in ((np.float32, (5000, 3, 4)), (np.float64, (3001, 4, 3))):
+        rays = rng.standard_normal(shape).astype(dtype)
+        times = []
+        outs = []
+        for cls in (ref_cls, ours.RayDataset):
+            it = iter(DataLoader(cls(rays), batch_size=1024, shuffle=True, num_workers=0,
+                                 generator=torch.Generator(device="cpu").manual_seed(3)))
+            t0 = time.perf_counter()
+            outs.append([b for b in it])
+            times.append(time.perf_counter() - t0)
+        assert len(outs[0]) == len(outs[1]) == -(-shape[0] // 1024)
+        for a, b in zip(*outs):
+            assert a.dtype == b.dtype == torch.float32 and torch.equal(a, b)
+    assert torch.equal(ours.RayDataset(rays)[5], ref_cls(rays)[5])
+    print(f"RayDataset epoch: reference {times[0] * 1e3:.1f} ms, drop-in {times[1] * 1e3:.1f} ms")

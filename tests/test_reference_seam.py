@@ -22,6 +22,8 @@ def test_unmodified_reference_trainer_runs_over_the_dropin():
     res = json.loads(line[5:])
     assert res["helpers_file"] == os.path.join(ROOT, "spin-nerf_b200", "dropin", "run_nerf_helpers.py")
     assert res["run_nerf_file"] == "/root/reference/DS_NeRF/run_nerf.py"
+    assert res["data_file"] == os.path.join(ROOT, "spin-nerf_b200", "dropin", "data.py")       # batched RayDataset (row f1)
+    assert res["load_llff_file"] == "/root/reference/DS_NeRF/load_llff.py"                     # everything else: the reference's
     assert res["nerf_class_module"].endswith("nerf") and "spin-nerf_b200" in res["nerf_class_module"]
     # one reference train step = three render() calls (run_nerf.py:1455-1470), each coarse + fine, then autograd backward
     render = ["spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points", "spn_raw2outputs_fwd"]
