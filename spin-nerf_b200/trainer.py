@@ -182,14 +182,15 @@ class Trainer:
             ros.append(ro.reshape(-1, 3)); rds.append(rd.reshape(-1, 3)); shapes.append(tuple(ro.shape[:2]))
         rb = ops.build_ray_batch(torch.cat(ros), torch.cat(rds), self.near, self.far, self.ndc, Hs, Ws, fs)
         cfg, k = self._forward(0, None, True, rb=rb, test_kwargs=True)
-        rgb = k["rgb_map"].detach().clone().requires_grad_(True)        # [n,3]: the only tensor torch autograd sees
-        term, off = 0.0, 0
-        for i, (h, w) in zip(mine, shapes):
-            pred = ((rgb[off:off + h * w].view(h, w, 3) - 0.5) * 2).permute(2, 0, 1)[None, ...]      # :1552
-            term = term + lpips_fn(pred, targets[i].to(self.device)).mean()
-            off += h * w
-        term = term * (float(weight) / batch_size)
-        g_rgb, = torch.autograd.grad(term * float(self.sharder.world), rgb)
+        with torch.enable_grad():
+            rgb = k["rgb_map"].detach().clone().requires_grad_(True)    # [n,3]: the only tensor torch autograd sees
+            term, off = 0.0, 0
+            for i, (h, w) in zip(mine, shapes):
+                pred = ((rgb[off:off + h * w].view(h, w, 3) - 0.5) * 2).permute(2, 0, 1)[None, ...]      # :1552
+                term = term + lpips_fn(pred, targets[i].to(self.device)).mean()
+                off += h * w
+            term = term * (float(weight) / batch_size)
+            g_rgb, = torch.autograd.grad(term * float(self.sharder.world), rgb)
         gc, gf = self.grads
         chunk_backward(cfg, k, self.net_c, self.net_f, {"rgb_map": g_rgb.contiguous()}, gc, gf,
                        self._scratch(cfg), self._ws(cfg))
