@@ -20,9 +20,13 @@ import test_host_glue_dry_run as dry            # noqa: E402
 
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    every = sys.argv[2] if len(sys.argv) > 2 else "100000"      # i_video / i_testset / i_weights period
     rec = dry.Recorder()
     for m in (dry.L, dry.ops, dry.render_mod):
         m.lib = (lambda rec=rec: rec); m.ptr = dry._ptr; m.stream = (lambda: 0)
+    # the recorder computes nothing: hand out zero-filled outputs instead of uninitialised memory, so that the run is
+    # deterministic (a NaN disparity loss is skipped by the trainer, run_nerf.py:1520, which would change the call list)
+    dry.ops._empty = lambda shape, like, dtype=torch.float32: torch.zeros(shape, device=like.device, dtype=dtype)
     dry.nerf_mod.NeRF._sync = lambda self: (self.flat_params(), torch.zeros(64, dtype=torch.uint8))
     sio = importlib.import_module("spin-nerf_b200.scene_io")
     scene = tempfile.mkdtemp(prefix="spn_scene_")
@@ -37,13 +41,20 @@ def main():
     sys.argv = ["run_nerf.py", "--expname", "t", "--datadir", scene, "--basedir", os.path.join(work, "logs"),
                 "--dataset_type", "llff", "--factor", "2", "--N_rand", "32", "--N_samples", "8", "--N_importance", "8",
                 "--use_viewdirs", "--raw_noise_std", "1.0", "--no_ndc", "--lindisp", "--white_bkgd", "--no_tcnn", "--N_gt", "0",
-                "--N_iters", str(iters), "--i_video", "100000", "--i_testset", "100000", "--i_weights", "100000",
+                "--N_iters", str(iters), "--i_video", every, "--i_testset", every, "--i_weights", every,
                 "--i_feat", "100000", "--i_print", "1", "--chunk", "512", "--netchunk", "4096"]
     import run_nerf
     helpers = sys.modules["run_nerf_helpers"]
     torch.autograd.set_detect_anomaly(False)                # values are garbage here; anomaly mode would trip on NaNs
     run_nerf.train()
-    print("SEAM " + json.dumps({"helpers_file": helpers.__file__, "run_nerf_file": run_nerf.__file__,
+    logdir = os.path.join(work, "logs", "t")
+    files = sorted(os.path.relpath(os.path.join(r, f), logdir) for r, _, fs in os.walk(logdir) for f in fs)
+    ckpt_keys = {}
+    for f in files:
+        if f.endswith(".tar"):
+            ck = torch.load(os.path.join(logdir, f), map_location="cpu", weights_only=False)
+            ckpt_keys = {k: (sorted(v.keys()) if isinstance(v, dict) and k.startswith("network") else None) for k, v in ck.items()}
+    print("SEAM " + json.dumps({"files": files, "ckpt": ckpt_keys, "helpers_file": helpers.__file__, "run_nerf_file": run_nerf.__file__,
                                 "nerf_class_module": run_nerf.NeRF.__module__, "data_file": sys.modules["data"].__file__,
                                 "load_llff_file": sys.modules["load_llff"].__file__, "calls": rec.names()}))
 

@@ -30,3 +30,27 @@ def test_unmodified_reference_trainer_runs_over_the_dropin():
     step = render * 3 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * 6
     assert res["calls"] == step * iters, res["calls"]
     assert p.stdout.count("[TRAIN] Iter:") == iters          # the trainer's own progress line (run_nerf.py:1699-1701)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/DS_NeRF/run_nerf.py"), reason="reference checkout not present")
+@pytest.mark.timeout(900)
+def test_unmodified_reference_trainer_checkpoints_and_videos_over_the_dropin():
+    """Same run with i_weights = i_video = i_testset = 2: the reference's checkpoint writer (run_nerf.py:1626-1636), its own
+    render_path over the 120 spiral poses + mp4 export (:1638-1671) and the test-set render (:1682-1697) all go through the
+    drop-in's get_rays / NeRF / raw2outputs / sample_pdf and the import shims."""
+    env = dict(os.environ, PYTHONSAFEPATH="1", OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "seam_driver.py"), "2", "2"], capture_output=True,
+                       text=True, env=env, timeout=880)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1][5:])
+    files = res["files"]
+    assert "000002.tar" in files and "args.txt" in files
+    assert sum(f.endswith("rgb.mp4") for f in files) == 1 and sum(f.endswith("disp.mp4") for f in files) == 1
+    assert any(f.startswith("testset_000002") and f.endswith(".png") for f in files)
+    # checkpoint layout of run_nerf.py:1628-1633 with reference-shaped state_dicts (24 tensors per network, helpers:86-102)
+    assert set(res["ckpt"]) >= {"global_step", "network_fn_state_dict", "network_fine_state_dict", "optimizer_state_dict"}
+    for k in ("network_fn_state_dict", "network_fine_state_dict"):
+        keys = res["ckpt"][k]
+        assert len(keys) == 24 and "pts_linears.5.weight" in keys and "views_linears.0.bias" in keys and "alpha_linear.weight" in keys
+    n_get_rays = res["calls"].count("spn_get_rays")
+    assert n_get_rays == 120 + 1 + 1           # the spiral video, the held-out video frame, the test-set frame
