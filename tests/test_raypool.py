@@ -135,3 +135,14 @@ def test_dropin_raydataset_batches_equal_the_references():
             assert a.dtype == b.dtype == torch.float32 and torch.equal(a, b)
     assert torch.equal(ours.RayDataset(rays)[5], ref_cls(rays)[5])
     print(f"RayDataset epoch: reference {times[0] * 1e3:.1f} ms, drop-in {times[1] * 1e3:.1f} ms")
+
+
+def test_train_synthetic_example_dry_run():
+    """tools/train_synthetic.py --dry_run --lpips: scene written, loaded, pools built, first step's indices and LPIPS
+    patches drawn — everything of the example that precedes the first GPU call."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "train_synthetic.py"), "--dry_run", "--lpips", "--views", "8",
+                        "--height", "48", "--width", "64"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "first step would use indices (3, 1024)" in p.stdout and "first LPIPS step would render views" in p.stdout
