@@ -3,8 +3,6 @@ tensors cross the boundary as device pointers only.  Names/semantics mirror the 
 DS_NeRF/run_nerf_helpers.py (file:line in each docstring)."""
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib as L

@@ -15,8 +15,8 @@ import torch
 from . import _lib as L
 from . import ops
 from ._lib import check, f32, lib, ptr, stream
-from .frame_io import FrameWriter, dump_frame, to8b
-from .nerf import NeRF, NeRF_RGB
+from .frame_io import FrameWriter, dump_frame, to8b  # noqa: F401  (to8b re-exported: run_nerf.py uses it next to render_path)
+from .nerf import NeRF
 
 _DIFF = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0")
 

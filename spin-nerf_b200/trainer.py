@@ -6,8 +6,6 @@ vector (rays are sharded across ranks), one flat Adam laun
 """
 from __future__ import annotations
 
-import math
-
 import torch
 
 from . import _lib as L
