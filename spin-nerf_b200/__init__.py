@@ -9,10 +9,13 @@ from . import _lib
 from ._lib import PREC_BF16, PREC_FP32, LIB_PATH, MLP_NPARAMS
 from . import ops
 from .nerf import NeRF, NeRF_RGB, default_precision, set_default_precision
-from .render import render, render_rays, batchify_rays, render_path, render_path_sharded, render_rays_composed
+from .embed import Embedder, get_embedder
+from .render import (render, render_rays, batchify_rays, render_path, render_path_sharded, render_rays_composed, batchify,
+                     run_network, create_nerf)
 from . import frame_io, lpips_patch
 
-__all__ = ["ops", "NeRF", "NeRF_RGB", "render", "render_rays", "batchify_rays", "render_path", "render_path_sharded",
+__all__ = ["ops", "NeRF", "NeRF_RGB", "render", "render_rays", "batchify_rays", "render_path", "render_path_sharded", "batchify", "run_network",
+           "create_nerf", "get_embedder", "Embedder",
            "frame_io", "lpips_patch", "PREC_BF16",
            "PREC_FP32", "set_default_precision", "default_precision"]
 __version__ = "0.1.0"

@@ -37,34 +37,10 @@ img2l1 = lambda x, y: torch.mean(torch.abs(x - y))
 mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device if torch.is_tensor(x) else None))
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
-LAZY_EMBED = os.environ.get("SPN_LAZY_EMBED", "1") != "0"
-
-
-class Embedder:
-    """helpers:22-52.  With LAZY_EMBED (default) embed() hands the raw 3-vector through and NeRF.forward
-    encodes inside the fused MLP kernel; out_dim still reports the encoded width (63 / 27) so
-    create_nerf builds reference-shaped layers (run_nerf.py:383-396)."""
-
-    def __init__(self, **kwargs):
-        self.kwargs = kwargs
-        assert kwargs['include_input'] and kwargs['input_dims'] == 3 and kwargs['log_sampling']
-        self.n_freqs = kwargs['num_freqs']
-        self.out_dim = 3 + 6 * self.n_freqs
-
-    def embed(self, inputs):
-        if LAZY_EMBED:
-            return inputs
-        return _ops.embed(inputs, self.n_freqs)
-
-
-def get_embedder(multires, i=0):
-    """helpers:55-70."""
-    if i == -1:
-        return nn.Identity(), 3
-    embedder_obj = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
-                            log_sampling=True, periodic_fns=[torch.sin, torch.cos])
-    embed = lambda x, eo=embedder_obj: eo.embed(x)
-    return embed, embedder_obj.out_dim
+_embed = importlib.import_module("spin-nerf_b200.embed")
+LAZY_EMBED = _embed.LAZY_EMBED
+Embedder = _embed.Embedder             # helpers:22-52 (lazy by default: NeRF.forward encodes inside the fused MLP kernel)
+get_embedder = _embed.get_embedder     # helpers:55-70
 
 
 NeRF = _spn.NeRF

@@ -81,8 +81,11 @@ class NeRF(nn.Module):
     # ---- flat storage --------------------------------------------------------------------
     def _flat_params(self):
         # registration order == spn_mlp_param_offsets order (sub-modules such as alpha_model excluded)
-        mods = list(self.pts_linears) + [self.views_linears[0], self.feature_linear, self.alpha_linear, self.rgb_linear]
+        mods = list(self.pts_linears) + [self.views_linears[0], self.feature_linear, self._alpha_head(), self.rgb_linear]
         return [p for m in mods for p in (m.weight, m.bias)]
+
+    def _alpha_head(self):
+        return self.alpha_linear
 
     def _flatten(self):
         ps = self._flat_params()
@@ -173,37 +176,29 @@ class NeRF(nn.Module):
         put(self.feature_linear, 2 * self.D)
         put(self.views_linears[0], 2 * self.D + 2)
         put(self.rgb_linear, 2 * self.D + 4)
-        put(self.alpha_linear, 2 * self.D + 6)
+        put(self._alpha_head(), 2 * self.D + 6)
         self.mark_params_changed()
 
 
 class NeRF_RGB(NeRF):
-    """helpers:159-245: colour head trained on top of a frozen density provider `alpha_model`
-    (its sigma replaces this network's, under no_grad, helpers:202-203).  Has no alpha_linear."""
+    """helpers:159-245: colour head trained on top of a frozen density provider `alpha_model` (its sigma replaces this
+    network's, under no_grad, helpers:202-203).  Like the reference module it owns no alpha_linear: parameters(),
+    state_dict() and the optimizer see the reference's 22 tensors (+ the registered alpha_model's); the kernels' flat
+    parameter layout keeps a zero density head that is not a registered parameter."""
 
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False,
                  alpha_model=None):
         super().__init__(D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs)
-        # the reference module owns no alpha_linear; keep a frozen zero one so the flat layout is unchanged
-        self.alpha_linear.weight.requires_grad_(False)
-        self.alpha_linear.bias.requires_grad_(False)
+        head = self.alpha_linear
+        del self.alpha_linear
+        head.weight.requires_grad_(False); head.bias.requires_grad_(False)
         with torch.no_grad():
-            self.alpha_linear.weight.zero_(); self.alpha_linear.bias.zero_()
+            head.weight.zero_(); head.bias.zero_()
+        object.__setattr__(self, "_zero_alpha_head", head)      # plain attribute: not a sub-module, not in state_dict
         self.alpha_model = alpha_model
 
-    def state_dict(self, *a, **k):
-        sd = super().state_dict(*a, **k)
-        for key in [k_ for k_ in sd if "alpha_linear" in k_ and not k_.startswith("alpha_model")]:
-            sd.pop(key)
-        return sd
-
-    def load_state_dict(self, sd, strict=True):
-        sd = dict(sd)
-        own = super().state_dict()
-        for key in own:
-            if "alpha_linear" in key and not key.startswith("alpha_model") and key not in sd:
-                sd[key] = own[key]
-        return super().load_state_dict(sd, strict=strict)
+    def _alpha_head(self):
+        return self._zero_alpha_head
 
     def forward(self, x):
         raw = super().forward(x)

@@ -16,7 +16,8 @@ from . import _lib as L
 from . import ops
 from ._lib import check, f32, lib, ptr, stream
 from .frame_io import FrameWriter, dump_frame, to8b  # noqa: F401  (to8b re-exported: run_nerf.py uses it next to render_path)
-from .nerf import NeRF
+from .embed import get_embedder
+from .nerf import NeRF, NeRF_RGB
 
 _DIFF = ("rgb_map", "disp_map", "acc_map", "depth_map", "weights", "rgb0", "disp0", "acc0")
 
@@ -135,6 +136,102 @@ class RenderChunk(torch.autograd.Function):
         return (None,) * 8 + tuple(grads)
 
 
+def batchify(fn, chunk):
+    """run_nerf.py:44-53: `fn` applied to slices of `chunk` rows."""
+    if chunk is None:
+        return fn
+    return lambda inputs: torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """run_nerf.py:56-71 with the reference's arguments: flatten the points, embed them and the per-ray view directions
+    (broadcast over the samples), concatenate, evaluate `fn` in slices of `netchunk`, restore the leading shape.  With the
+    lazy embedders of embed.get_embedder the concatenation is the raw [pt, viewdir] 6-vector and NeRF.forward encodes and
+    evaluates it in one kernel; materialised embeddings (90 columns) are accepted as well."""
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(input_dirs, [-1, input_dirs.shape[-1]]))], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+
+
+def default_query_fn(netchunk=1024 * 64):
+    """The `network_query_fn` create_nerf builds (run_nerf.py:427-430) for the reference's default embedders."""
+    embed_fn, _ = get_embedder(10, 0)
+    embeddirs_fn, _ = get_embedder(4, 0)
+    return lambda inputs, viewdirs, network_fn: run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn,
+                                                            embeddirs_fn=embeddirs_fn, netchunk=netchunk)
+
+
+def create_nerf(args, device=None):
+    """run_nerf.py:380-496 for the `--no_tcnn` model: embedders, coarse / fine networks (NeRF, or NeRF_RGB over a frozen
+    density provider loaded from --alpha_model_path, optionally --no_coarse), the query function, torch.optim.Adam over
+    the trainable parameters, checkpoint reload from --ft_path or the newest *.tar of basedir/expname, and the train /
+    test render kwargs.  Returns (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer) like the reference;
+    checkpoints interchange with it (same state_dict keys).  `--sigma_loss` is outside this path and raises."""
+    if device is None:
+        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    embed_fn, input_ch = get_embedder(args.multires, args.i_embed)
+    input_ch_views, embeddirs_fn = 0, None
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    shape = dict(input_ch=input_ch, output_ch=output_ch, skips=[4], input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs)
+    alpha_model = None
+    if getattr(args, "alpha_model_path", None) is None:
+        model = NeRF(D=args.netdepth, W=args.netwidth, **shape).to(device)
+        grad_vars = list(model.parameters())
+    else:
+        alpha_model = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, **shape).to(device)
+        alpha_model.load_state_dict(torch.load(args.alpha_model_path, map_location=device)['network_fine_state_dict'])
+        if not args.no_coarse:
+            model = NeRF_RGB(D=args.netdepth, W=args.netwidth, alpha_model=alpha_model, **shape).to(device)
+            grad_vars = list(model.parameters())
+        else:
+            model, grad_vars = None, []
+    model_fine = None
+    if args.N_importance > 0:
+        if alpha_model is None:
+            model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, **shape).to(device)
+        else:
+            model_fine = NeRF_RGB(D=args.netdepth_fine, W=args.netwidth_fine, alpha_model=alpha_model, **shape).to(device)
+        grad_vars += list(model_fine.parameters())
+
+    def network_query_fn(inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn, netchunk=args.netchunk)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    logdir = os.path.join(args.basedir, args.expname)
+    if args.ft_path is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        ckpts = [os.path.join(logdir, f) for f in sorted(os.listdir(logdir)) if 'tar' in f] if os.path.isdir(logdir) else []
+    if len(ckpts) > 0 and not args.no_reload:
+        ckpt = torch.load(ckpts[-1], map_location=device)
+        start = ckpt['global_step']
+        optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        if model is not None:
+            model.load_state_dict(ckpt['network_fn_state_dict'])
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt['network_fine_state_dict'])
+
+    render_kwargs_train = {'network_query_fn': network_query_fn, 'perturb': args.perturb, 'N_importance': args.N_importance,
+                           'network_fine': model_fine, 'N_samples': args.N_samples, 'network_fn': model,
+                           'use_viewdirs': args.use_viewdirs, 'white_bkgd': args.white_bkgd, 'raw_noise_std': args.raw_noise_std}
+    if args.dataset_type != 'llff' or args.no_ndc:      # NDC only suits forward-facing LLFF captures (run_nerf.py:478-483)
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    else:
+        render_kwargs_train['ndc'] = True
+    render_kwargs_test = dict(render_kwargs_train, perturb=False, raw_noise_std=0.)
+    if getattr(args, "sigma_loss", False):
+        raise NotImplementedError("sigma_loss (DS_NeRF/loss.py) is outside the B200 hot path")
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
+
+
 def _np_rand(*shape, device):
     """The reference's pytest=True stream: re-seeded before every draw (run_nerf.py:662-666)."""
     np.random.seed(0)
@@ -190,6 +287,8 @@ def render_rays_composed(ray_batch, network_fn, network_query_fn, N_samples, ret
     --no_coarse / alpha_model, run_nerf.py:680-692): same CUDA ops, Python control flow."""
     n = ray_batch.shape[0]
     dev = ray_batch.device
+    if network_query_fn is None:
+        network_query_fn = default_query_fn()
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 9 else None
     t_rand = None

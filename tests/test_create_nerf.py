@@ -1,0 +1,126 @@
+"""create_nerf / run_network / batchify of the render API (SURVEY.md section 8 a4 + the model set-up of a1-a3) against the
+unmodified reference's functions (imported through oracle/ref_loader.py where the reference checkout exists)."""
+import argparse
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+
+spn = importlib.import_module("spin-nerf_b200")
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+
+
+def _args(tmp, **over):
+    a = argparse.Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=64, N_samples=64,
+                           netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, alpha_model_path=None,
+                           no_coarse=False, netchunk=4096, lrate=5e-4, basedir=str(tmp), expname="exp", ft_path=None,
+                           no_reload=False, perturb=1.0, white_bkgd=True, raw_noise_std=1.0, dataset_type="llff", no_ndc=True,
+                           lindisp=True, sigma_loss=False)
+    a.__dict__.update(over)
+    os.makedirs(os.path.join(a.basedir, a.expname), exist_ok=True)
+    return a
+
+
+def test_run_network_hands_the_mlp_points_and_viewdirs():
+    """With the lazy embedders the network receives the raw [pt, viewdir] rows (what the fused kernel encodes); with
+    materialising embedders of the reference's layout it receives 90 columns whose raw part NeRF._as_points extracts."""
+    g = torch.Generator().manual_seed(0)
+    pts = torch.randn(5, 7, 3, generator=g); dirs = torch.randn(5, 3, generator=g)
+    seen = []
+    fn = lambda x: (seen.append(x), x[:, :4] * 2)[1]
+    e, d = spn.get_embedder(10, 0); ev, dv = spn.get_embedder(4, 0)
+    assert (d, dv) == (63, 27)
+    out = spn.run_network(pts, dirs, fn, e, ev, netchunk=16)
+    assert out.shape == (5, 7, 4) and [s.shape[0] for s in seen] == [16, 16, 3]        # batchify slices
+    x = torch.cat(seen, 0)
+    assert torch.equal(x[:, :3], pts.reshape(-1, 3)) and torch.equal(x[:, 3:], dirs[:, None].expand(5, 7, 3).reshape(-1, 3))
+    net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    fat = torch.cat([x[:, :3], torch.zeros(35, 60), x[:, 3:], torch.zeros(35, 24)], -1)   # [gamma(pt) | gamma(dir)] layout
+    assert torch.equal(net._as_points(fat), x) and net._as_points(x) is x
+    assert spn.batchify(fn, None) is fn
+
+
+@needs_ref
+def test_run_network_matches_the_references_plumbing():
+    _, R = ref_loader.load()
+    g = torch.Generator().manual_seed(1)
+    pts = torch.randn(4, 6, 3, generator=g); dirs = torch.randn(4, 3, generator=g)
+    ident = lambda x: x
+    fn = lambda x: x.sum(-1, keepdim=True).expand(-1, 4).contiguous()
+    ours = spn.run_network(pts, dirs, fn, ident, ident, netchunk=5)
+    ref = R.run_network(pts, dirs, fn, ident, ident, netchunk=5)
+    assert torch.equal(ours, ref)
+    assert torch.equal(spn.batchify(fn, 7)(pts.reshape(-1, 3)), R.batchify(fn, 7)(pts.reshape(-1, 3)))
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", ["plain", "ndc", "alpha_model", "no_coarse"])
+def test_create_nerf_builds_what_the_reference_builds(tmp_path, variant):
+    H, R = ref_loader.load()
+    over = {}
+    if variant == "ndc":
+        over.update(no_ndc=False)
+    if variant in ("alpha_model", "no_coarse"):
+        provider = H.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+        path = str(tmp_path / "provider.tar")
+        torch.save({"network_fine_state_dict": provider.state_dict()}, path)
+        over.update(alpha_model_path=path, no_coarse=(variant == "no_coarse"))
+    a_ref, a_our = _args(tmp_path / "ref", **over), _args(tmp_path / "our", **over)
+    saved_dev = R.device
+    R.device = torch.device("cpu")
+    try:
+        torch.manual_seed(0)
+        tr_r, te_r, start_r, gv_r, opt_r = R.create_nerf(a_ref)
+    finally:
+        R.device = saved_dev
+    tr_o, te_o, start_o, gv_o, opt_o = spn.create_nerf(a_our, device=torch.device("cpu"))
+    assert start_o == start_r == 0
+    assert set(tr_o) == set(tr_r) and set(te_o) == set(te_r)
+    for k in tr_r:
+        if k not in ("network_query_fn", "network_fn", "network_fine"):
+            assert tr_o[k] == tr_r[k] and te_o[k] == te_r[k], k
+    assert te_o["perturb"] is False and te_o["raw_noise_std"] == 0.
+    assert [tuple(p.shape) for p in gv_o] == [tuple(p.shape) for p in gv_r]            # trainable tensors, in order
+    assert opt_o.defaults["lr"] == opt_r.defaults["lr"] and opt_o.defaults["betas"] == opt_r.defaults["betas"]
+    for k in ("network_fn", "network_fine"):
+        m_o, m_r = tr_o[k], tr_r[k]
+        assert (m_o is None) == (m_r is None)
+        if m_r is not None:
+            assert type(m_o).__name__ == type(m_r).__name__
+            assert [(n, tuple(v.shape)) for n, v in m_o.state_dict().items()] == [(n, tuple(v.shape)) for n, v in m_r.state_dict().items()]
+    if variant in ("alpha_model", "no_coarse"):                                        # the provider's weights were loaded
+        got = tr_o["network_fine"].alpha_model.state_dict()
+        for n, v in provider.state_dict().items():
+            assert torch.equal(got[n], v)
+
+
+@needs_ref
+def test_create_nerf_resumes_from_a_reference_checkpoint(tmp_path):
+    """Checkpoints interchange (run_nerf.py:443-461, 1626-1636): a .tar written from the reference's modules and optimizer
+    is picked up as the newest checkpoint of basedir/expname."""
+    H, R = ref_loader.load()
+    a = _args(tmp_path)
+    torch.manual_seed(3)
+    nets = [H.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True) for _ in range(2)]
+    params = list(nets[0].parameters()) + list(nets[1].parameters())
+    opt = torch.optim.Adam(params=params, lr=a.lrate, betas=(0.9, 0.999))
+    for p in params:
+        p.grad = torch.ones_like(p) * 1e-3
+    opt.step()
+    logdir = os.path.join(a.basedir, a.expname)
+    torch.save({"global_step": 1}, os.path.join(logdir, "000001.tar"))                 # an older one: must not be chosen
+    torch.save({"global_step": 1234, "network_fn_state_dict": nets[0].state_dict(), "network_fine_state_dict": nets[1].state_dict(),
+                "optimizer_state_dict": opt.state_dict()}, os.path.join(logdir, "001234.tar"))
+    tr, te, start, gv, opt2 = spn.create_nerf(a, device=torch.device("cpu"))
+    assert start == 1234
+    for k, net in (("network_fn", nets[0]), ("network_fine", nets[1])):
+        for n, v in net.state_dict().items():
+            assert torch.equal(tr[k].state_dict()[n], v)
+    st = opt2.state_dict()["state"]
+    assert len(st) == 48 and all(int(s["step"]) == 1 for s in st.values())
+    a.no_reload = True
+    assert spn.create_nerf(a, device=torch.device("cpu"))[2] == 0

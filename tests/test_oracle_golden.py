@@ -135,6 +135,55 @@ def test_render_end_to_end(tag):
         cm(out["alpha"], G("alpha"), rtol=0, atol=2e-4); close(out["alpha0"], G("alpha0"), atol=2e-4)
 
 
+@pytest.mark.parametrize("tag", ["depths", "c2w_patch", "staticcam", "rgb_net", "no_coarse"])
+def test_render_call_variants(tag):
+    """render()'s other call forms (tests/golden/make_variants_golden.py ran the unmodified reference): a depth column,
+    rays from c2w with a patch window, c2w_staticcam, a NeRF_RGB fine network over a frozen density provider, --no_coarse."""
+    g = load_golden("render_variants")
+    H, W, f = 12, 16, 14.4
+    pc = O.init_params(11); pc["alpha_linear.bias"] = pc["alpha_linear.bias"] + 1.0
+    pf = O.init_params(12); pf["alpha_linear.bias"] = pf["alpha_linear.bias"] + 1.0
+    pr = O.init_params(13)
+    ro, rd = g["rays"][0], g["rays"][1]
+    kw = {}
+    if tag == "depths":
+        rb = O.make_ray_batch(ro, rd, 1.2, 8.0, depths=g["depths"])
+        assert rb.shape[1] == 12
+    elif tag == "c2w_patch":
+        fo, fd = O.get_rays(H, W, f, g["pose_a"])
+        rb = O.make_ray_batch(fo[3:9, 5:13].reshape(-1, 3), fd[3:9, 5:13].reshape(-1, 3), 1.2, 8.0)
+    elif tag == "staticcam":
+        _, view_d = O.get_rays(H, W, f, g["pose_a"])                 # view directions from c2w ...
+        so, sd = O.get_rays(H, W, f, g["pose_b"])                    # ... rays from the static camera (run_nerf.py:128-133)
+        rb = O.make_ray_batch(so.reshape(-1, 3), sd.reshape(-1, 3), 1.2, 8.0)
+        vd = view_d.reshape(-1, 3)
+        rb[:, -3:] = vd / np.linalg.norm(vd, axis=-1, keepdims=True)
+    else:
+        rb = O.make_ray_batch(ro, rd, 1.2, 8.0)
+    n = rb.shape[0]
+    kw = dict(lindisp=True, white_bkgd=True, u=np.broadcast_to(O.linspace01(64), (n, 64)), retraw=True)
+    if tag == "rgb_net":
+        out = O.render_rays(rb, pc, pr, 64, 64, need_alpha=True, p_alpha=pf, **kw)
+    elif tag == "no_coarse":
+        out = O.render_rays(rb, None, pr, 64, 64, p_alpha=pf, **kw)
+    else:
+        out = O.render_rays(rb, pc, pf, 64, 64, **kw)
+    G = lambda k: g[f"{tag}__{k}"].reshape(n, *g[f"{tag}__{k}"].shape[(2 if tag in ("c2w_patch", "staticcam") else 1):])
+    close_mostly(out["rgb_map"], G("rgb"), rtol=0, atol=2e-4); close_mostly(out["acc_map"], G("acc"), rtol=0, atol=2e-4)
+    close_mostly(out["depth_map"], G("depth"), rtol=2e-4, atol=2e-4); close_mostly(out["disp_map"], G("disp"), rtol=5e-4, atol=0)
+    close(out["rgb0"], G("rgb0"), atol=2e-4); close(out["disp0"], G("disp0"), rtol=5e-4)
+    close_mostly(out["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
+    if tag in ("depths", "rgb_net", "no_coarse"):
+        close_mostly(out["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
+        close_mostly(out["raw"], G("raw"), rtol=1e-3, atol=1e-3)
+        close_mostly(out["weights"], G("weights"), rtol=0, atol=2e-4)
+    if tag == "rgb_net":
+        close_mostly(out["alpha"], G("alpha"), rtol=0, atol=2e-4); close(out["alpha0"], G("alpha0"), atol=2e-4)
+    if tag == "depths":      # the depth column is carried, not used (sigma_loss aside): same render as without it
+        ref = O.render_rays(O.make_ray_batch(ro, rd, 1.2, 8.0), pc, pf, 64, 64, **kw)
+        np.testing.assert_array_equal(out["rgb_map"], ref["rgb_map"])
+
+
 def test_train_step_oracle_matches_reference_autograd():
     """oracle/train_oracle.py (loss, both nets' gradients, two Adam steps) vs autograd + torch.optim.Adam run
     through the reference's render() (golden train_step)."""

@@ -137,6 +137,58 @@ def test_step_with_lpips_is_step_plus_patch_gradients(prec_name):
     assert 0 < step.max() <= 5e-4 * 1.01               # one Adam step: |delta| <= lr
 
 
+def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
+    a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
+    err = np.abs(a - b); tol = atol + rtol * np.abs(b)
+    assert np.mean(err > tol) <= max_frac, (np.mean(err > tol), err.max())
+    assert err.max() <= hard * max(1.0, np.abs(b).max()), err.max()
+
+
+@pytest.mark.parametrize("tag", ["depths", "c2w_patch", "staticcam", "rgb_net", "no_coarse"])
+def test_render_call_variants_match_reference_fp32(tag):
+    """render()'s other call forms against the unmodified reference (tests/golden/render_variants.npz): a depth column
+    (12-column ray matrix), rays from c2w with a patch window, c2w_staticcam, a NeRF_RGB fine network over a frozen density
+    provider (operator-level composition, run_nerf.py:680-692), --no_coarse.  Same tolerances as the main render parity test."""
+    from conftest import load_golden
+    g = load_golden("render_variants")
+    H, W, f = 12, 16, 14.4
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    kw = dict(chunk=32768, retraw=True, use_viewdirs=True, network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64,
+              N_importance=64, ndc=False, lindisp=True, white_bkgd=True, perturb=0., raw_noise_std=0., near=1.2, far=8.0)
+    if tag in ("rgb_net", "no_coarse"):
+        pr = O.init_params(13)
+        rgb_net = spn.NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, alpha_model=netf)
+        sd = {k: torch.from_numpy(v.copy()) for k, v in pr.items() if not k.startswith("alpha_linear")}
+        sd.update({"alpha_model." + k: v for k, v in netf.state_dict().items()})
+        rgb_net.load_state_dict(sd)
+        rgb_net = rgb_net.to(DEV); rgb_net.precision = spn.PREC_FP32; rgb_net.alpha_model.precision = spn.PREC_FP32
+        kw.update(network_fine=rgb_net, network_fn=None if tag == "no_coarse" else netc, need_alpha=(tag == "rgb_net"))
+    if tag == "depths":
+        kw.update(rays=T(g["rays"]), depths=T(g["depths"]))
+    elif tag == "c2w_patch":
+        kw.update(c2w=T(g["pose_a"]), patch=(3, 5, 6, 8))
+    elif tag == "staticcam":
+        kw.update(c2w=T(g["pose_a"]), c2w_staticcam=T(g["pose_b"]))
+    else:
+        kw.update(rays=T(g["rays"]))
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, **kw)
+    G = lambda k: g[f"{tag}__{k}"]
+    assert tuple(rgb.shape) == G("rgb").shape
+    close_mostly(rgb, G("rgb"), rtol=0, atol=2e-4); close_mostly(acc, G("acc"), rtol=0, atol=2e-4)
+    close_mostly(depth, G("depth"), rtol=2e-4, atol=2e-4); close_mostly(disp, G("disp"), rtol=5e-4, atol=0)
+    np.testing.assert_allclose(N(ex["rgb0"]), G("rgb0"), rtol=1e-5, atol=2e-4)
+    np.testing.assert_allclose(N(ex["disp0"]), G("disp0"), rtol=5e-4, atol=1e-6)
+    close_mostly(ex["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
+    if tag in ("depths", "rgb_net", "no_coarse"):
+        close_mostly(ex["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
+        close_mostly(ex["raw"], G("raw"), rtol=1e-3, atol=1e-3)
+        close_mostly(ex["weights"], G("weights"), rtol=0, atol=2e-4)
+    if tag == "rgb_net":
+        close_mostly(ex["alpha"], G("alpha"), rtol=0, atol=2e-4)
+        np.testing.assert_allclose(N(ex["alpha0"]), G("alpha0"), rtol=0, atol=2e-4)
+
+
 def test_render_path_frames_and_dumps(tmp_path):
     """render_path (run_nerf.py:168-307) through the asynchronous frame sink: the returned stacks and the dumped arrays are
     the per-frame render() outputs, in order, for more frames than staging buffers and several chunks per frame."""
