@@ -509,7 +509,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr0, float decay_base, float decay_steps, float b1,
                                  float b2) {
   const float k = state[0] + 1.0f;                                  // 1-based step about to be applied
-  const float lr = lr0 * powf(decay_base, (k - 1.0f) / decay_steps);  // run_nerf.py:1616-1622
+  // run_nerf.py:1611-1622: the rate is updated AFTER optimizer.step() from the 0-based global_step, so step k runs at
+  // lr0 * base^((k-2)/decay_steps) (steps 1 and 2 both at lr0)
+  const float lr = lr0 * powf(decay_base, fmaxf(k - 2.0f, 0.0f) / decay_steps);
   state[0] = k;
   state[1] = lr / (1.0f - powf(b1, k));
   state[2] = sqrtf(1.0f - powf(b2, k));

@@ -257,7 +257,9 @@ class Trainer:
         if self.adam_state is not None:
             L.check(L.lib().spn_adam_tick(L.ptr(self.adam_state), self.lr0, 0.1, float(self.lrate_decay * 1000),
                                           self.betas[0], self.betas[1], L.stream()), "spn_adam_tick")
-        lr = self.lr0 * (0.1 ** ((self.global_step - 1) / (self.lrate_decay * 1000)))
+        # the reference sets the rate AFTER optimizer.step() from its 0-based global_step (run_nerf.py:1611-1622, 1703): step k
+        # (1-based) runs at lr0 * 0.1^((k-2)/decay_steps), steps 1 and 2 both at lr0
+        lr = self.lr0 * (0.1 ** (max(self.global_step - 2, 0) / (self.lrate_decay * 1000)))
         for net, g, m, v in zip((self.net_c, self.net_f), self.grads, self.m, self.v):
             if net is None:
                 continue

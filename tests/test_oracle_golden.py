@@ -233,3 +233,31 @@ def test_one_chunk_step_equals_three_render_calls():
         for k in a:
             scale = np.abs(b[k]).max()
             assert np.abs(a[k] - b[k]).max() <= 2e-5 * max(scale, 1e-12), k
+
+
+def test_spin_step_trajectory_starts_like_the_references():
+    """tests/golden/convergence.npz: the unmodified reference trained for 300 steps of the SPIn-NeRF step (three render
+    calls, six MSE terms, Adam, lr decay) on a small analytic scene.  The oracle's one-chunk formulation of the step + Adam
+    walks the same trajectory (first steps here; over all 300 steps the oracle's final loss was within 0.05 % when the
+    fixture was made).  The GPU trainer is held to the same trajectory in tests/test_zz_gpu_next_rows.py."""
+    import importlib.util
+    import os
+    from conftest import GOLDEN
+    from oracle import train_oracle as TO
+    spec = importlib.util.spec_from_file_location("make_convergence_golden", os.path.join(GOLDEN, "make_convergence_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = load_golden("convergence")
+    ro, rd, rgb_t, disp_t, idx = gen.problem()
+    assert int(idx.sum()) == int(gold["idx_checksum"][0])          # the numpy stream reproduced the fixture's batches
+    pc, pf = gen.params()
+    sc, sf = TO.AdamState(pc), TO.AdamState(pf)
+    for it in range(3):
+        b = [(O.make_ray_batch(ro[idx[it, k]], rd[idx[it, k]], gen.NEAR, gen.FAR), (rgb_t if k < 2 else disp_t)[idx[it, k]])
+             for k in range(3)]
+        loss, gc, gf = TO.spin_step_grads(b, pc, pf, one_chunk=True)
+        assert abs(loss - float(gold["loss"][it])) <= 1e-4 * float(gold["loss"][it]), (it, loss, float(gold["loss"][it]))
+        lr = gen.LR * 0.1 ** (max(it - 1, 0) / (gen.DECAY * 1000))     # step k = it+1 runs at lr0 * 0.1^((k-2)/decay_steps)
+        for p, g, st in ((pc, gc, sc), (pf, gf, sf)):
+            st.step += 1
+            for k in p:
+                p[k], st.m[k], st.v[k] = O.adam_step(p[k], g[k], st.m[k], st.v[k], st.step, lr)
