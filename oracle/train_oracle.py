@@ -82,22 +82,31 @@ def train_step(rb, target, tdisp, pc, pf, st_c, st_f, lr, n_samples=64, n_import
     return box["loss"], gc, gf
 
 
-def spin_step_grads(batches, pc, pf, one_chunk, n_samples=64, n_importance=64, lindisp=True, white_bkgd=True):
+def spin_step_grads(batches, pc, pf, one_chunk, n_samples=64, n_importance=64, lindisp=True, white_bkgd=True,
+                    depth_lambda=0.1):
     """Loss and parameter gradients of the SPIn-NeRF step (run_nerf.py:1455-1521, default flags) for
-    batches = [(rb_unmasked, rgb_target), (rb_masked, rgb_target), (rb_inpainted, disp_target)]:
+    batches = [(rb_unmasked, rgb_target), (rb_masked, rgb_target), (rb_inpainted, disp_target)] and, optionally, a fourth
+    (rb_sparse_depth, depth_target) for `--colmap_depth --depth_loss` (run_nerf.py:1475-1477, 1491-1506: loss +=
+    depth_lambda * img2mse(depth_map, target_depth), fine depth only):
       one_chunk=False: three render calls as in the reference — MSE on rgb/rgb0 for the first two (the second with
                        detach_weights=True), MSE on disp/disp0 for the third — gradients summed;
       one_chunk=True:  the three ray batches concatenated into one render call, every loss term and detach_weights
                        applied to its ray range (what spin-nerf_b200/trainer.py:Trainer.step launches on the GPU).
     Deterministic sampling (perturb=0, no noise).  Returns (loss, grads_coarse, grads_fine)."""
-    (rb1, t1), (rb2, t2), (rb3, t3) = batches
+    (rb1, t1), (rb2, t2), (rb3, t3) = batches[:3]
     n1, n2, n3 = len(rb1), len(rb2), len(rb3)
+    rb4, t4 = batches[3] if len(batches) > 3 else (np.zeros((0, rb1.shape[1]), F32), np.zeros((0,), F32))
+    n4 = len(rb4)
     if not one_chunk:
         total, gc_sum, gf_sum = 0.0, None, None
         for i, (rb, tgt) in enumerate(batches):
             box = {}
 
             def g_out(o, i=i, tgt=tgt, box=box):
+                if i == 3:
+                    l, g = mse_grad(o["depth_map"], tgt)
+                    box["loss"] = depth_lambda * l
+                    return {"depth_map": (F32(depth_lambda) * g).astype(F32)}
                 a, b = ("rgb_map", "rgb0") if i < 2 else ("disp_map", "disp0")
                 la, ga = mse_grad(o[a], tgt); lb, gb = mse_grad(o[b], tgt)
                 box["loss"] = la + lb
@@ -108,11 +117,11 @@ def spin_step_grads(batches, pc, pf, one_chunk, n_samples=64, n_importance=64, l
             gc_sum = gc if gc_sum is None else {k: gc_sum[k] + gc[k] for k in gc}
             gf_sum = gf if gf_sum is None else {k: gf_sum[k] + gf[k] for k in gf}
         return total, gc_sum, gf_sum
-    rb = np.concatenate([rb1, rb2, rb3], 0)
+    rb = np.concatenate([rb1, rb2, rb3, rb4], 0)
     box = {}
 
     def g_out(o):
-        g = {k: np.zeros_like(o[k]) for k in ("rgb_map", "rgb0", "disp_map", "disp0")}
+        g = {k: np.zeros_like(o[k]) for k in ("rgb_map", "rgb0", "disp_map", "disp0", "depth_map")}
         loss = 0.0
         for lo, hi, tgt, keys in ((0, n1, t1, ("rgb_map", "rgb0")), (n1, n1 + n2, t2, ("rgb_map", "rgb0")),
                                   (n1 + n2, n1 + n2 + n3, t3, ("disp_map", "disp0"))):
@@ -120,9 +129,14 @@ def spin_step_grads(batches, pc, pf, one_chunk, n_samples=64, n_importance=64, l
                 l, gk = mse_grad(o[k][lo:hi], tgt)
                 loss += l
                 g[k][lo:hi] = gk
+        if n4:
+            m = n1 + n2 + n3
+            l, gk = mse_grad(o["depth_map"][m:], t4)
+            loss += depth_lambda * l
+            g["depth_map"][m:] = F32(depth_lambda) * gk
         box["loss"] = loss
         return g
-    detach = np.zeros(n1 + n2 + n3, bool)
+    detach = np.zeros(n1 + n2 + n3 + n4, bool)
     detach[n1:n1 + n2] = True
     _, gc, gf = render_with_grads(rb, pc, pf, n_samples, n_importance, lindisp, white_bkgd, g_out, detach_weights=detach)
     return box["loss"], gc, gf

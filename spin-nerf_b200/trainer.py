@@ -83,7 +83,8 @@ class Trainer:
             n1 = torch.randn(n, S + NI, device=self.device) if NI else None
         return chunk_forward(opts, rb, self.net_c, self.net_f, t_rand, u, n0, n1, train=True, pool=self.pools[idx])
 
-    def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp, _apply=True):
+    def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp, rays_depth=None, target_depth=None,
+             depth_lambda=0.1, _apply=True):
         """One optimisation step on this rank's shard of the three ray batches.  Returns the (local) loss and
         psnr like run_nerf.py:1481-1521 defines them for the default flags.
 
@@ -91,7 +92,11 @@ class Trainer:
         independent, so here they are concatenated into ONE chunk: one sampling / MLP / compositing pass forward and
         one backward over 3x the rays (fewer, fuller kernel launches).  What differs between the calls — which loss
         a ray feeds and detach_weights=True for the masked rays — is applied per ray range (spn_train_losses,
-        spn_render_grads.detach_begin/end)."""
+        spn_render_grads.detach_begin/end).
+
+        rays_depth [2,n4,3] / target_depth [n4]: the optional fourth render call of `--colmap_depth --depth_loss`
+        (run_nerf.py:1400-1413, 1475-1477, 1491-1506: rays through COLMAP's sparse points, loss += depth_lambda *
+        img2mse(depth_map, target_depth)); they ride in the same chunk as a fourth ray range."""
         sh = self.sharder
         rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
         rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
@@ -99,14 +104,21 @@ class Trainer:
         n1, n2, n3 = rays_clf.shape[1], rays_s.shape[1], rays_inp.shape[1]
         if target_clf.shape[0] != n1 or target_s.shape[0] != n2 or depth_inp.shape[0] != n3:
             raise RuntimeError("Trainer.step: every ray batch needs one target per ray")
-        n = n1 + n2 + n3
+        groups, n4 = [rays_clf, rays_s, rays_inp], 0
+        if rays_depth is not None:
+            rays_depth, target_depth = sh.shard(rays_depth, 1), L.f32(sh.shard(target_depth))
+            n4 = rays_depth.shape[1]
+            if target_depth.shape[0] != n4:
+                raise RuntimeError("Trainer.step: every ray batch needs one target per ray")
+            groups.append(rays_depth)
+        n = n1 + n2 + n3 + n4
         P = self.shared
         rays = P("rays_cat", (2, n, 3), torch.float32)
-        torch.cat([rays_clf, rays_s, rays_inp], 1, out=rays)
+        torch.cat(groups, 1, out=rays)
         tgt_rgb = P("tgt_rgb", (n1 + n2, 3), torch.float32)
         torch.cat([target_clf, target_s], 0, out=tgt_rgb)
         cfg, k = self._forward(0, rays, False)
-        return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3, _apply)
+        return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3, _apply, n4, target_depth, depth_lambda)
 
     def step_from_pool(self, pool_od, rgb_pool, disp_pool, idx, _apply=True):
         """The same step fed by a device-resident ray pool: pool_od [2,M,3] all rays of the
@@ -129,8 +141,8 @@ class Trainer:
         cfg, k = self._forward(0, None, False, rb=rb)
         return self._finish_step(cfg, k, tgt_rgb, tgt_disp, m, m, m, _apply)
 
-    def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3, apply=True):
-        n = n1 + n2 + n3
+    def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3, apply=True, n4=0, target_depth=None, depth_lambda=0.1):
+        n = n1 + n2 + n3 + n4
         P = self.shared
         g_rgb, g_rgb0 = P("g_rgb", (n, 3), torch.float32), P("g_rgb0", (n, 3), torch.float32)
         g_disp, g_disp0 = P("g_disp", (n,), torch.float32), P("g_disp0", (n,), torch.float32)
@@ -140,15 +152,26 @@ class Trainer:
                                          L.ptr(tgt_rgb), L.ptr(depth_inp), n1, n2, n3, L.ptr(sums), L.ptr(g_rgb),
                                          L.ptr(g_rgb0), L.ptr(g_disp), L.ptr(g_disp0), L.ptr(out), L.stream()),
                 "spn_train_losses")
+        g = {"rgb_map": g_rgb, "rgb0": g_rgb0, "disp_map": g_disp, "disp0": g_disp0}
+        depth_term = None
+        if n4:      # sparse-depth rays: only the fine depth_map is supervised (run_nerf.py:1506); the loss kernel filled rows < m
+            m = n1 + n2 + n3
+            for t in (g_rgb, g_rgb0, g_disp, g_disp0):
+                t[m:].zero_()
+            diff = k["depth_map"][m:n] - target_depth
+            depth_term = float(depth_lambda) * torch.mean(diff * diff)
+            g_depth = P("g_depth", (n,), torch.float32)
+            g_depth[:m].zero_()
+            torch.mul(diff, 2.0 * float(depth_lambda) / n4, out=g_depth[m:])
+            g["depth_map"] = g_depth
         self.grad_all.zero_()
         gc, gf = self.grads
-        chunk_backward(cfg, k, self.net_c, self.net_f,
-                       {"rgb_map": g_rgb, "rgb0": g_rgb0, "disp_map": g_disp, "disp0": g_disp0}, gc, gf,
+        chunk_backward(cfg, k, self.net_c, self.net_f, g, gc, gf,
                        self._scratch(cfg), self._ws(cfg), detach_range=(n1, n1 + n2))
         if apply:
             self.apply_gradients()
         res = out[:2].clone()          # `out` is a pooled buffer: hand back copies of (loss, psnr)
-        return res[0], res[1]
+        return (res[0] if depth_term is None else res[0] + depth_term), res[1]
 
     # ---------------------------------------------------------------------------------------
     # perceptual-loss branch (run_nerf.py:1523-1561, `--lpips`)

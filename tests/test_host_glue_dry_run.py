@@ -148,3 +148,18 @@ def test_gradient_vectors_share_one_buffer():
     assert gc.numel() == gf.numel() == spn.MLP_NPARAMS and gc.is_contiguous() and gf.is_contiguous()
     assert gc.data_ptr() == tr.grad_all.data_ptr() and (gf.data_ptr() - gc.data_ptr()) % 512 == 0
     assert gf.data_ptr() + 4 * gf.numel() <= tr.grad_all.data_ptr() + 4 * tr.grad_all.numel()
+
+
+def test_step_with_sparse_depth_group(rec):
+    """--colmap_depth --depth_loss: the fourth render call rides in the chunk as a fourth ray range with a depth_map gradient."""
+    tr = _trainer()
+    g = torch.Generator().manual_seed(1)
+    loss, _ = tr.step(*_batch(8), rays_depth=torch.rand(2, 5, 3, generator=g), target_depth=torch.rand(5, generator=g), depth_lambda=0.1)
+    assert rec.names() == ["spn_build_ray_batch", "spn_render_rays_fwd", "spn_train_losses", "spn_render_rays_bwd",
+                           "spn_adam_step", "spn_adam_step"]
+    assert rec.calls[1][1][0]._obj.n_rays == 29 and rec.calls[2][1][6:9] == (8, 8, 8)
+    gr = rec.calls[3][1][2]._obj
+    assert gr.g_depth and gr.g_rgb and (gr.detach_begin, gr.detach_end) == (8, 16)
+    assert loss.shape == ()
+    with pytest.raises(RuntimeError):
+        tr.step(*_batch(8), rays_depth=torch.rand(2, 5, 3), target_depth=torch.rand(4))

@@ -261,3 +261,27 @@ def test_spin_step_trajectory_starts_like_the_references():
             st.step += 1
             for k in p:
                 p[k], st.m[k], st.v[k] = O.adam_step(p[k], g[k], st.m[k], st.v[k], st.step, lr)
+
+
+@pytest.mark.parametrize("one_chunk", [False, True])
+def test_spin_step_with_sparse_depth_rays_matches_reference(one_chunk):
+    """The shipped config's step (colmap_depth + depth_loss, DS_NeRF/configs/config.txt): four reference render() calls and
+    loss += 0.1 * img2mse(depth_col, target_depth) (tests/golden/train_step_depth.npz) against the oracle, as four calls
+    and as the one-chunk formulation Trainer.step launches."""
+    import importlib.util
+    import os
+    from conftest import GOLDEN
+    from oracle import train_oracle as TO
+    spec = importlib.util.spec_from_file_location("make_depth_step_golden", os.path.join(GOLDEN, "make_depth_step_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = load_golden("train_step_depth")
+    pc, pf = gen.params()
+    batches = [(O.make_ray_batch(r[0], r[1], gen.NEAR, gen.FAR), t) for r, t in gen.problem()]
+    loss, gc, gf = TO.spin_step_grads(batches, pc, pf, one_chunk=one_chunk, depth_lambda=gen.DEPTH_LAMBDA)
+    assert abs(loss - float(gold["loss"])) <= 1e-4 * float(gold["loss"]), (loss, float(gold["loss"]))
+    for nm, grads in (("c", gc), ("f", gf)):
+        for k, gv in grads.items():
+            ref_abs = float(gold[f"g_abs__{nm}__{k}"])
+            assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
+            close_mostly(gv.reshape(-1)[::997], gold[f"g_sub__{nm}__{k}"], rtol=1e-2, atol=1e-3 * np.abs(gv).max() + 1e-9,
+                         max_frac=0.03, hard=1.0)

@@ -179,6 +179,33 @@ def test_training_reaches_the_references_psnr(prec_name):
     assert ours > float(gold["psnr"][:20].mean()) + 15.0          # and it did train (reference: +21 dB)
 
 
+def test_trainer_step_with_sparse_depth_rays_matches_reference_fp32():
+    """Trainer.step with the fourth ray group of `--colmap_depth --depth_loss` against the unmodified reference's four
+    render() calls + autograd (tests/golden/train_step_depth.npz): loss and both networks' gradients."""
+    import importlib.util
+    from conftest import GOLDEN, load_golden
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    spec = importlib.util.spec_from_file_location("make_depth_step_golden", os.path.join(GOLDEN, "make_depth_step_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = load_golden("train_step_depth")
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    tr = trainer_mod.Trainer(netc, netf, lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.0,
+                             raw_noise_std=0.0, near=gen.NEAR, far=gen.FAR)
+    (r1, t1), (r2, t2), (r3, t3), (r4, t4) = [(T(r), T(t)) for r, t in gen.problem()]
+    loss, _ = tr.step(r1, t1, r2, t2, r3, t3, rays_depth=r4, target_depth=t4, depth_lambda=gen.DEPTH_LAMBDA)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-4 * float(gold["loss"]), (float(loss), float(gold["loss"]))
+    names = [n for n, _ in netc.named_parameters()]
+    for nm, net, flat in (("c", netc, tr.grads[0]), ("f", netf, tr.grads[1])):
+        for k, o, p in zip(names, net._offsets, net._flat_params()):
+            gv = N(flat[o:o + p.numel()])
+            ref_abs = float(gold[f"g_abs__{nm}__{k}"])
+            assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
+            sub, ref = gv.reshape(-1)[::997], gold[f"g_sub__{nm}__{k}"]
+            err = np.abs(sub - ref); tol = 1e-3 * np.abs(gv).max() + 1e-9 + 1e-2 * np.abs(ref)
+            assert np.mean(err > tol) <= 0.03, (nm, k, err.max())
+
+
 def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
     a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
     err = np.abs(a - b); tol = atol + rtol * np.abs(b)
