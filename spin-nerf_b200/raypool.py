@@ -75,6 +75,32 @@ def build_ray_pools(images, poses, hwf, masks, inpainted_depths, i_train, prepar
     return RayPools(o, d, rgb, lab, dsp, idx_clf, idx_inp, idx_rgb)
 
 
+def sparse_depth_rays(depth_gts, poses, hwf, masks, i_train, prepare=False):
+    """The fourth pool of `--colmap_depth` (run_nerf.py:1266-1300): one ray through every COLMAP point a training view
+    observes OUTSIDE its mask (all points with `prepare`), with that point's depth and confidence weight.
+    depth_gts: scene_io.colmap_depth_rays(...) (one {"depth", "coord", "weight"} per view); masks [N,H,W].
+    Returns (rays [2,M,3] float32, depth [M] float32, weight [M] float32) in the reference's order (views in i_train order, points
+    in file order); `np.concatenate([rays.transpose(1,0,2), repeat(depth), repeat(weight)], 1)` is its `rays_depth` [M,4,3]."""
+    H, W, focal = int(hwf[0]), int(hwf[1]), hwf[2]
+    o, d, dep, wgt = [], [], [], []
+    for i in i_train:
+        coord, depth, weight = (np.asarray(depth_gts[i][k]) for k in ("coord", "depth", "weight"))
+        if not prepare:      # keep points whose (clamped, truncated) pixel carries mask label 0 (:1272-1283)
+            m = np.asarray(masks[i])
+            rows = np.minimum(coord[:, 1].astype(np.int64), m.shape[0] - 1)
+            cols = np.minimum(coord[:, 0].astype(np.int64), m.shape[1] - 1)
+            keep = m[rows, cols] == 0
+            coord, depth, weight = coord[keep], depth[keep], weight[keep]
+        c2w = np.asarray(poses[i])[:3, :4]
+        # get_rays_by_coord_np (run_nerf_helpers.py:275-280): no rounding of the sub-pixel COLMAP coordinates
+        px, py = (coord[:, 0] - W * 0.5) / focal, -(coord[:, 1] - H * 0.5) / focal
+        dirs = np.stack([px, py, -np.ones_like(px)], -1)
+        rd = np.sum(dirs[..., np.newaxis, :] * c2w[:3, :3], -1)
+        o.append(np.broadcast_to(c2w[:3, -1], rd.shape)); d.append(rd); dep.append(depth); wgt.append(weight)
+    cat = lambda parts: np.concatenate(parts, 0).astype(np.float32)
+    return np.stack([cat(o), cat(d)], 0), cat(dep), cat(wgt)
+
+
 def draw_step_indices(dev_pools, n_rand, generator=None):
     """[3, n_rand] int64 pool indices for one step, drawn ON THE DEVICE from the three index sets of RayPools.to(device)
     (with replacement — a uniform draw per step instead of the DataLoader's epoch-wise shuffle), ready for

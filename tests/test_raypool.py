@@ -146,3 +146,45 @@ def test_train_synthetic_example_dry_run():
                         "--height", "48", "--width", "64"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "first step would use indices (3, 1024)" in p.stdout and "first LPIPS step would render views" in p.stdout
+
+
+def test_sparse_depth_rays_reproduce_the_references_rays_depth():
+    """raypool.sparse_depth_rays against run_nerf.py:1266-1300 restated with the reference's own get_rays_by_coord_np
+    (imported when the checkout is present, else the drop-in's identical numpy function)."""
+    rp_mod = importlib.import_module("spin-nerf_b200.raypool")
+    rng = np.random.default_rng(5)
+    H, W, focal, N = 20, 30, 27.0, 4
+    poses = rng.standard_normal((N, 3, 5)).astype(np.float32)
+    masks = (rng.uniform(0, 1, (N, H, W)) > 0.6).astype(np.float32)
+    masks[2] = -masks[2]                                     # LPIPS views carry label -1 (load_llff.py:161)
+    gts = []
+    for i in range(N):
+        m = int(rng.integers(5, 40))
+        coord = np.stack([rng.uniform(0, W + 1.5, m), rng.uniform(0, H + 1.5, m)], -1)     # some fall outside: clamped (:1274-1279)
+        gts.append({"coord": coord, "depth": rng.uniform(1, 8, m), "weight": rng.uniform(0, 2, m)})
+    try:
+        from oracle import ref_loader
+        by_coord = ref_loader.load()[0].get_rays_by_coord_np if ref_loader.available() else None
+    except Exception:
+        by_coord = None
+    if by_coord is None:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spin-nerf_b200", "dropin"))
+        by_coord = importlib.import_module("run_nerf_helpers").get_rays_by_coord_np
+    i_train = [0, 2, 3]
+    for prepare in (False, True):
+        ref_list = []
+        for i in i_train:                                    # run_nerf.py:1270-1296
+            g = {k: v.copy() for k, v in gts[i].items()}
+            if not prepare:
+                ind = [_ for _ in range(len(g['coord']))
+                       if masks[i][min(int(g['coord'][_][1]), masks[i].shape[0] - 1)][min(int(g['coord'][_][0]), masks[i].shape[1] - 1)] == 0]
+                g = {k: v[ind] for k, v in g.items()}
+            rd = np.transpose(np.stack(by_coord(H, W, focal, poses[i, :3, :4], g['coord']), axis=0), [1, 0, 2])
+            ref_list.append(np.concatenate([rd, np.repeat(g['depth'][:, None, None], 3, axis=2),
+                                            np.repeat(g['weight'][:, None, None], 3, axis=2)], axis=1))
+        ref = np.concatenate(ref_list, axis=0)
+        rays, depth, weight = rp_mod.sparse_depth_rays(gts, poses, (H, W, focal), masks, i_train, prepare=prepare)
+        assert rays.shape == (2, ref.shape[0], 3) and rays.dtype == np.float32
+        np.testing.assert_array_equal(rays.transpose(1, 0, 2), ref[:, :2].astype(np.float32))
+        np.testing.assert_array_equal(depth, ref[:, 2, 0].astype(np.float32))
+        np.testing.assert_array_equal(weight, ref[:, 3, 0].astype(np.float32))
