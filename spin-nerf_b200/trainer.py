@@ -295,6 +295,51 @@ class Trainer:
             net.mark_params_changed()
 
     # ---------------------------------------------------------------------------------------
+    # checkpoints in the reference's layout (run_nerf.py:443-461, 1626-1636)
+    def checkpoint(self):
+        """{'global_step', 'network_fn_state_dict', 'network_fine_state_dict', 'optimizer_state_dict'} exactly as the
+        reference trainer saves it: the optimizer entry is a torch.optim.Adam state_dict over the 48 parameter tensors
+        (coarse then fine, registration order) cut out of the flat moment vectors, so either side can resume the other's run."""
+        lr = self.lr0 * (0.1 ** (max(self.global_step - 1, 0) / (self.lrate_decay * 1000)))     # the rate the NEXT step runs at
+        state, i = {}, 0
+        for net, m, v in zip((self.net_c, self.net_f), self.m, self.v):
+            net.flat_params()
+            for o, p in zip(net._offsets, net._flat_params()):
+                state[i] = {"step": torch.tensor(float(self.global_step)),
+                            "exp_avg": m[o:o + p.numel()].view(p.shape).clone(),
+                            "exp_avg_sq": v[o:o + p.numel()].view(p.shape).clone()}
+                i += 1
+        group = {"lr": lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(i))}
+        # the reference saves its 0-based loop counter, i.e. (optimizer steps done - 1), next to the optimizer state (:1629, 1703)
+        return {"global_step": max(self.global_step - 1, 0), "network_fn_state_dict": self.net_c.state_dict(),
+                "network_fine_state_dict": self.net_f.state_dict(), "optimizer_state_dict": {"state": state, "param_groups": [group]}}
+
+    def load_checkpoint(self, ckpt):
+        """Resume from a checkpoint written by `checkpoint()` or by the reference trainer (create_nerf's reload,
+        run_nerf.py:452-461): weights, Adam moments, step counter."""
+        self.net_c.load_state_dict(ckpt["network_fn_state_dict"])
+        self.net_f.load_state_dict(ckpt["network_fine_state_dict"])
+        self.net_c.mark_params_changed(); self.net_f.mark_params_changed()
+        st = ckpt["optimizer_state_dict"]["state"]
+        # optimizer steps done: Adam's own counter where there is one (the reference's `global_step` lags it by one, :1703)
+        self.global_step = int(st[0]["step"]) if 0 in st else int(ckpt["global_step"])
+        i = 0
+        for net, m, v in zip((self.net_c, self.net_f), self.m, self.v):
+            net.flat_params()
+            for o, p in zip(net._offsets, net._flat_params()):
+                if i in st:        # a fresh optimizer has no state yet
+                    m[o:o + p.numel()].copy_(st[i]["exp_avg"].reshape(-1))
+                    v[o:o + p.numel()].copy_(st[i]["exp_avg_sq"].reshape(-1))
+                else:
+                    m[o:o + p.numel()].zero_(); v[o:o + p.numel()].zero_()
+                i += 1
+        if self.adam_state is not None:
+            self.adam_state[0] = float(self.global_step)
+        return self
+
+    # ---------------------------------------------------------------------------------------
     def step_graphed(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
         """`step` replayed as ONE CUDA graph (the whole step is ~45 small and 6 large launches; replaying it removes the
         launch latency a caller that reads the loss back every step would otherwise expose).  Inputs may live on the

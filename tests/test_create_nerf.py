@@ -124,3 +124,54 @@ def test_create_nerf_resumes_from_a_reference_checkpoint(tmp_path):
     assert len(st) == 48 and all(int(s["step"]) == 1 for s in st.values())
     a.no_reload = True
     assert spn.create_nerf(a, device=torch.device("cpu"))[2] == 0
+
+
+@needs_ref
+def test_trainer_checkpoints_interchange_with_the_reference(tmp_path):
+    """Trainer.checkpoint / load_checkpoint use the reference trainer's file layout (run_nerf.py:1626-1636): a checkpoint of
+    reference modules + torch.optim.Adam resumes our fused trainer (flat moments), and ours resumes the reference's
+    optimizer — weights, both Adam moments and the step count survive the round trip in both directions."""
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    H, R = ref_loader.load()
+    torch.manual_seed(5)
+    ref_nets = [H.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True) for _ in range(2)]
+    params = list(ref_nets[0].parameters()) + list(ref_nets[1].parameters())
+    opt = torch.optim.Adam(params=params, lr=5e-4, betas=(0.9, 0.999))
+    for k in range(3):                                              # three reference optimizer steps with synthetic gradients
+        for j, p in enumerate(params):
+            p.grad = torch.full_like(p, 1e-3 * (k + 1) * ((j % 5) - 2))
+        opt.step()
+        for group in opt.param_groups:                              # run_nerf.py:1616-1622 with global_step = k
+            group["lr"] = 5e-4 * (0.1 ** (k / (250 * 1000)))
+    path = str(tmp_path / "000002.tar")
+    torch.save({"global_step": 2, "network_fn_state_dict": ref_nets[0].state_dict(),
+                "network_fine_state_dict": ref_nets[1].state_dict(), "optimizer_state_dict": opt.state_dict()}, path)
+
+    mk = lambda: spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    tr = trainer_mod.Trainer(mk(), mk()).load_checkpoint(torch.load(path, weights_only=False))
+    assert tr.global_step == 3
+    flat = lambda ts: torch.cat([t.reshape(-1) for t in ts])
+    for net, ref, m, v, lo in ((tr.net_c, ref_nets[0], tr.m[0], tr.v[0], 0), (tr.net_f, ref_nets[1], tr.m[1], tr.v[1], 24)):
+        assert torch.equal(net.flat_params(), flat(ref.parameters()))
+        assert torch.equal(m, flat([opt.state[p]["exp_avg"] for p in params[lo:lo + 24]]))
+        assert torch.equal(v, flat([opt.state[p]["exp_avg_sq"] for p in params[lo:lo + 24]]))
+
+    # ... and back: the reference's create_nerf-style reload of OUR checkpoint
+    out = str(tmp_path / "000003_ours.tar")
+    torch.save(tr.checkpoint(), out)
+    ck = torch.load(out, weights_only=False)
+    nets2 = [H.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True) for _ in range(2)]
+    params2 = list(nets2[0].parameters()) + list(nets2[1].parameters())
+    opt2 = torch.optim.Adam(params=params2, lr=5e-4, betas=(0.9, 0.999))
+    opt2.load_state_dict(ck["optimizer_state_dict"])                # run_nerf.py:456
+    nets2[0].load_state_dict(ck["network_fn_state_dict"]); nets2[1].load_state_dict(ck["network_fine_state_dict"])
+    assert ck["global_step"] == 2 and opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
+    for p, q in zip(params, params2):
+        assert torch.equal(p, q)
+        assert torch.equal(opt.state[p]["exp_avg"], opt2.state[q]["exp_avg"])
+        assert torch.equal(opt.state[p]["exp_avg_sq"], opt2.state[q]["exp_avg_sq"])
+        assert float(opt2.state[q]["step"]) == 3.0
+    for j, (p, q) in enumerate(zip(params, params2)):               # and the next optimizer step agrees
+        p.grad = torch.full_like(p, 2e-3); q.grad = torch.full_like(q, 2e-3)
+    opt.step(); opt2.step()
+    assert all(torch.equal(p, q) for p, q in zip(params, params2))
