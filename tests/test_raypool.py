@@ -188,3 +188,60 @@ def test_sparse_depth_rays_reproduce_the_references_rays_depth():
         np.testing.assert_array_equal(rays.transpose(1, 0, 2), ref[:, :2].astype(np.float32))
         np.testing.assert_array_equal(depth, ref[:, 2, 0].astype(np.float32))
         np.testing.assert_array_equal(weight, ref[:, 3, 0].astype(np.float32))
+
+
+def test_run_nerf_fused_cli_dry_run(tmp_path):
+    """tools/run_nerf_fused.py with a reference-style config file (the keys of DS_NeRF/configs/config.txt) on a synthetic scene
+    with a COLMAP sparse model: config parsing, scene loading, the four ray pools, LPIPS sampler — up to the first GPU call."""
+    import subprocess
+    sio = importlib.import_module("spin-nerf_b200.scene_io")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scene = str(tmp_path / "scene")
+    info = sio.synthetic_scene(scene, n_views=6, hw=(24, 32), factor=2, seed=1, n_unlabelled=1)
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(-1, 1, 60), rng.uniform(-1, 1, 60), rng.uniform(-6, -2.5, 60)], 1)
+    sio.write_colmap_model(scene, info["c2w"], info["focal"], (48, 64), pts, rng.uniform(0.2, 2.0, 60), rng)
+    cfg = tmp_path / "config.txt"
+    cfg.write_text("expname = t\nN_gt = 40\nbasedir = %s\ndataset_type = llff\nfactor = 2\nN_rand = 64\nN_samples = 64\n"
+                   "N_importance = 64\nuse_viewdirs = True\nraw_noise_std =1e0\ncolmap_depth = True\ndepth_loss = True\n"
+                   "depth_lambda = 0.1\nno_ndc = True\nlindisp = True\nrender_factor = 1\ni_feat = 2000\ni_video = 2000\n"
+                   "feat_weight = 0.1\nlrate = 0.03\nlrate_decay = 10\nwhite_bkgd = True\n" % (tmp_path / "logs"))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
+                        "--lpips", "--no_tcnn", "--dry_run"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-3000:]
+    assert "sparse-depth rays" in p.stdout and "dry run: stopping before the first GPU call" in p.stdout
+    written = (tmp_path / "logs" / "t" / "args.txt").read_text()
+    assert "lrate = 0.03" in written and "colmap_depth = True" in written and "N_rand = 64" in written
+    bad = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
+                          "--sigma_loss", "--dry_run"], capture_output=True, text=True, timeout=300)
+    assert bad.returncode != 0 and "outside the fused hot path" in (bad.stdout + bad.stderr)
+
+
+def test_run_nerf_fused_cli_loop(tmp_path):
+    """The whole loop of tools/run_nerf_fused.py under the call recorder (tests/fused_cli_driver.py): 3 steps with the
+    sparse-depth group, checkpoint + video + test-set render at step 2, then a second run that resumes from the checkpoint."""
+    import json
+    import subprocess
+    sio = importlib.import_module("spin-nerf_b200.scene_io")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scene, logs = str(tmp_path / "scene"), str(tmp_path / "logs")
+    info = sio.synthetic_scene(scene, n_views=6, hw=(24, 32), factor=2, seed=1, n_unlabelled=1)
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(-1, 1, 60), rng.uniform(-1, 1, 60), rng.uniform(-6, -2.5, 60)], 1)
+    sio.write_colmap_model(scene, info["c2w"], info["focal"], (48, 64), pts, rng.uniform(0.2, 2.0, 60), rng)
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(root, "tests", "fused_cli_driver.py"), scene, logs] + list(extra),
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-3000:]
+        return json.loads([l for l in p.stdout.splitlines() if l.startswith("CLI ")][-1][4:]), p.stdout
+    res, out = run("--colmap_depth", "--depth_loss", "--N_iters", "3", "--i_weights", "2", "--i_video", "2", "--i_testset", "2")
+    assert res["rc"] == 0 and out.count("[TRAIN] Iter:") == 3
+    assert "000002.tar" in res["files"] and "t_000002_rgb.mp4" in res["files"] and "t_000002_disp.mp4" in res["files"]
+    assert any(f.startswith("testset_000002/rgb/") for f in res["files"])
+    c = res["counts"]
+    assert c["spn_render_rays_bwd"] == 3 and c["spn_adam_step"] == 6 and c["spn_train_losses"] == 3
+    assert c["spn_get_rays"] == 120 + 1                     # the spiral video and the held-out test view
+    res2, out2 = run("--N_iters", "4", "--i_weights", "100", "--lpips", "--lpips_from", "3")
+    assert res2["counts"]["spn_render_rays_bwd"] == 3       # step 3, step 4 and step 4's LPIPS patch chunk
+    assert "Reloading from" in out2 and out2.count("[TRAIN] Iter:") == 2 and "[TRAIN] Iter: 3 " in out2      # resumed after step 2
