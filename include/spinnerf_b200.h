@@ -183,8 +183,9 @@ int spn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   void* stream);
 /* The same update with the step counter and learning-rate schedule on the device, so that a whole train step can be
  * captured once and replayed as a CUDA graph.  state4 = {step, lr/bias_correction1, sqrt(bias_correction2), lr} (floats,
- * zero-initialised).  spn_adam_tick advances it once per optimisation step: step += 1, lr = lr0 * decay_base^((step-1) /
- * decay_steps) (run_nerf.py:1616-1622: decay_base 0.1, decay_steps lrate_decay*1000); spn_adam_step_dev applies it. */
+ * zero-initialised).  spn_adam_tick advances it once per optimisation step: step += 1, lr = lr0 * decay_base^(max(step-2, 0) /
+ * decay_steps) — the reference updates the rate AFTER optimizer.step() from its 0-based global_step (run_nerf.py:1611-1622,
+ * 1703), so steps 1 and 2 both run at lr0; decay_base 0.1, decay_steps lrate_decay*1000.  spn_adam_step_dev applies it. */
 int spn_adam_tick(float* state4, float lr0, float decay_base, float decay_steps, float beta1, float beta2, void* stream);
 int spn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* state4, float beta1, float beta2, float eps, float grad_scale, void* stream);
