@@ -139,6 +139,41 @@ def cpu_train_steps(n_rays, steps, warmup, seed=0):
     return RENDERS_PER_STEP * n_rays * len(times) / sum(times), float(np.mean(times))
 
 
+def gpu_reference_port(spn, dev, pool, rgb_pool, disp_pool, n_rand, steps=6, warmup=2):
+    """The like-for-like baseline of SURVEY.md section 8d: the reference's own formulation of the step — eager PyTorch ops,
+    fp32 GEMMs with TF32 off (torch's default, which the reference never changes), autograd, torch.optim.Adam — on the SAME
+    GPU and workload.  The unmodified reference cannot travel to the GPU box, so this times its PyTorch restatement
+    (oracle/torch_port.py, pinned on CPU against the reference's goldens); baseline only, never the product path."""
+    import torch
+    from oracle import torch_port as TP
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    nets = [spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True).seeded_init_(s)
+            for s in (1, 2)]
+    pc, pf = ({k: v.detach().clone().to(dev).requires_grad_(True) for k, v in n.state_dict().items()} for n in nets)
+    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    M = pool.shape[1]
+    evs = []
+    for it in range(warmup + steps):
+        idx = torch.randint(0, M, (3, n_rand), device=dev, generator=g)
+        b = [(pool[:, idx[0]], rgb_pool[idx[0]]), (pool[:, idx[1]], rgb_pool[idx[1]]), (pool[:, idx[2]], disp_pool[idx[2]])]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad()
+        loss, _ = TP.spin_step_loss(b, pc, pf, NEAR, FAR, perturb=True, raw_noise_std=1.0)
+        loss.backward()
+        opt.step()
+        e1.record()
+        if it >= warmup:
+            evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    return {"value": RENDERS_PER_STEP * n_rand / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "kind": "port: PyTorch restatement of the reference step (eager ops, fp32 GEMMs with TF32 off, autograd, "
+                    "torch.optim.Adam) on the same GPU and workload; device-timed", "final_loss": float(loss.detach())}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -581,6 +616,13 @@ def main():
                     "algorithmic_units": "wgrad: 76 x 16 KB stash/dstash atoms per 128-sample tile; fwd/dgrad: 1 186 816 / 1 115 392 FLOP per MLP evaluation",
                     "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
+    gpu_port = None
+    if not args.no_cpu_baseline and world == 1:
+        phase("gpu_reference_port (PyTorch restatement of the reference step on this GPU)")
+        try:
+            gpu_port = gpu_reference_port(spn, dev, pool, rgb_pool, disp_pool, n_rand)
+        except Exception as e:                           # a baseline must never cost the run its result line
+            gpu_port = {"error": f"{type(e).__name__}: {e}"[:300]}
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
         phase("cpu_baseline sample (oracle port on the host cores)")
@@ -597,7 +639,7 @@ def main():
             "config": workload_config(world, n_rand), "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu, "n_rand_per_sec": value / RENDERS_PER_STEP,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_reference_port": gpu_port, "n_rand_per_sec": value / RENDERS_PER_STEP,
             "wall_s_timed_region": wall, "final_loss": float(loss)}
     print(json.dumps(line))
 

@@ -285,3 +285,49 @@ def test_spin_step_with_sparse_depth_rays_matches_reference(one_chunk):
             assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
             close_mostly(gv.reshape(-1)[::997], gold[f"g_sub__{nm}__{k}"], rtol=1e-2, atol=1e-3 * np.abs(gv).max() + 1e-9,
                          max_frac=0.03, hard=1.0)
+
+
+def test_torch_port_render_matches_reference():
+    """oracle/torch_port.py (the PyTorch restatement bench.py times on the GPU as `gpu_reference_port`) against the
+    unmodified reference's render golden."""
+    import torch
+    from oracle import torch_port as TP
+    g = load_golden("render")
+    pc = O.init_params(11); pc["alpha_linear.bias"] = pc["alpha_linear.bias"] + 1.0
+    pf = O.init_params(12); pf["alpha_linear.bias"] = pf["alpha_linear.bias"] + 1.0
+    with torch.no_grad():
+        out = TP.render_rays(torch.from_numpy(g["rays"][0]), torch.from_numpy(g["rays"][1]), 1.2, 8.0,
+                             TP.make_params(pc, "cpu"), TP.make_params(pf, "cpu"))
+    G = lambda k: g[f"det_lindisp_white__{k}"]
+    N = lambda t: t.numpy()
+    close_mostly(N(out["z_vals"]), G("z_vals"), rtol=2e-5, atol=1e-5)
+    close_mostly(N(out["weights"]), G("weights"), rtol=0, atol=2e-4)
+    close_mostly(N(out["rgb_map"]), G("rgb"), rtol=0, atol=2e-4); close_mostly(N(out["disp_map"]), G("disp"), rtol=5e-4, atol=0)
+    close(N(out["rgb0"]), G("rgb0"), atol=2e-4); close(N(out["disp0"]), G("disp0"), rtol=5e-4)
+
+
+def test_torch_port_walks_the_references_training_trajectory():
+    """... and its train step (autograd + torch.optim.Adam + the reference's schedule) against the first steps of the
+    reference's 300-step run (tests/golden/convergence.npz)."""
+    import importlib.util
+    import os
+    import torch
+    from conftest import GOLDEN
+    from oracle import torch_port as TP
+    spec = importlib.util.spec_from_file_location("make_convergence_golden", os.path.join(GOLDEN, "make_convergence_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = load_golden("convergence")
+    ro, rd, rgb_t, disp_t, idx = gen.problem()
+    pc, pf = (TP.make_params(p, "cpu") for p in gen.params())
+    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=gen.LR, betas=(0.9, 0.999))
+    T = torch.from_numpy
+    for it in range(4):
+        b = [(T(np.stack([ro[idx[it, k]], rd[idx[it, k]]], 0)), T((rgb_t if k < 2 else disp_t)[idx[it, k]])) for k in range(3)]
+        opt.zero_grad()
+        loss, psnr = TP.spin_step_loss(b, pc, pf, gen.NEAR, gen.FAR)
+        loss.backward()
+        opt.step()
+        for group in opt.param_groups:
+            group["lr"] = gen.LR * (0.1 ** (it / (gen.DECAY * 1000)))
+        assert abs(float(loss) - float(gold["loss"][it])) <= 1e-4 * float(gold["loss"][it]), (it, float(loss))
+        assert abs(float(psnr) - float(gold["psnr"][it])) <= 1e-3
