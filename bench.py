@@ -85,55 +85,45 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle port of the train step on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_threads_best(n_rays=64):
-    """BLAS thread count for the CPU arm: all host threads unless fewer are measurably faster (on a 128-core box the 256-wide
-    GEMMs of this workload ran 5x slower on 128 threads than on 16).  One probe step per candidate."""
+    """Thread count for the CPU arm: all host threads unless fewer are measurably faster (on a 128-core box the 256-wide GEMMs
+    of this workload ran 5x slower on 128 threads than on 16).  One probe step per candidate."""
+    import torch
     cores = os.cpu_count() or 1
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        return cores, None
     best, best_t = cores, None
     for c in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
-        with threadpool_limits(limits=c):
-            _, t = cpu_train_steps(n_rays, 1, 1)
+        torch.set_num_threads(c)
+        _, t = cpu_train_steps(n_rays, 1, 1)
         if best_t is None or t < 0.9 * best_t:
             best, best_t = c, t
-    return best, threadpool_limits
+    torch.set_num_threads(best)
+    return best
 
 
 def cpu_train_steps(n_rays, steps, warmup, seed=0):
+    """The reference's formulation of the train step on the host cores: eager PyTorch CPU ops, autograd, torch.optim.Adam
+    (oracle/torch_port.py — the PyTorch restatement pinned against the reference's goldens; the unmodified reference is
+    Python + PyTorch too but cannot travel to the GPU box).  Returns (rays/s, seconds per step)."""
+    import torch
     from oracle import nerf_oracle as O
-    from oracle import train_oracle as TO
+    from oracle import torch_port as TP
     rng = np.random.default_rng(seed)
-    pc, pf = O.init_params(1), O.init_params(2)
-    sc, sf = TO.AdamState(pc), TO.AdamState(pf)
-    ps = poses(4)
-    all_rays = [O.get_rays(H, W, FOCAL, p) for p in ps]      # the scene's rays are resident before the timed steps, as on the GPU
+    g = torch.Generator().manual_seed(seed)
+    pc, pf = TP.make_params(O.init_params(1), "cpu"), TP.make_params(O.init_params(2), "cpu")
+    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
+    all_rays = [O.get_rays(H, W, FOCAL, p) for p in poses(4)]   # the scene's rays are resident before the timed steps, as on the GPU
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
+        batches = []
         for call in range(RENDERS_PER_STEP):
-            ro, rd = all_rays[(it + call) % len(ps)]
+            ro, rd = all_rays[(it + call) % len(all_rays)]
             sel = rng.choice(H * W, n_rays, replace=False)
-            rb = O.make_ray_batch(ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], NEAR, FAR)
-            tgt = rng.uniform(0, 1, (n_rays, 3)).astype(np.float32); td = rng.uniform(0, 1, n_rays).astype(np.float32)
-            t_rand = rng.uniform(0, 1, (n_rays, 64)).astype(np.float32); u = rng.uniform(0, 1, (n_rays, 64)).astype(np.float32)
-
-            def g_out(o, call=call):
-                if call < 2:
-                    return dict(rgb_map=TO.mse_grad(o["rgb_map"], tgt)[1], rgb0=TO.mse_grad(o["rgb0"], tgt)[1])
-                return dict(disp_map=TO.mse_grad(o["disp_map"], td)[1], disp0=TO.mse_grad(o["disp0"], td)[1])
-            _, gc, gf = TO.render_with_grads(rb, pc, pf, 64, 64, True, True, g_out, detach_weights=(call == 1), u=u,
-                                             t_rand=t_rand, noise0=rng.standard_normal((n_rays, 64)).astype(np.float32),
-                                             noise1=rng.standard_normal((n_rays, 128)).astype(np.float32))
-            if call == 0:
-                acc_c, acc_f = gc, gf
-            else:
-                acc_c = {k: acc_c[k] + gc[k] for k in gc}; acc_f = {k: acc_f[k] + gf[k] for k in gf}
-        for p, g, st in ((pc, acc_c, sc), (pf, acc_f, sf)):
-            st.step += 1
-            for k in p:
-                p[k], st.m[k], st.v[k] = O.adam_step(p[k], g[k], st.m[k], st.v[k], st.step, 5e-4)
+            rays = torch.from_numpy(np.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0))
+            batches.append((rays, torch.rand((n_rays, 3) if call < 2 else (n_rays,), generator=g)))
+        opt.zero_grad()
+        loss, _ = TP.spin_step_loss(batches, pc, pf, NEAR, FAR, perturb=True, raw_noise_std=1.0)
+        loss.backward()
+        opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     return RENDERS_PER_STEP * n_rays * len(times) / sum(times), float(np.mean(times))
@@ -179,21 +169,20 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cpu_rays
-    cores, limits = cpu_threads_best()
-    ctx = limits(limits=cores) if limits else __import__("contextlib").nullcontext()
-    with ctx:
-        # bounded sample: one probe step sizes the per-step ray count so that warmup + steps end within ~4 minutes
-        _, probe = cpu_train_steps(n, 1, 0)
-        budget = 240.0 / max(1, args.steps + args.warmup)
-        while n > 8 and probe * (n / args.cpu_rays) > budget:
-            n //= 2
-        rps, sec = cpu_train_steps(n, args.steps, args.warmup)
+    cores = cpu_threads_best()
+    # bounded sample: one probe step sizes the per-step ray count so that warmup + steps end within ~4 minutes
+    _, probe = cpu_train_steps(n, 1, 0)
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    while n > 8 and probe * (n / args.cpu_rays) > budget:
+        n //= 2
+    rps, sec = cpu_train_steps(n, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "rays/sec (train-step)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus, n),
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{RENDERS_PER_STEP}x{n} rays per step (same scene/config), numpy+BLAS oracle port of the reference train step"},
+                             "sample": f"{RENDERS_PER_STEP}x{n} rays per step (same scene/config), PyTorch CPU restatement of the reference train "
+                                       "step (oracle/torch_port.py: eager ops, autograd, torch.optim.Adam)"},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -627,12 +616,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
         phase("cpu_baseline sample (oracle port on the host cores)")
         t0 = time.perf_counter()
-        cores, limits = cpu_threads_best()
-        with (limits(limits=cores) if limits else __import__("contextlib").nullcontext()):
-            rps, sec = cpu_train_steps(args.cpu_rays, 2, 1)
+        cores = cpu_threads_best()
+        rps, sec = cpu_train_steps(args.cpu_rays, 4, 1)
         cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"3 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, numpy+BLAS oracle port "
-                         f"of the reference train step ({time.perf_counter() - t0:.1f} s)"}
+               "sample": f"5 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, PyTorch CPU restatement "
+                         f"of the reference train step (oracle/torch_port.py) ({time.perf_counter() - t0:.1f} s)"}
     line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
