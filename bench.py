@@ -616,11 +616,14 @@ def main():
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
         phase("cpu_baseline sample (oracle port on the host cores)")
         t0 = time.perf_counter()
-        cores = cpu_threads_best()
-        rps, sec = cpu_train_steps(args.cpu_rays, 4, 1)
-        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"5 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, PyTorch CPU restatement "
-                         f"of the reference train step (oracle/torch_port.py) ({time.perf_counter() - t0:.1f} s)"}
+        try:
+            cores = cpu_threads_best()
+            rps, sec = cpu_train_steps(args.cpu_rays, 4, 1)
+            cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                   "sample": f"5 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, PyTorch CPU "
+                             f"restatement of the reference train step (oracle/torch_port.py) ({time.perf_counter() - t0:.1f} s)"}
+        except Exception as e:                           # a baseline must never cost the run its result line
+            cpu = {"error": f"{type(e).__name__}: {e}"[:300]}
     line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
