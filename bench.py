@@ -398,6 +398,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n_rand", type=int, default=1024)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver's 1/2/4/8 series measures): --n_rand rays per render call PER GPU; strong: "
+                         "--n_rand_global rays per render call in total, split over the ranks (BASELINE configs[3]: 8192 over 8 GPUs)")
+    ap.add_argument("--n_rand_global", type=int, default=8192)
     ap.add_argument("--cpu_rays", type=int, default=128, help="rays per render call in the CPU sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "train_lpips", "render"],
@@ -453,7 +457,7 @@ def main():
         net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
         net = net.seeded_init_(seed).to(dev); net.precision = prec
         nets.append(net)
-    n_rand = args.n_rand
+    n_rand = args.n_rand if args.scaling == "weak" else max(1, args.n_rand_global // world)
     sharder = trainer_mod.RaySharder(rank, world)
     tr = trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
                              perturb=1.0, raw_noise_std=1.0, near=NEAR, far=FAR, ndc=False, hwf=(H, W, FOCAL),
@@ -521,7 +525,7 @@ def main():
     rays_per_step = RENDERS_PER_STEP * global_n
     value = rays_per_step * args.steps / (step_ms * 1e-3)
     PARTIAL.update({"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                    "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                    "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
                     "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
                     "config": workload_config(world, n_rand), "gpu_launches": launches, "e2e": None})
 
@@ -625,7 +629,7 @@ def main():
         except Exception as e:                           # a baseline must never cost the run its result line
             cpu = {"error": f"{type(e).__name__}: {e}"[:300]}
     line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16" if prec == spn.PREC_BF16 else "f32", "data": "synthetic",
             "config": workload_config(world, n_rand), "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
