@@ -99,10 +99,11 @@ def cpu_threads_best(n_rays=64):
     return best
 
 
-def cpu_train_steps(n_rays, steps, warmup, seed=0):
+def cpu_train_steps(n_rays, steps, warmup, seed=0, anomaly=False):
     """The reference's formulation of the train step on the host cores: eager PyTorch CPU ops, autograd, torch.optim.Adam
     (oracle/torch_port.py — the PyTorch restatement pinned against the reference's goldens; the unmodified reference is
-    Python + PyTorch too but cannot travel to the GPU box).  Returns (rays/s, seconds per step)."""
+    Python + PyTorch too but cannot travel to the GPU box).  Returns (rays/s, MEDIAN seconds per step).  anomaly=True runs
+    with autograd anomaly detection on, which the reference switches on globally at import (run_nerf_helpers.py:5)."""
     import torch
     from oracle import nerf_oracle as O
     from oracle import torch_port as TP
@@ -112,6 +113,7 @@ def cpu_train_steps(n_rays, steps, warmup, seed=0):
     opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
     all_rays = [O.get_rays(H, W, FOCAL, p) for p in poses(4)]   # the scene's rays are resident before the timed steps, as on the GPU
     times = []
+    torch.autograd.set_detect_anomaly(bool(anomaly))
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         batches = []
@@ -126,7 +128,9 @@ def cpu_train_steps(n_rays, steps, warmup, seed=0):
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return RENDERS_PER_STEP * n_rays * len(times) / sum(times), float(np.mean(times))
+    torch.autograd.set_detect_anomaly(False)
+    med = float(np.median(times))
+    return RENDERS_PER_STEP * n_rays / med, med
 
 
 def gpu_reference_port(spn, dev, pool, rgb_pool, disp_pool, n_rand, steps=6, warmup=2):
@@ -176,13 +180,15 @@ def run_reference(args):
     while n > 8 and probe * (n / args.cpu_rays) > budget:
         n //= 2
     rps, sec = cpu_train_steps(n, args.steps, args.warmup)
+    rps_anom, _ = cpu_train_steps(n, min(args.steps, 3), 1, anomaly=True)
     line = {"impl": "reference", "metric": "rays/sec (train-step)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus, n),
-            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "anomaly_mode_on_value": rps_anom,
                              "sample": f"{RENDERS_PER_STEP}x{n} rays per step (same scene/config), PyTorch CPU restatement of the reference train "
-                                       "step (oracle/torch_port.py: eager ops, autograd, torch.optim.Adam)"},
+                                       "step (oracle/torch_port.py: eager ops, autograd, torch.optim.Adam), median step time; `value` with autograd anomaly "
+                                       "detection off (the faster way), `anomaly_mode_on_value` with it on as the reference runs"},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -622,10 +628,13 @@ def main():
         t0 = time.perf_counter()
         try:
             cores = cpu_threads_best()
-            rps, sec = cpu_train_steps(args.cpu_rays, 4, 1)
-            cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": f"5 steps (1 warm-up) of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, PyTorch CPU "
-                             f"restatement of the reference train step (oracle/torch_port.py) ({time.perf_counter() - t0:.1f} s)"}
+            rps, sec = cpu_train_steps(args.cpu_rays, 5, 2)
+            rps_anom, _ = cpu_train_steps(args.cpu_rays, 3, 1, anomaly=True)
+            cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "anomaly_mode_on_value": rps_anom,
+                   "sample": f"median of 5 steps after 2 warm-ups of {RENDERS_PER_STEP}x{args.cpu_rays} rays, same scene/config, "
+                             "PyTorch CPU restatement of the reference train step (oracle/torch_port.py); `value` with autograd "
+                             "anomaly detection off, `anomaly_mode_on_value` with it on as the reference runs (run_nerf_helpers.py:5) "
+                             f"({time.perf_counter() - t0:.1f} s)"}
         except Exception as e:                           # a baseline must never cost the run its result line
             cpu = {"error": f"{type(e).__name__}: {e}"[:300]}
     line = {"metric": "rays/sec (train-step)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
