@@ -245,6 +245,9 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     `network_query_fn` is not called: encoding + MLP run inside the fused kernels."""
     if sigma_loss is not None:
         raise NotImplementedError("sigma_loss (DS_NeRF/loss.py) is outside the B200 hot path")
+    if need_alpha and N_importance <= 0:
+        # the reference builds ret['alpha0'] from a name that only exists after a fine pass (run_nerf.py:696, 719-721)
+        raise NameError("name 'alpha0' is not defined (need_alpha=True requires N_importance > 0, as in the reference)")
     fused = type(network_fn) is NeRF and (network_fine is None or type(network_fine) is NeRF)
     if not fused:
         return render_rays_composed(ray_batch, network_fn, network_query_fn, N_samples, retraw, lindisp, perturb,

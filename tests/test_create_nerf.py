@@ -175,3 +175,13 @@ def test_trainer_checkpoints_interchange_with_the_reference(tmp_path):
         p.grad = torch.full_like(p, 2e-3); q.grad = torch.full_like(q, 2e-3)
     opt.step(); opt2.step()
     assert all(torch.equal(p, q) for p, q in zip(params, params2))
+
+
+def test_need_alpha_without_fine_pass_fails_like_the_reference():
+    """SURVEY.md section 8 a3: the reference raises NameError (alpha0 undefined) for need_alpha=True with N_importance == 0;
+    ours fails the same way before touching the GPU instead of returning an undefined alpha0."""
+    net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    with pytest.raises(NameError):
+        spn.render_rays(torch.zeros(4, 11), net, None, 64, N_importance=0, need_alpha=True)
+    with pytest.raises(NotImplementedError):
+        spn.render_rays(torch.zeros(4, 11), net, None, 64, N_importance=0, sigma_loss=object())
