@@ -16,6 +16,8 @@ done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ $rc -ne 0 ]; then cat "$HERE"/obj/*.log; exit 1; fi
+# the logs are tracked (ptxas -v: registers, spills, shared memory per kernel): drop the only lines that differ from build to build
+for f in "${SRCS[@]}"; do sed -i '/Compile time = /d' "$HERE/obj/$f.log"; done
 OBJS=()
 for f in "${SRCS[@]}"; do OBJS+=("$HERE/obj/$f.o"); done
 "$NVCC" "${ARCH[@]}" --shared -o "$OUT" "${OBJS[@]}"
