@@ -190,6 +190,27 @@ int spn_adam_tick(float* state4, float lr0, float decay_base, float decay_steps,
 int spn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* state4, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- (e)  multi-GPU gradient exchange over NVLink peer memory, fused with the optimiser ------------------------------
+ * No counterpart in the reference (single GPU, run_nerf.py:39); replaces "NCCL all-reduce of the flat gradients, then
+ * spn_adam_step per network" of the ray-sharded step.  OPT-IN and not yet run on hardware
+ * (csrc/peer_reduce.cu header); the default path is NCCL.
+ * Each rank allocates one region of spn_peer_region_bytes(n_floats) with spn_peer_alloc (cudaMalloc + IPC handle, zeroed),
+ * exchanges the 64-byte handles out of band, maps the others with spn_peer_open and, after a host-side barrier, calls
+ * spn_peer_allreduce_adam once per optimisation step with the same monotonically increasing `epoch` (>= 1) on every rank.
+ * The rank's flat gradients live INSIDE its region (spn_peer_grad_ptr): [coarse n_params | pad | fine n_params | pad] with
+ * the fine vector at float offset `stride`, n_floats >= 2*stride, all multiples of 4.  `regions` is a HOST array of `world`
+ * device pointers (own region at [rank]).  lr / betas / eps / step / grad_scale as in spn_adam_step (both networks). */
+size_t spn_peer_region_bytes(int64_t n_floats);
+int spn_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int spn_peer_open(const unsigned char* handle64, void** dev_ptr);
+int spn_peer_close(void* dev_ptr);
+int spn_peer_free(void* dev_ptr);
+void* spn_peer_grad_ptr(void* region);
+int spn_peer_allreduce_adam(void* const* regions, int world, int rank, unsigned int epoch, int64_t n_floats,
+                            int64_t n_params, int64_t stride, float* param_c, float* m_c, float* v_c,
+                            float* param_f, float* m_f, float* v_f, float lr, float beta1, float beta2,
+                            float eps, int step, float grad_scale, void* stream);
+
 /* ---- a1-a3  render_rays, whole chunk (run_nerf.py:593-737) --------------------------------- */
 typedef struct {
   int n_rays;          /* rays in this chunk                                         */

@@ -78,6 +78,14 @@ _SIGS = {
     "spn_adam_tick": (C.c_int, [c_fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_fp]),
     "spn_adam_step_dev": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_float, C.c_float, C.c_float, C.c_float, c_fp]),
     "spn_adam_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, c_fp]),
+    "spn_peer_region_bytes": (C.c_size_t, [C.c_int64]),
+    "spn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "spn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "spn_peer_close": (C.c_int, [c_fp]),
+    "spn_peer_free": (C.c_int, [c_fp]),
+    "spn_peer_grad_ptr": (C.c_void_p, [c_fp]),
+    "spn_peer_allreduce_adam": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_int64, C.c_int64, C.c_int64]
+                                + [c_fp] * 6 + [C.c_float] * 4 + [C.c_int, C.c_float, c_fp]),
     "spn_render_rays_fwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), c_fp]),
     "spn_render_rays_bwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(RenderIO), C.POINTER(RenderGrads), c_fp]),
     "spn_render_host": (C.c_int, [C.POINTER(RenderCfg), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),

@@ -6,7 +6,7 @@ OUT="${SPN_LIB_OUT:-$HERE/../libspinnerf_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH=(-gencode arch=compute_100a,code=sm_100a)
 FLAGS=(-O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v ${SPN_EXTRA_NVCC_FLAGS:-})
-SRCS=(api ops_render mlp_fp32 mlp_tc mlp_tc_bwd)
+SRCS=(api ops_render mlp_fp32 mlp_tc mlp_tc_bwd peer_reduce)
 mkdir -p "$HERE/obj"
 pids=()
 for f in "${SRCS[@]}"; do

@@ -10,6 +10,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from . import peer
 from .dist import RaySharder, allreduce_sum_
 from .render import chunk_backward, chunk_forward
 
@@ -53,6 +54,12 @@ class Trainer:
         stride = (L.MLP_NPARAMS + 127) // 128 * 128
         self.grad_all = torch.zeros(2 * stride, device=dev)
         self.grads = [self.grad_all[:L.MLP_NPARAMS], self.grad_all[stride:stride + L.MLP_NPARAMS]]
+        self.peer = None
+        if self.sharder.world > 1 and peer.enabled():
+            # opt-in (SPN_P2P_ALLREDUCE=1): the gradient vector lives in an IPC-exported region and the step ends with the
+            # fused reduce-scatter / all-gather / Adam over NVLink peer memory (csrc/peer_reduce.cu) instead of NCCL + Adam
+            self.peer = peer.PeerGradExchange(L.MLP_NPARAMS, dev, process_group)
+            self.grad_all, self.grads = self.peer.grad_all, self.peer.grads
         self.m = [z(), z()]
         self.v = [z(), z()]
         self.global_step = 0
@@ -275,6 +282,13 @@ class Trainer:
         """NCCL all-reduce (mean over ranks) of the two flat gradient vectors, then one Adam launch per network;
         learning-rate schedule of run_nerf.py:1616-1622.  With `self.adam_state` set (CUDA-graph mode) the step counter
         and schedule live on the device (spn_adam_tick / spn_adam_step_dev) so the launches are replayable."""
+        if self.peer is not None and self.adam_state is None:
+            self.global_step += 1
+            lr = self.lr0 * (0.1 ** (max(self.global_step - 2, 0) / (self.lrate_decay * 1000)))
+            self.peer.allreduce_adam(self.global_step, self.net_c, self.net_f, self.m, self.v, lr, self.betas, self.eps,
+                                     self.global_step)
+            self.net_c.mark_params_changed(); self.net_f.mark_params_changed()
+            return
         scale = allreduce_sum_([self.grad_all], self.pg) if self.sharder.world > 1 else 1.0
         self.global_step += 1
         if self.adam_state is not None:

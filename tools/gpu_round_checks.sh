@@ -31,5 +31,10 @@ run ncu_full       600 ncu --set full --clock-control none --import-source on -k
                        -o "$OUT/${TAG}_mlp" -f python bench.py --steps 8 --warmup 3 --no_cpu_baseline --deadline 0
 run san_memcheck   600 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()"
 run san_racecheck  900 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()"
+# multi-GPU only (gpurun --gpus 2): the opt-in peer-memory gradient exchange against NCCL
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  run peer_allreduce 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_peer_allreduce.py
+  run bench_n2       420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2
+fi
 grep -h '^{' "$OUT/${TAG}"_bench_*.log > "$OUT/${TAG}_bench_lines.jsonl" 2>/dev/null
 tail -n 3 "$OUT/${TAG}"_tests_gpu.log "$OUT/${TAG}"_smoke.log "$OUT/${TAG}"_san_*.log
