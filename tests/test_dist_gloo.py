@@ -85,6 +85,43 @@ def test_two_rank_frame_gather_restores_frame_order(tmp_path):
     assert torch.equal(dist_mod.gather_frames(one, 5, 0, 1), one)
 
 
+def _video_worker(rank, world, port, out):
+    """render_path_sharded under gloo with the C library replaced by the call recorder (zero-filled outputs): the frame
+    dealing, the per-rank device buffer, the gather and the hand-over, end to end in two processes."""
+    import importlib
+    import test_host_glue_dry_run as dry
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    rec = dry.Recorder()
+    for m in (dry.L, dry.ops, dry.render_mod):
+        m.lib = (lambda rec=rec: rec); m.ptr = dry._ptr; m.stream = (lambda: 0)
+    dry.ops._empty = lambda shape, like, dtype=torch.float32: torch.zeros(shape, device=like.device, dtype=dtype)
+    dry.nerf_mod.NeRF._sync = lambda self: (self.flat_params(), torch.zeros(64, dtype=torch.uint8))
+    # zero-filled chunk outputs: chunk_forward allocates with torch.empty, make that deterministic too
+    real_empty = torch.empty
+    dry.render_mod.torch.empty = lambda *a, **k: real_empty(*a, **k).zero_()
+    dist_mod.init_from_env("gloo")
+    spn = importlib.import_module("spin-nerf_b200")
+    nets = [spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True) for _ in range(2)]
+    kw = dict(network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=8, N_importance=8, lindisp=True,
+              white_bkgd=True, perturb=0., raw_noise_std=0., use_viewdirs=True, ndc=False, near=1.2, far=8.0)
+    poses = np.tile(np.eye(4, dtype=np.float32)[None, :3, :], (5, 1, 1))
+    rgbs, disps = spn.render_path_sharded(poses, [12, 16, 14.4], 64, kw, render_factor=2)
+    only = spn.render_path_sharded(poses, [12, 16, 14.4], 64, kw, dst=1)
+    mine = dist_mod.frames_for_rank(5, rank, world)
+    ok = (rgbs.shape == (5, 6, 8, 3) and disps.shape == (5, 6, 8) and rec.names().count("spn_get_rays") == 2 * len(mine)
+          and ((only[0] is None) == (rank != 1)) and (rank != 1 or only[0].shape == (5, 12, 16, 3)))
+    np.save(out + f".{rank}.npy", np.array([int(ok)]))
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_video_render_glue(tmp_path):
+    out = str(tmp_path / "video")
+    mp.spawn(_video_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert all(int(np.load(out + f".{r}.npy")[0]) == 1 for r in range(2))
+
+
 def test_sharder_partitions_exactly():
     for n in (1, 7, 1024, 8192):
         for w in (1, 2, 3, 8):
