@@ -115,6 +115,41 @@ def _video_worker(rank, world, port, out):
     torch.distributed.destroy_process_group()
 
 
+def _trainer_worker(rank, world, port, out):
+    """Trainer.step on two ranks over gloo with the call recorder: each rank renders its contiguous half of every ray group,
+    the single gradient buffer is all-reduced once, Adam is told to average (grad_scale = 1 / world)."""
+    import importlib
+    import test_host_glue_dry_run as dry
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    rec = dry.Recorder()
+    for m in (dry.L, dry.ops, dry.render_mod):
+        m.lib = (lambda rec=rec: rec); m.ptr = dry._ptr; m.stream = (lambda: 0)
+    dry.nerf_mod.NeRF._sync = lambda self: (self.flat_params(), torch.zeros(64, dtype=torch.uint8))
+    dist_mod.init_from_env("gloo")
+    tmod = dry.trainer_mod
+
+    def fake_backward(cfg, k, net_c, net_f, g, gc, gf, scratch=None, ws=None, detach_range=(0, 0)):
+        gc.fill_(float(rank + 1)); gf.fill_(float(10 * (rank + 1)))       # what a rank's backward would accumulate
+    tmod.chunk_backward = fake_backward
+    tr = dry._trainer(rank=rank, world=world)
+    tr.step(*dry._batch(8))
+    cfg = rec.calls[1][1][0]._obj
+    adam = [c for c in rec.calls if c[0] == "spn_adam_step"]
+    ok = (cfg.n_rays == 12 and len(adam) == 2 and abs(adam[0][1][10] - 0.5) < 1e-12           # grad_scale = 1 / world
+          and float(tr.grads[0].min()) == float(tr.grads[0].max()) == 3.0                    # 1 + 2 summed over the ranks
+          and float(tr.grads[1].min()) == float(tr.grads[1].max()) == 30.0 and tr.global_step == 1)
+    np.save(out + f".{rank}.npy", np.array([int(ok)]))
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_trainer_step_glue(tmp_path):
+    out = str(tmp_path / "trainer")
+    mp.spawn(_trainer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert all(int(np.load(out + f".{r}.npy")[0]) == 1 for r in range(2))
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_sharded_video_render_glue(tmp_path):
     out = str(tmp_path / "video")
