@@ -11,7 +11,7 @@ import torch
 
 from oracle import nerf_oracle as O
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]      # written without a GPU at hand: a stall must fail, not hang
 
 spn = importlib.import_module("spin-nerf_b200")
 DEV = "cuda"
