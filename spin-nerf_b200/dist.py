@@ -48,6 +48,18 @@ def allreduce_sum_(flat_grads, group=None):
     return 1.0 / world
 
 
+def broadcast_parameters(nets, src=0, group=None):
+    """Replicas must start identical ("initial weight broadcast (or identical seeds)"): one broadcast of
+    each network's flat parameter vector from rank `src`.  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for net in nets:
+        if net is None:
+            continue
+        dist.broadcast(net.flat_params(), src=src, group=group)
+        net.mark_params_changed()
+
+
 def frames_for_rank(n_frames, rank, world):
     """render_path sharding (config 5): frames round-robin over ranks."""
     return list(range(rank, n_frames, world))

@@ -133,10 +133,15 @@ def _trainer_worker(rank, world, port, out):
         gc.fill_(float(rank + 1)); gf.fill_(float(10 * (rank + 1)))       # what a rank's backward would accumulate
     tmod.chunk_backward = fake_backward
     tr = dry._trainer(rank=rank, world=world)
+    with torch.no_grad():                                   # replicas that start different (a per-rank torch seed) ...
+        tr.net_c.flat_params().add_(float(rank)); tr.net_f.flat_params().add_(float(rank))
+    dist_mod.broadcast_parameters([tr.net_c, tr.net_f])     # ... are made identical to rank 0's
+    same = dry._trainer(rank=0, world=1)
+    bcast_ok = torch.equal(tr.net_c.flat_params(), same.net_c.flat_params()) and torch.equal(tr.net_f.flat_params(), same.net_f.flat_params())
     tr.step(*dry._batch(8))
     cfg = rec.calls[1][1][0]._obj
     adam = [c for c in rec.calls if c[0] == "spn_adam_step"]
-    ok = (cfg.n_rays == 12 and len(adam) == 2 and abs(adam[0][1][10] - 0.5) < 1e-12           # grad_scale = 1 / world
+    ok = (bcast_ok and cfg.n_rays == 12 and len(adam) == 2 and abs(adam[0][1][10] - 0.5) < 1e-12           # grad_scale = 1 / world
           and float(tr.grads[0].min()) == float(tr.grads[0].max()) == 3.0                    # 1 + 2 summed over the ranks
           and float(tr.grads[1].min()) == float(tr.grads[1].max()) == 30.0 and tr.global_step == 1)
     np.save(out + f".{rank}.npy", np.array([int(ok)]))
