@@ -10,6 +10,9 @@ scene_io.load_scene (load_llff_data), resident ray pools + device-side sampling 
 (raypool, Trainer.step_from_pool), the step's three or four render calls as ONE chunk with analytic losses and the flat Adam
 (Trainer.step), the `--lpips` branch (Trainer.step_with_lpips), checkpoints in the reference's layout (Trainer.checkpoint:
 either trainer resumes the other's run), videos / test renders through render_path's asynchronous frame sink.
+Under torchrun (one process per GPU) N_rand stays the GLOBAL batch of the reference: every rank draws the same indices and
+renders its contiguous 1/W of each ray group, gradients are averaged over NVLink, videos are rendered frame-sharded; rank 0
+logs, checkpoints and writes files.
 Flags keep the reference's names and defaults (config_parser, run_nerf.py:740-925); flags outside this path
 (--sigma_loss, tcnn, blender / DTU data, object removal, ...) are rejected rather than ignored.
 """
@@ -67,6 +70,15 @@ def main(argv=None):
     sio, rp = importlib.import_module("spin-nerf_b200.scene_io"), importlib.import_module("spin-nerf_b200.raypool")
     lp = importlib.import_module("spin-nerf_b200.lpips_patch")
     trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    dist_mod = importlib.import_module("spin-nerf_b200.dist")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not args.dry_run:
+        torch.cuda.set_device(local)
+        args.device = f"cuda:{local}"
+        dist_mod.init_from_env()
+    __import__("random").seed(0); np.random.seed(0)          # every rank must draw the same LPIPS views / patch origins
+    say = print if rank == 0 else (lambda *a, **k: None)
 
     # ---- data (run_nerf.py:978-1012, 1225-1329)
     images, poses, bds, render_poses, i_test, masks, depths, mask_indices = sio.load_scene(
@@ -92,7 +104,7 @@ def main(argv=None):
     with open(os.path.join(logdir, 'args.txt'), 'w') as f:                                     # run_nerf.py:1133-1137
         for arg in sorted(vars(args)):
             f.write('{} = {}\n'.format(arg, getattr(args, arg)))
-    print(f"{len(images)} views {hwf[0]}x{hwf[1]}, near/far {near:.3f}/{far:.3f}, pool {len(pools.label)} rays (unmasked "
+    say(f"{len(images)} views {hwf[0]}x{hwf[1]}, near/far {near:.3f}/{far:.3f}, pool {len(pools.label)} rays (unmasked "
           f"{len(pools.idx_clf)}, masked {len(pools.idx_rgb)}, inpainted {len(pools.idx_inp)})"
           + (f", {depth_pool[1].shape[0]} sparse-depth rays" if depth_pool is not None else ""))
     if args.dry_run:
@@ -108,11 +120,13 @@ def main(argv=None):
         nets.append(net)
     tr = trainer_mod.Trainer(nets[0], nets[1], lr=args.lrate, lrate_decay=args.lrate_decay, N_samples=args.N_samples,
                              N_importance=args.N_importance, lindisp=args.lindisp, white_bkgd=args.white_bkgd,
-                             perturb=args.perturb, raw_noise_std=args.raw_noise_std, near=near, far=far, ndc=not args.no_ndc, hwf=hwf)
+                             perturb=args.perturb, raw_noise_std=args.raw_noise_std, near=near, far=far, ndc=not args.no_ndc, hwf=hwf,
+                             sharder=trainer_mod.RaySharder(rank, world))
+    dist_mod.broadcast_parameters(nets)                      # torch's default init differs per process
     ckpts = [args.ft_path] if args.ft_path not in (None, 'None') else \
         [os.path.join(logdir, f) for f in sorted(os.listdir(logdir)) if 'tar' in f]
     if ckpts and not args.no_reload:
-        print('Reloading from', ckpts[-1])
+        say('Reloading from', ckpts[-1])
         tr.load_checkpoint(torch.load(ckpts[-1], map_location=dev, weights_only=False))
     start = tr.global_step
     test_kw = dict(network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=args.N_samples,
@@ -120,8 +134,13 @@ def main(argv=None):
                    use_viewdirs=True, ndc=not args.no_ndc, near=near, far=far)
 
     def video(tag, poses_, savedir=None, gt=None):
-        rgbs, disps, _ = spn.render_path(poses_, list(hwf), args.chunk, test_kw, gt_imgs=gt, savedir=savedir,
-                                         render_factor=args.render_factor, need_alpha=True)
+        if world > 1:        # frames dealt round-robin to the ranks, gathered over NVLink, handed to rank 0 (no per-frame dumps)
+            rgbs, disps = spn.render_path_sharded(poses_, list(hwf), args.chunk, test_kw, render_factor=args.render_factor, dst=0)
+            if rank != 0:
+                return None
+        else:
+            rgbs, disps, _ = spn.render_path(poses_, list(hwf), args.chunk, test_kw, gt_imgs=gt, savedir=savedir,
+                                             render_factor=args.render_factor, need_alpha=True)
         base = os.path.join(logdir, tag)
         spn.frame_io.write_video(base + 'rgb.mp4', rgbs)
         spn.frame_io.write_video(base + 'disp.mp4', disps / np.nanmax(disps))
@@ -131,7 +150,7 @@ def main(argv=None):
         out = os.path.join(logdir, 'renderonly_path_{:06d}'.format(start))
         os.makedirs(out, exist_ok=True)
         video(os.path.basename(out) + '_', render_poses, savedir=out)
-        print('Done rendering', out)
+        say('Done rendering', out)
         return 0
 
     # ---- optimisation loop (run_nerf.py:1360-1703)
@@ -146,11 +165,12 @@ def main(argv=None):
         lpips_fn = lpips_mod.LPIPS(net='vgg').to(dev)
     poses_t = torch.from_numpy(np.ascontiguousarray(poses[:, :3, :4])).float()
     t0, rays_done = time.perf_counter(), 0
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + start)    # same stream on every rank: the trainer shards the draw
     for i in range(start + 1, args.N_iters + 1):
-        idx = rp.draw_step_indices(dev_pools, args.N_rand)
+        idx = rp.draw_step_indices(dev_pools, args.N_rand, generator=gen)
         kw = {}
         if dpool is not None:
-            di = torch.randint(0, dpool[1].numel(), (args.N_rand,), device=dev)
+            di = torch.randint(0, dpool[1].numel(), (args.N_rand,), device=dev, generator=gen)
             kw = dict(rays_depth=dpool[0][:, di], target_depth=dpool[1][di], depth_lambda=args.depth_lambda)
         if kw or (sampler is not None and i > args.lpips_from):
             batch = (dev_pools["pool_od"][:, idx[0]], dev_pools["rgb"][idx[0]], dev_pools["pool_od"][:, idx[1]],
@@ -165,20 +185,23 @@ def main(argv=None):
         else:
             loss, psnr = tr.step_from_pool(dev_pools["pool_od"], dev_pools["rgb"], dev_pools["disp"], idx)
         rays_done += (4 if kw else 3) * args.N_rand
-        if i % args.i_weights == 0:
+        if i % args.i_weights == 0 and rank == 0:
             path = os.path.join(logdir, '{:06d}.tar'.format(i))
             torch.save(tr.checkpoint(), path)
             print('Saved checkpoints at', path)
         if args.i_video > 0 and i % args.i_video == 0:
             video('{}_{:06d}_'.format(args.expname, i), render_poses)
-        if i % args.i_testset == 0 and len(i_test) > 0:
+        if i % args.i_testset == 0 and len(i_test) > 0 and rank == 0:
             out = os.path.join(logdir, 'testset_{:06d}'.format(i))
             os.makedirs(out, exist_ok=True)
             spn.render_path(poses[i_test], list(hwf), args.chunk, test_kw, gt_imgs=images[i_test], savedir=out,
                             render_factor=args.render_factor)
-        if i % args.i_print == 0:
+        if i % args.i_print == 0 and rank == 0:
             print(f"[TRAIN] Iter: {i} Loss: {float(loss)}  PSNR: {float(psnr)}  "
                   f"({rays_done / (time.perf_counter() - t0) / 1e3:.0f} k rays/s wall clock)")
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return 0
 
 
