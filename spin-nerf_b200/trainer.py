@@ -36,7 +36,7 @@ class BufferPool:
 class Trainer:
     def __init__(self, net_c, net_f, lr=5e-4, lrate_decay=250, N_samples=64, N_importance=64, lindisp=True,
                  white_bkgd=True, perturb=1.0, raw_noise_std=1.0, near=1.2, far=8.0, ndc=False, hwf=None,
-                 process_group=None, sharder=None, betas=(0.9, 0.999), eps=1e-8):
+                 process_group=None, sharder=None, betas=(0.9, 0.999), eps=1e-8, seed=None):
         self.net_c, self.net_f = net_c, net_f
         self.lr0, self.lrate_decay = float(lr), lrate_decay
         self.betas, self.eps = betas, eps
@@ -66,10 +66,27 @@ class Trainer:
         self.pools = [BufferPool(dev)] * 3      # each render is consumed (backward) before the next starts
         self.shared = BufferPool(dev)
         self.adam_state = None                  # device-resident {step, lr/bc1, sqrt(bc2), lr}: CUDA-graph mode
+        # seed: a private random stream for the jitter / resampling / density noise.  With it, a W-rank run consumes the
+        # stream of the single-process run: every rank draws the step's GLOBAL random tensors and keeps the rows of its rays
+        # (SURVEY.md section 8e "the union of shards equals the single-GPU stream"), so the two runs differ only by the
+        # summation order of the gradient all-reduce.  None: torch's default generator, one local draw per rank.
+        self.gen = None
+        if seed is not None:
+            self.gen = torch.Generator(device=dev)
+            self.gen.manual_seed(int(seed))
         self._graph = None
 
     # ---------------------------------------------------------------------------------------
-    def _forward(self, idx, rays_od, detach_weights, rb=None, test_kwargs=False):
+    def _global_rows(self, sizes_global):
+        """Row ids, in the single-process chunk [group 1 | group 2 | ...] of the GLOBAL batch, of this rank's rays."""
+        rows, off = [], 0
+        for n in sizes_global:
+            lo, hi = self.sharder.bounds(int(n))
+            rows.append(torch.arange(off + lo, off + hi, device=self.device))
+            off += int(n)
+        return torch.cat(rows), off
+
+    def _forward(self, idx, rays_od, detach_weights, rb=None, test_kwargs=False, sizes_global=None):
         """rays_od [2,n,3] (origin, direction) or a ready ray matrix rb [n,11] -> chunk state; random draws made on
         the device.  test_kwargs: render like render_kwargs_test (perturb=False, raw_noise_std=0, run_nerf.py:485-488)."""
         if rb is None:
@@ -82,12 +99,19 @@ class Trainer:
         if test_kwargs:
             opts.update(perturb=False, raw_noise_std=0.0)
         t_rand = u = n0 = n1 = None
+        if self.gen is None:
+            draw = lambda fn, cols: fn(n, cols, device=self.device)
+        elif self.sharder.world == 1 or sizes_global is None:
+            draw = lambda fn, cols: fn(n, cols, device=self.device, generator=self.gen)
+        else:
+            rows, n_global = self._global_rows(sizes_global)
+            draw = lambda fn, cols: fn(n_global, cols, device=self.device, generator=self.gen)[rows]
         if opts["perturb"]:
-            t_rand = torch.rand(n, S, device=self.device)
-            u = torch.rand(n, NI, device=self.device) if NI else None
+            t_rand = draw(torch.rand, S)
+            u = draw(torch.rand, NI) if NI else None
         if opts["raw_noise_std"] > 0:
-            n0 = torch.randn(n, S, device=self.device)
-            n1 = torch.randn(n, S + NI, device=self.device) if NI else None
+            n0 = draw(torch.randn, S)
+            n1 = draw(torch.randn, S + NI) if NI else None
         return chunk_forward(opts, rb, self.net_c, self.net_f, t_rand, u, n0, n1, train=True, pool=self.pools[idx])
 
     def step(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp, rays_depth=None, target_depth=None,
@@ -105,6 +129,7 @@ class Trainer:
         (run_nerf.py:1400-1413, 1475-1477, 1491-1506: rays through COLMAP's sparse points, loss += depth_lambda *
         img2mse(depth_map, target_depth)); they ride in the same chunk as a fourth ray range."""
         sh = self.sharder
+        sizes_global = [rays_clf.shape[1], rays_s.shape[1], rays_inp.shape[1]] + ([rays_depth.shape[1]] if rays_depth is not None else [])
         rays_clf, target_clf = sh.shard(rays_clf, 1), sh.shard(target_clf)
         rays_s, target_s = sh.shard(rays_s, 1), sh.shard(target_s)
         rays_inp, depth_inp = sh.shard(rays_inp, 1), sh.shard(depth_inp)
@@ -124,7 +149,7 @@ class Trainer:
         torch.cat(groups, 1, out=rays)
         tgt_rgb = P("tgt_rgb", (n1 + n2, 3), torch.float32)
         torch.cat([target_clf, target_s], 0, out=tgt_rgb)
-        cfg, k = self._forward(0, rays, False)
+        cfg, k = self._forward(0, rays, False, sizes_global=sizes_global)
         return self._finish_step(cfg, k, tgt_rgb, L.f32(depth_inp), n1, n2, n3, _apply, n4, target_depth, depth_lambda)
 
     def step_from_pool(self, pool_od, rgb_pool, disp_pool, idx, _apply=True):
@@ -145,7 +170,7 @@ class Trainer:
                                              int(self.ndc), int(H), int(W), float(f), L.ptr(rb), L.ptr(rgb_pool),
                                              L.ptr(tgt_rgb), 2 * m, L.ptr(disp_pool), L.ptr(tgt_disp), L.stream()),
                 "spn_gather_ray_batch")
-        cfg, k = self._forward(0, None, False, rb=rb)
+        cfg, k = self._forward(0, None, False, rb=rb, sizes_global=[idx.shape[1]] * 3)
         return self._finish_step(cfg, k, tgt_rgb, tgt_disp, m, m, m, _apply)
 
     def _finish_step(self, cfg, k, tgt_rgb, depth_inp, n1, n2, n3, apply=True, n4=0, target_depth=None, depth_lambda=0.1):

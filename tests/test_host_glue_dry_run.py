@@ -163,3 +163,35 @@ def test_step_with_sparse_depth_group(rec):
     assert loss.shape == ()
     with pytest.raises(RuntimeError):
         tr.step(*_batch(8), rays_depth=torch.rand(2, 5, 3), target_depth=torch.rand(4))
+
+
+def test_seeded_ranks_consume_the_single_process_random_stream(rec, monkeypatch):
+    """Trainer(seed=...): the jitter / resampling / noise tensors of a 2-rank run are the rows of the single-process run's
+    tensors that belong to each rank's rays (three ray groups, each split contiguously), so multi-GPU training differs from
+    single-GPU training only by the gradient all-reduce's summation order."""
+    seen = {}
+    real = trainer_mod.chunk_forward
+
+    def spy(tag):
+        def f(opts, rays, net_c, net_f, t_rand=None, u=None, noise0=None, noise1=None, train=False, pool=None):
+            seen[tag] = [t.clone() for t in (t_rand, u, noise0, noise1)]
+            return real(opts, rays, net_c, net_f, t_rand, u, noise0, noise1, train, pool)
+        return f
+    batch = _batch(8)
+
+    def run(tag, rank, world, from_pool):
+        nets = [spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True).seeded_init_(s)
+                for s in (1, 2)]
+        tr = trainer_mod.Trainer(nets[0], nets[1], hwf=(24, 32, 28.8), sharder=trainer_mod.RaySharder(rank, world), seed=7)
+        tr.apply_gradients = lambda: None
+        monkeypatch.setattr(trainer_mod, "chunk_forward", spy(tag))
+        if from_pool:
+            tr.step_from_pool(torch.rand(2, 50, 3), torch.rand(50, 3), torch.rand(50), torch.randint(0, 50, (3, 8)))
+        else:
+            tr.step(*batch)
+    for from_pool in (False, True):
+        run("one", 0, 1, from_pool); run("r0", 0, 2, from_pool); run("r1", 1, 2, from_pool)
+        rows = lambda r: torch.cat([torch.arange(8 * g + 4 * r, 8 * g + 4 * r + 4) for g in range(3)])
+        for t_one, t0, t1 in zip(seen["one"], seen["r0"], seen["r1"]):
+            assert t_one.shape[0] == 24 and t0.shape[0] == t1.shape[0] == 12
+            assert torch.equal(t0, t_one[rows(0)]) and torch.equal(t1, t_one[rows(1)])

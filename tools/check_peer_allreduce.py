@@ -4,7 +4,9 @@ one box under a short timeout (the kernels trap after ~4 s without a peer, so a 
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \\
         tools/check_peer_allreduce.py
 
-Each rank runs the same 4 ray-sharded train steps twice from identical weights — once ending in NCCL all-reduce + flat Adam,
+First (NCCL path only) the W-rank run is compared with a single-process run on the full batches: with Trainer(seed=...) the
+ranks consume the single-process random stream, so the parameter trajectories must agree up to summation order.  Then each
+rank runs the same 4 ray-sharded train steps twice from identical weights — once ending in NCCL all-reduce + flat Adam,
 once in the fused peer-memory kernels — and compares the two parameter trajectories (fp32 sums in a different order:
 |delta| <= 1e-6 + 1e-3 * lr) and, for the peer path, that all ranks hold bit-identical replicas afterwards."""
 import importlib
@@ -51,6 +53,21 @@ def main():
                 ref = p.clone(); dist.broadcast(ref, 0)
                 assert torch.equal(ref, p), "replicas diverged"
             tr.peer.close()
+    # ---- sharded == single process: with Trainer(seed=...) every rank consumes the single-process random stream, so W ranks on
+    # 1/W of the rays each must walk the trajectory of one process on all rays (stochastic sampling and density noise ON)
+    os.environ["SPN_P2P_ALLREDUCE"] = "0"
+    traj = {}
+    for mode, shard in (("sharded", trainer_mod.RaySharder(rank, world)), ("single", trainer_mod.RaySharder(0, 1))):
+        nets = [spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True).seeded_init_(s).to(dev)
+                for s in (1, 2)]
+        tr = trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, perturb=1.0, raw_noise_std=1.0, near=1.2, far=8.0, sharder=shard, seed=5)
+        for b in steps:
+            tr.step(*b)
+        torch.cuda.synchronize()
+        traj[mode] = (nets[0].flat_params().clone(), nets[1].flat_params().clone())
+    for a, b in zip(traj["sharded"], traj["single"]):
+        d = float((a - b).abs().max())
+        assert d <= 1e-6 + 0.2 * 5e-4, ("sharded vs single-process parameters", d)     # 4 Adam steps of <= lr each; sums reorder
     for a, b in zip(results["nccl"][1:], results["peer"][1:]):
         d = float((a - b).abs().max())
         assert d <= 1e-6 + 1e-3 * 5e-4, d
