@@ -115,6 +115,12 @@ int spn_sample_pdf_cdf(const float* bins, const float* weights, const float* u, 
                        float* samples, int64_t* inds, float* cdf_out, void* stream);
 /* out[n,sa+sb] = sort(cat(a[n,sa], b[n,sb])) (b is unsorted when u is random: warp bitonic sort). */
 int spn_merge_sorted(const float* a, const float* b, int n, int sa, int sb, float* out, void* stream);
+/* Batched row-wise searchsorted with numpy semantics — the function of the reference's only native component
+ * (DS_NeRF/torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu:83-142; wrapper src/torchsearchsorted/searchsorted.py:20-53),
+ * which its hot path does not call (run_nerf_helpers.py:10 imports torch.searchsorted).  a [nrow_a, ncol_a] sorted rows,
+ * v [nrow_v, ncol_v] queries, out [max(nrow_a, nrow_v), ncol_v] int64; nrow_a == nrow_v or one of them 1. */
+int spn_searchsorted(const float* a, const float* v, int64_t* out, int nrow_a, int nrow_v, int ncol_a, int ncol_v,
+                     int side_left, void* stream);
 /* render_rays' whole resampling block (run_nerf.py:696-702,726) in one launch:
  * mids -> sample_pdf(mids, weights[:,1:-1]) -> merge with z -> population std of the samples. */
 int spn_resample(const float* z, const float* weights, const float* u, int n, int S, int n_imp,

@@ -57,6 +57,7 @@ _SIGS = {
     "spn_raw2outputs_bwd": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int] + [c_fp] * 7),
     "spn_sample_pdf": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp]),
     "spn_sample_pdf_cdf": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp]),
+    "spn_searchsorted": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "spn_merge_sorted": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "spn_resample": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "spn_mlp_param_offsets": (C.c_int, [C.POINTER(C.c_int64)]),

@@ -504,6 +504,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+// Batched row-wise searchsorted, the function of the reference's one native component (DS_NeRF/torchsearchsorted/src/cuda/
+// searchsorted_cuda_kernel.cu:41-107, dead code on its hot path: run_nerf_helpers.py:10 uses torch.searchsorted).  One thread
+// per query; numpy semantics like its unit test demands (test/test_searchsorted.py): left -> first i with a[i] >= v,
+// right -> first i with a[i] > v.  Either operand may have a single row that is shared by all rows of the other.
+__global__ void searchsorted_kernel(const float* __restrict__ a, const float* __restrict__ v, int64_t* __restrict__ out,
+                                    int nrow_a, int nrow_v, int ncol_a, int ncol_v, int side_left) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nrow = nrow_a > nrow_v ? nrow_a : nrow_v;
+  if (q >= (int64_t)nrow * ncol_v) return;
+  const int row = (int)(q / ncol_v), col = (int)(q % ncol_v);
+  const float* ar = a + (int64_t)(nrow_a == 1 ? 0 : row) * ncol_a;
+  const float x = v[(int64_t)(nrow_v == 1 ? 0 : row) * ncol_v + col];
+  int lo = 0, hi = ncol_a;                       // invariant: answer in [lo, hi]
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const float m = ar[mid];
+    if (side_left ? (m < x) : (m <= x)) lo = mid + 1; else hi = mid;
+  }
+  out[q] = lo;
+}
+
 // Adam with the step counter and schedule resident on the device, so a whole train step can be replayed as a CUDA graph:
 // state = {step, lr / bias_correction1, sqrt(bias_correction2), lr}; adam_tick advances it once per step.
 __global__ void adam_tick_kernel(float* __restrict__ state, float lr0, float decay_base, float decay_steps, float b1,
@@ -666,6 +687,18 @@ extern "C" int spn_sample_pdf_cdf(const float* bins, const float* weights, const
 extern "C" int spn_sample_pdf(const float* bins, const float* weights, const float* u, int n, int nb, int ns,
                               float* samples, int64_t* inds, void* stream) {
   return spn_sample_pdf_cdf(bins, weights, u, n, nb, ns, samples, inds, nullptr, stream);
+}
+
+extern "C" int spn_searchsorted(const float* a, const float* v, int64_t* out, int nrow_a, int nrow_v, int ncol_a, int ncol_v,
+                                int side_left, void* stream) {
+  SPN_CHECK_ARG(a && v && out && nrow_a >= 1 && nrow_v >= 1 && ncol_a >= 0 && ncol_v >= 0 &&
+                (nrow_a == nrow_v || nrow_a == 1 || nrow_v == 1), "spn_searchsorted: bad shapes (%d x %d, %d x %d)", nrow_a,
+                ncol_a, nrow_v, ncol_v);
+  const int64_t work = (int64_t)(nrow_a > nrow_v ? nrow_a : nrow_v) * ncol_v;
+  if (work == 0) return SPN_OK;
+  searchsorted_kernel<<<blocks_for(work, 256), 256, 0, as_stream(stream)>>>(a, v, out, nrow_a, nrow_v, ncol_a, ncol_v, side_left);
+  SPN_LAUNCH_CHECK("searchsorted_kernel");
+  return SPN_OK;
 }
 
 extern "C" int spn_merge_sorted(const float* a, const float* b, int n, int sa, int sb, float* out, void* stream) {

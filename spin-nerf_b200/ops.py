@@ -149,6 +149,26 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False, u=None, return
     return samples
 
 
+def searchsorted(a, v, out=None, side='left'):
+    """torchsearchsorted.searchsorted (DS_NeRF/torchsearchsorted/src/torchsearchsorted/searchsorted.py:20-53): row-wise
+    np.searchsorted of v [Bv,V] in the sorted rows of a [Ba,A] (Ba == Bv or one of them 1) -> int64 [max(Ba,Bv), V]."""
+    assert len(a.shape) == 2, "input `a` must be 2-D."
+    assert len(v.shape) == 2, "input `v` must be 2-D."
+    assert a.shape[0] == v.shape[0] or a.shape[0] == 1 or v.shape[0] == 1, \
+        "`a` and `v` must have the same number of rows or one of them must have only one"
+    assert a.device == v.device, '`a` and `v` must be on the same device'
+    shape = (max(a.shape[0], v.shape[0]), v.shape[1])
+    if out is not None:
+        assert out.device == a.device and out.dtype == torch.long and tuple(out.shape) == shape, \
+            "`out` must be a torch.long tensor of the result shape on the device of `a`"
+    else:
+        out = torch.empty(shape, device=v.device, dtype=torch.long)
+    af, vf = f32(a), f32(v)
+    check(lib().spn_searchsorted(ptr(af), ptr(vf), ptr(out), a.shape[0], v.shape[0], a.shape[1], v.shape[1],
+                                 1 if side == 'left' else 0, stream()), "spn_searchsorted")
+    return out
+
+
 def merge_sorted(a, b):
     """sort(cat([a, b], -1)) values (run_nerf.py:702)."""
     a = f32(a); b = f32(b)

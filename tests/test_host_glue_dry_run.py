@@ -195,3 +195,16 @@ def test_seeded_ranks_consume_the_single_process_random_stream(rec, monkeypatch)
         for t_one, t0, t1 in zip(seen["one"], seen["r0"], seen["r1"]):
             assert t_one.shape[0] == 24 and t0.shape[0] == t1.shape[0] == 12
             assert torch.equal(t0, t_one[rows(0)]) and torch.equal(t1, t_one[rows(1)])
+
+
+def test_searchsorted_wrapper_validates_like_the_references(rec):
+    """ops.searchsorted keeps the argument checks of torchsearchsorted's Python wrapper (searchsorted.py:23-40)."""
+    a, v = torch.sort(torch.rand(4, 9), 1)[0], torch.rand(4, 5)
+    out = ops.searchsorted(a, v, side='right')
+    assert out.dtype == torch.long and tuple(out.shape) == (4, 5)
+    assert rec.calls[-1][0] == "spn_searchsorted" and rec.calls[-1][1][3:8] == (4, 4, 9, 5, 0)
+    assert tuple(ops.searchsorted(a[:1], v).shape) == (4, 5) and tuple(ops.searchsorted(a, v[:1]).shape) == (4, 5)
+    for bad in (lambda: ops.searchsorted(a[0], v), lambda: ops.searchsorted(a, v[0]), lambda: ops.searchsorted(a[:3], v),
+                lambda: ops.searchsorted(a, v, out=torch.empty(4, 5)), lambda: ops.searchsorted(a, v, out=torch.empty(3, 5, dtype=torch.long))):
+        with pytest.raises(AssertionError):
+            bad()

@@ -206,6 +206,32 @@ def test_trainer_step_with_sparse_depth_rays_matches_reference_fp32():
             assert np.mean(err > tol) <= 0.03, (nm, k, err.max())
 
 
+def test_searchsorted_matches_numpy_on_the_references_grid():
+    """The reference's only unit test (DS_NeRF/torchsearchsorted/test/test_searchsorted.py:9-44): row-wise np.searchsorted is
+    the oracle, over its parameter grid (Ba, Bv in {1,100,200}, A in {1,50,500}, V in {1,12,120}, both sides), integer-exact."""
+    from itertools import product
+    rng = np.random.default_rng(0)
+    for Ba, Bv, A, V, side in product([1, 100, 200], [1, 100, 200], [1, 50, 500], [1, 12, 120], ['left', 'right']):
+        if Ba > 1 and Bv > 1 and Ba != Bv:
+            continue
+        for rep in range(3):
+            a = np.sort(rng.uniform(0, 1, (Ba, A)).astype(np.float32), axis=1)
+            v = rng.uniform(0, 1, (Bv, V)).astype(np.float32)
+            if rep == 2 and A > 1:
+                v[:, ::2] = a[:, rng.integers(0, A, v[:, ::2].shape[1])][:Bv] if Ba >= Bv else a[0, rng.integers(0, A, v[:, ::2].shape)]   # exact ties
+            nrow = max(Ba, Bv)
+            want = np.stack([np.searchsorted(a[0 if Ba == 1 else r], v[0 if Bv == 1 else r], side=side) for r in range(nrow)], 0)
+            got = spn.ops.searchsorted(T(a), T(v), side=side)
+            assert got.dtype == torch.long and tuple(got.shape) == (nrow, V)
+            np.testing.assert_array_equal(N(got), want)
+    out = torch.empty((100, 12), dtype=torch.long, device=DEV)          # caller-provided output (test_searchsorted_output_dtype)
+    a = torch.sort(torch.rand(100, 50, device=DEV), dim=1)[0]; v = torch.rand(100, 12, device=DEV)
+    assert spn.ops.searchsorted(a, v, out) is out
+    np.testing.assert_array_equal(N(out), np.stack([np.searchsorted(N(a)[r], N(v)[r]) for r in range(100)], 0))
+    with pytest.raises(AssertionError):
+        spn.ops.searchsorted(torch.zeros(3, 4, device=DEV), torch.zeros(2, 4, device=DEV))
+
+
 def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
     a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
     err = np.abs(a - b); tol = atol + rtol * np.abs(b)
