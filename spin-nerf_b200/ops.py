@@ -163,7 +163,10 @@ def searchsorted(a, v, out=None, side='left'):
             "`out` must be a torch.long tensor of the result shape on the device of `a`"
     else:
         out = torch.empty(shape, device=v.device, dtype=torch.long)
-    af, vf = f32(a), f32(v)
+    if a.dtype != torch.float32 or v.dtype != torch.float32:
+        raise NotImplementedError("spinnerf_b200.searchsorted is built for float32 (the dtype of the render path); a silent "
+                                  "cast could reorder ties")
+    af, vf = a.contiguous(), v.contiguous()
     check(lib().spn_searchsorted(ptr(af), ptr(vf), ptr(out), a.shape[0], v.shape[0], a.shape[1], v.shape[1],
                                  1 if side == 'left' else 0, stream()), "spn_searchsorted")
     return out
