@@ -205,12 +205,17 @@ def workload_config(n_gpus, n_rand):
 # ------------------------------------------------------------------------------------------------
 # the other two GPU configurations of BASELINE.json (not the headline line; same JSON contract)
 # ------------------------------------------------------------------------------------------------
+def _device(local):
+    import torch
+    return torch.device("cuda", local)
+
+
 def _init_dist():
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = _device(local)
     if world > 1:
         import datetime
         import torch.distributed as dist
@@ -443,7 +448,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = _device(local)
     if world > 1:
         import datetime
         import torch.distributed as dist
@@ -624,7 +629,7 @@ def main():
             gpu_port = {"error": f"{type(e).__name__}: {e}"[:300]}
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
-        phase("cpu_baseline sample (oracle port on the host cores)")
+        phase("cpu_baseline sample (PyTorch restatement of the reference step on the host cores)")
         t0 = time.perf_counter()
         try:
             cores = cpu_threads_best()
