@@ -33,7 +33,7 @@ int sm_count() {
   return n;
 }
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 // ---- in-library kernel timing (bench.py's roofline leg): cudaEvent pairs on the launching stream ----
 namespace {
@@ -87,9 +87,7 @@ extern "C" int spn_profile_read(int kind, int* launches, float* total_ms) {
 }
 
 extern "C" long long spn_launch_count(int reset) {
-  long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 extern "C" int spn_version(void) { return SPN_VERSION; }

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/spinnerf_b200.h"
 
 namespace spn {
@@ -34,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return spn::cuda_fail(e__, name);        \
   } while (0)
 
-extern long long g_launches;   // kernels launched by this library (spn_launch_count)
+extern std::atomic<long long> g_launches;   // kernels launched by this library (spn_launch_count); host threads may launch concurrently
 
 // optional in-library CUDA-event timing of the dominant kernels, on the launching stream
 enum ProfKind : int { PROF_MLP_FWD = 0, PROF_MLP_DGRAD = 1, PROF_MLP_WGRAD = 2, PROF_KINDS = 3 };
