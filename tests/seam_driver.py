@@ -21,6 +21,7 @@ import test_host_glue_dry_run as dry            # noqa: E402
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     every = sys.argv[2] if len(sys.argv) > 2 else "100000"      # i_video / i_testset / i_weights period
+    extra = sys.argv[3:]                                        # further reference flags, e.g. --lpips
     rec = dry.Recorder()
     for m in (dry.L, dry.ops, dry.render_mod):
         m.lib = (lambda rec=rec: rec); m.ptr = dry._ptr; m.stream = (lambda: 0)
@@ -42,7 +43,7 @@ def main():
                 "--dataset_type", "llff", "--factor", "2", "--N_rand", "32", "--N_samples", "8", "--N_importance", "8",
                 "--use_viewdirs", "--raw_noise_std", "1.0", "--no_ndc", "--lindisp", "--white_bkgd", "--no_tcnn", "--N_gt", "0",
                 "--N_iters", str(iters), "--i_video", every, "--i_testset", every, "--i_weights", every,
-                "--i_feat", "100000", "--i_print", "1", "--chunk", "512", "--netchunk", "4096"]
+                "--i_feat", "100000", "--i_print", "1", "--chunk", "512", "--netchunk", "4096"] + extra
     import run_nerf
     helpers = sys.modules["run_nerf_helpers"]
     torch.autograd.set_detect_anomaly(False)                # values are garbage here; anomaly mode would trip on NaNs

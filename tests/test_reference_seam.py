@@ -54,3 +54,28 @@ def test_unmodified_reference_trainer_checkpoints_and_videos_over_the_dropin():
         assert len(keys) == 24 and "pts_linears.5.weight" in keys and "views_linears.0.bias" in keys and "alpha_linear.weight" in keys
     n_get_rays = res["calls"].count("spn_get_rays")
     assert n_get_rays == 120 + 1 + 1           # the spiral video, the held-out video frame, the test-set frame
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/DS_NeRF/run_nerf.py"), reason="reference checkout not present")
+@pytest.mark.timeout(900)
+def test_unmodified_reference_trainer_lpips_branch_over_the_dropin():
+    """`--lpips` for 305 iterations: the reference's perceptual-loss branch (run_nerf.py:1523-1561, iterations > 300: its own
+    render_path with patch windows over our get_rays / NeRF / raw2outputs / sample_pdf, the `lpips` import shim) on top of
+    the three render calls, differentiated by autograd through our backward ops."""
+    env = dict(os.environ, PYTHONSAFEPATH="1", OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "seam_driver.py"), "304", "100000", "--lpips"],
+                       capture_output=True, text=True, env=env, timeout=880)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1][5:])
+    calls = res["calls"]
+    lpips_iters = 4                                              # the loop runs i = 1 .. 304 (run_nerf.py:1359-1360); i > 300 -> 4
+    assert calls.count("spn_get_rays") == 4 * lpips_iters        # lpips_batch_size patches per iteration, rays from c2w
+    render = ["spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points", "spn_raw2outputs_fwd"]
+    plain_step = render * 3 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * 6
+    assert calls[:len(plain_step) * 300] == plain_step * 300
+    tail = calls[len(plain_step) * 300:]
+    # an LPIPS iteration: the step's three calls, per patch rays + one render, then backward: the step's six (coarse + fine of
+    # three calls) and ONE per patch — weights are detached and z_samples carry no gradient, so only the fine network of a
+    # patch is differentiated (run_nerf.py:1541-1549)
+    lpips_step = render * 3 + (["spn_get_rays"] + render) * 4 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * (6 + 4)
+    assert tail == lpips_step * lpips_iters
