@@ -31,7 +31,12 @@ def main():
     dry.nerf_mod.NeRF._sync = lambda self: (self.flat_params(), torch.zeros(64, dtype=torch.uint8))
     sio = importlib.import_module("spin-nerf_b200.scene_io")
     scene = tempfile.mkdtemp(prefix="spn_scene_")
-    sio.synthetic_scene(scene, n_views=8, hw=(24, 32), factor=2, seed=0, n_unlabelled=1)
+    info = sio.synthetic_scene(scene, n_views=8, hw=(24, 32), factor=2, seed=0, n_unlabelled=1)
+    if "--colmap_depth" in extra:       # a COLMAP sparse model for load_colmap_depth (load_llff.py:448-501)
+        import numpy as np
+        rng = np.random.default_rng(0)
+        pts = np.stack([rng.uniform(-1, 1, 80), rng.uniform(-1, 1, 80), rng.uniform(-6, -2.5, 80)], 1)
+        sio.write_colmap_model(scene, info["c2w"], info["focal"], (48, 64), pts, rng.uniform(0.2, 2.0, 80), rng)
     work = tempfile.mkdtemp(prefix="spn_work_")
     os.chdir(work)
     os.makedirs("lama/LaMa_test_images", exist_ok=True)

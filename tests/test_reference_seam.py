@@ -79,3 +79,18 @@ def test_unmodified_reference_trainer_lpips_branch_over_the_dropin():
     # patch is differentiated (run_nerf.py:1541-1549)
     lpips_step = render * 3 + (["spn_get_rays"] + render) * 4 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * (6 + 4)
     assert tail == lpips_step * lpips_iters
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/DS_NeRF/run_nerf.py"), reason="reference checkout not present")
+@pytest.mark.timeout(600)
+def test_unmodified_reference_trainer_sparse_depth_step_over_the_dropin():
+    """`--colmap_depth --depth_loss` (the shipped config): the reference's own load_colmap_depth reads the COLMAP model that
+    scene_io.write_colmap_model wrote, its train step makes FOUR render calls, and the depth term differentiates only the fine
+    network of the fourth (7 backward pairs) — what Trainer.step's fourth ray group reproduces in one chunk."""
+    env = dict(os.environ, PYTHONSAFEPATH="1", OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "seam_driver.py"), "2", "100000", "--colmap_depth", "--depth_loss"],
+                       capture_output=True, text=True, env=env, timeout=580)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1][5:])
+    render = ["spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points", "spn_raw2outputs_fwd"]
+    assert res["calls"] == (render * 4 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * 7) * 2
