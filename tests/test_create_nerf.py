@@ -185,3 +185,35 @@ def test_need_alpha_without_fine_pass_fails_like_the_reference():
         spn.render_rays(torch.zeros(4, 11), net, None, 64, N_importance=0, need_alpha=True)
     with pytest.raises(NotImplementedError):
         spn.render_rays(torch.zeros(4, 11), net, None, 64, N_importance=0, sigma_loss=object())
+
+
+@needs_ref
+def test_dropin_host_helpers_equal_the_references():
+    """The drop-in module's host-side helpers (numpy ray generation used to precompute the training rays, the loss lambdas)
+    against the reference module's, bit for bit."""
+    import sys
+    H, _ = ref_loader.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "spin-nerf_b200", "dropin"))
+    try:
+        sys.modules.pop("run_nerf_helpers", None)
+        D = importlib.import_module("run_nerf_helpers")
+    finally:
+        sys.path.pop(0); sys.modules.pop("run_nerf_helpers", None)
+    assert D.__file__.endswith(os.path.join("dropin", "run_nerf_helpers.py"))
+    rng = np.random.default_rng(0)
+    c2w = rng.standard_normal((3, 4)).astype(np.float32)
+    for a, b in zip(D.get_rays_np(13, 17, 15.5, c2w), H.get_rays_np(13, 17, 15.5, c2w)):
+        np.testing.assert_array_equal(a, b)
+    coords = rng.uniform(0, 16, (40, 2))
+    for a, b in zip(D.get_rays_by_coord_np(13, 17, 15.5, c2w, coords), H.get_rays_by_coord_np(13, 17, 15.5, c2w, coords)):
+        np.testing.assert_array_equal(a, b)
+    x, y = torch.rand(7, 3), torch.rand(7, 3)
+    assert torch.equal(D.img2mse(x, y), H.img2mse(x, y)) and torch.equal(D.img2l1(x, y), H.img2l1(x, y))
+    assert torch.equal(D.mse2psnr(D.img2mse(x, y)), H.mse2psnr(H.img2mse(x, y)))
+    img = rng.uniform(-0.2, 1.2, (5, 6, 3))
+    np.testing.assert_array_equal(D.to8b(img), H.to8b(img))
+    e, d = D.get_embedder(10, 0)
+    assert d == H.get_embedder(10, 0)[1] == 63 and D.get_embedder(4, 0)[1] == H.get_embedder(4, 0)[1] == 27
+    ident, d3 = D.get_embedder(10, -1)
+    assert d3 == 3 and isinstance(ident, torch.nn.Identity)
