@@ -168,6 +168,29 @@ def gpu_reference_port(spn, dev, pool, rgb_pool, disp_pool, n_rand, steps=6, war
                     "torch.optim.Adam) on the same GPU and workload; device-timed", "final_loss": float(loss.detach())}
 
 
+def psnr_vs_reference_port(spn, dev, nets, pool, n_rays=512):
+    """The second half of BASELINE.json's metric ("PSNR vs ref"): this library's render (the benchmark's arithmetic mode) against
+    the reference's fp32 formulation (oracle/torch_port.py, TF32 off) on identical rays and the networks as the timed steps left
+    them, deterministic sampling (render_kwargs_test).  A checker leg: a failure costs only this key."""
+    import torch
+    from oracle import torch_port as TP
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    ix = torch.randint(0, pool.shape[1], (n_rays,), device=dev, generator=g)
+    rays = pool[:, ix].contiguous()
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, FOCAL, chunk=32768, rays=rays, use_viewdirs=True, ndc=False, near=NEAR, far=FAR,
+                                               network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=64,
+                                               N_importance=64, lindisp=True, white_bkgd=True, perturb=0., raw_noise_std=0.)
+        pc, pf = ({k: v.detach().clone().float() for k, v in n.state_dict().items()} for n in nets)
+        ref = TP.render_rays(rays[0], rays[1], NEAR, FAR, pc, pf, lindisp=True, white_bkgd=True)
+        mse = float(torch.mean((rgb - ref["rgb_map"]) ** 2))
+        mse0 = float(torch.mean((ex["rgb0"] - ref["rgb0"]) ** 2))
+    db = lambda m: float(-10.0 * np.log10(max(m, 1e-20)))
+    return {"rgb_db": db(mse), "rgb0_db": db(mse0), "rays": n_rays,
+            "checker": "oracle/torch_port.py: fp32 PyTorch render of the same rays with the same (trained) weights, TF32 off"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -620,6 +643,13 @@ def main():
                     "algorithmic_units": "wgrad: 76 x 16 KB stash/dstash atoms per 128-sample tile; fwd/dgrad: 1 186 816 / 1 115 392 FLOP per MLP evaluation",
                     "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
+    psnr = None
+    if world == 1:
+        phase("PSNR of the render against the fp32 reference formulation")
+        try:
+            psnr = psnr_vs_reference_port(spn, dev, nets, pool)
+        except Exception as e:
+            psnr = {"error": f"{type(e).__name__}: {e}"[:300]}
     gpu_port = None
     if not args.no_cpu_baseline and world == 1:
         phase("gpu_reference_port (PyTorch restatement of the reference step on this GPU)")
@@ -648,7 +678,7 @@ def main():
             "config": workload_config(world, n_rand), "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu, "gpu_reference_port": gpu_port, "n_rand_per_sec": value / RENDERS_PER_STEP,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_reference_port": gpu_port, "psnr_vs_ref": psnr, "n_rand_per_sec": value / RENDERS_PER_STEP,
             "wall_s_timed_region": wall, "final_loss": float(loss)}
     print(json.dumps(line))
 
