@@ -242,6 +242,11 @@ def test_run_nerf_fused_cli_loop(tmp_path):
     c = res["counts"]
     assert c["spn_render_rays_bwd"] == 3 and c["spn_adam_step"] == 6 and c["spn_train_losses"] == 3
     assert c["spn_get_rays"] == 120 + 1                     # the spiral video and the held-out test view
+    lama = str(tmp_path / "lama")
+    res3, out3 = run("--prepare", "--no_reload", "--N_iters", "2", "--i_feat", "2", "--i_weights", "100", "--render_factor", "1",
+                     "--lama_dir", lama)
+    assert sorted(os.listdir(lama)) == ["img%03d.png" % j for j in range(6)] + ["label"] and len(os.listdir(os.path.join(lama, "label"))) == 6
+    assert res3["counts"]["spn_train_losses"] == 2 and "disparity / mask pairs" in out3
     res2, out2 = run("--N_iters", "4", "--i_weights", "100", "--lpips", "--lpips_from", "3")
     assert res2["counts"]["spn_render_rays_bwd"] == 3       # step 3, step 4 and step 4's LPIPS patch chunk
     assert "Reloading from" in out2 and out2.count("[TRAIN] Iter:") == 2 and "[TRAIN] Iter: 3 " in out2      # resumed after step 2

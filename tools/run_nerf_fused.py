@@ -9,7 +9,9 @@ the same stages of `train()` (run_nerf.py:963-1703) for the flags of the hot pat
 scene_io.load_scene (load_llff_data), resident ray pools + device-side sampling instead of four DataLoaders
 (raypool, Trainer.step_from_pool), the step's three or four render calls as ONE chunk with analytic losses and the flat Adam
 (Trainer.step), the `--lpips` branch (Trainer.step_with_lpips), checkpoints in the reference's layout (Trainer.checkpoint:
-either trainer resumes the other's run), videos / test renders through render_path's asynchronous frame sink.
+either trainer resumes the other's run), videos / test renders through render_path's asynchronous frame sink, and with
+`--prepare` (stage A of the pipeline, README.md:58-67) the hand-over to the inpainter: every view's rendered disparity and
+mask as `<lama_dir>/img%03d.png`, `<lama_dir>/label/img%03d.png` every `i_feat` iterations (run_nerf.py:1563-1609).
 Under torchrun (one process per GPU) N_rand stays the GLOBAL batch of the reference: every rank draws the same indices and
 renders its contiguous 1/W of each ray group, gradients are averaged over NVLink, videos are rendered frame-sharded; rank 0
 logs, checkpoints and writes files.
@@ -54,6 +56,8 @@ def config_parser():
     A("--i_print", type=int, default=100); A("--i_weights", type=int, default=10000); A("--i_video", type=int, default=50000)
     A("--i_testset", type=int, default=50000); A("--i_feat", type=int, default=2000); A("--feat_weight", type=float, default=0.1)
     A("--precision", type=str, default="bf16", help="bf16 (tcgen05) | fp32 (CUDA cores, tight-parity mode)")
+    A("--lama_dir", type=str, default='lama/LaMa_test_images',
+      help="where --prepare leaves the rendered disparities and masks for the inpainter (run_nerf.py:1598-1609, relative to the cwd)")
     A("--dry_run", action='store_true', help="stop before the first GPU call (CPU-only check of config / data / pools)")
     A("--device", type=str, default="cuda:0", help="CUDA device (the library has no CPU implementation; tests drive the loop "
                                                     "with a call recorder in its place)")
@@ -172,9 +176,13 @@ def main(argv=None):
         if dpool is not None:
             di = torch.randint(0, dpool[1].numel(), (args.N_rand,), device=dev, generator=gen)
             kw = dict(rays_depth=dpool[0][:, di], target_depth=dpool[1][di], depth_lambda=args.depth_lambda)
-        if kw or (sampler is not None and i > args.lpips_from):
+        if kw or args.prepare or (sampler is not None and i > args.lpips_from):
+            if args.prepare:     # stage A renders no inpainted-disparity rays (run_nerf.py:1469-1473, 1515): an empty third group
+                inp = (dev_pools["pool_od"][:, :0], dev_pools["disp"][:0])
+            else:
+                inp = (dev_pools["pool_od"][:, idx[2]], dev_pools["disp"][idx[2]])
             batch = (dev_pools["pool_od"][:, idx[0]], dev_pools["rgb"][idx[0]], dev_pools["pool_od"][:, idx[1]],
-                     dev_pools["rgb"][idx[1]], dev_pools["pool_od"][:, idx[2]], dev_pools["disp"][idx[2]])
+                     dev_pools["rgb"][idx[1]]) + inp
             loss, psnr = tr.step(*batch, _apply=False, **kw)
             if sampler is not None and i > args.lpips_from:                                     # run_nerf.py:1523
                 views, Xs, Ys = sampler.sample()
@@ -184,7 +192,20 @@ def main(argv=None):
             tr.apply_gradients()
         else:
             loss, psnr = tr.step_from_pool(dev_pools["pool_od"], dev_pools["rgb"], dev_pools["disp"], idx)
-        rays_done += (4 if kw else 3) * args.N_rand
+        rays_done += (3 + (1 if kw else 0) - (1 if args.prepare else 0)) * args.N_rand
+        if args.prepare and i % args.i_feat == 0:               # hand-over to the inpainter (run_nerf.py:1563-1609)
+            rf = max(args.render_factor, 1)
+            if world > 1:
+                _, disps = spn.render_path_sharded(poses, list(hwf), args.chunk, test_kw, render_factor=args.render_factor, dst=0)
+            else:
+                _, disps, _ = spn.render_path(poses, list(hwf), args.chunk, test_kw, render_factor=args.render_factor)
+            if rank == 0:
+                import cv2
+                os.makedirs(os.path.join(args.lama_dir, 'label'), exist_ok=True)
+                for j in range(len(poses)):
+                    cv2.imwrite(os.path.join(args.lama_dir, f'img{j:0>3}.png'), disps[j] * 255)
+                    cv2.imwrite(os.path.join(args.lama_dir, 'label', f'img{j:0>3}.png'), masks[j][::rf, ::rf] * 255)
+                print('Wrote', len(poses), 'disparity / mask pairs to', args.lama_dir)
         if i % args.i_weights == 0 and rank == 0:
             path = os.path.join(logdir, '{:06d}.tar'.format(i))
             torch.save(tr.checkpoint(), path)
