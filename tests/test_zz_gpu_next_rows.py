@@ -206,6 +206,33 @@ def test_trainer_step_with_sparse_depth_rays_matches_reference_fp32():
             assert np.mean(err > tol) <= 0.03, (nm, k, err.max())
 
 
+def test_prepare_stage_step_without_disparity_rays_matches_autograd_fp32():
+    """Stage A (`--prepare`) renders no inpainted-disparity rays (run_nerf.py:1469-1473, 1515): Trainer.step with an EMPTY third
+    group against the same two render calls + four MSE terms differentiated by autograd through render()."""
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    rng = np.random.default_rng(8)
+    ro, rd = O.get_rays(24, 32, 28.8, poses(1)[0, :, :4])
+    rays = np.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    r1, r2 = T(rays[:, rng.permutation(768)[:72]]), T(rays[:, rng.permutation(768)[:56]])
+    t1, t2 = T(rng.uniform(0, 1, (72, 3)).astype(np.float32)), T(rng.uniform(0, 1, (56, 3)).astype(np.float32))
+    tr, _, _ = trainer(spn.PREC_FP32, 0.0)
+    loss, psnr = tr.step(r1, t1, r2, t2, r1[:, :0], t1[:0, 0], _apply=False)
+    torch.cuda.synchronize()
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    kw = render_kwargs(netc, netf)
+    mse = lambda a, b: torch.mean((a - b) ** 2)
+    rgb, _, _, _, ex = spn.render(*HWF, chunk=32768, rays=r1, retraw=True, **kw)
+    rgb_c, _, _, _, ex_c = spn.render(*HWF, chunk=32768, rays=r2, retraw=True, detach_weights=True, **kw)
+    ref = mse(rgb, t1) + mse(rgb_c, t2) + mse(ex_c["rgb0"], t2) + mse(ex["rgb0"], t1)
+    ref.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref.detach())) <= 1e-5 * float(ref.detach())
+    assert abs(float(psnr) + 10.0 * np.log10(float(mse(rgb, t1).detach()))) <= 1e-3
+    for flat, net in ((tr.grads[0], netc), (tr.grads[1], netf)):
+        want = np.concatenate([N(p.grad).reshape(-1) for p in net._flat_params()])
+        assert np.abs(want).max() > 0 and np.abs(N(flat) - want).max() <= 1e-4 * np.abs(want).max()
+
+
 def test_searchsorted_matches_numpy_on_the_references_grid():
     """The reference's only unit test (DS_NeRF/torchsearchsorted/test/test_searchsorted.py:9-44): row-wise np.searchsorted is
     the oracle, over its parameter grid (Ba, Bv in {1,100,200}, A in {1,50,500}, V in {1,12,120}, both sides), integer-exact."""
