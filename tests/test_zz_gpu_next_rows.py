@@ -72,6 +72,167 @@ def patch_targets(seed=1):
     return [T(rng.uniform(-1, 1, (1, 3, h, w)).astype(np.float32)) for h, w in SHAPES]
 
 
+def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
+    a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
+    err = np.abs(a - b); tol = atol + rtol * np.abs(b)
+    assert np.mean(err > tol) <= max_frac, (np.mean(err > tol), err.max())
+    assert err.max() <= hard * max(1.0, np.abs(b).max()), err.max()
+
+
+def test_searchsorted_matches_numpy_on_the_references_grid():
+    """The reference's only unit test (DS_NeRF/torchsearchsorted/test/test_searchsorted.py:9-44): row-wise np.searchsorted is
+    the oracle, over its parameter grid (Ba, Bv in {1,100,200}, A in {1,50,500}, V in {1,12,120}, both sides), integer-exact."""
+    from itertools import product
+    rng = np.random.default_rng(0)
+    for Ba, Bv, A, V, side in product([1, 100, 200], [1, 100, 200], [1, 50, 500], [1, 12, 120], ['left', 'right']):
+        if Ba > 1 and Bv > 1 and Ba != Bv:
+            continue
+        for rep in range(3):
+            a = np.sort(rng.uniform(0, 1, (Ba, A)).astype(np.float32), axis=1)
+            v = rng.uniform(0, 1, (Bv, V)).astype(np.float32)
+            if rep == 2 and A > 1:
+                v[:, ::2] = a[:, rng.integers(0, A, v[:, ::2].shape[1])][:Bv] if Ba >= Bv else a[0, rng.integers(0, A, v[:, ::2].shape)]   # exact ties
+            nrow = max(Ba, Bv)
+            want = np.stack([np.searchsorted(a[0 if Ba == 1 else r], v[0 if Bv == 1 else r], side=side) for r in range(nrow)], 0)
+            got = spn.ops.searchsorted(T(a), T(v), side=side)
+            assert got.dtype == torch.long and tuple(got.shape) == (nrow, V)
+            np.testing.assert_array_equal(N(got), want)
+    out = torch.empty((100, 12), dtype=torch.long, device=DEV)          # caller-provided output (test_searchsorted_output_dtype)
+    a = torch.sort(torch.rand(100, 50, device=DEV), dim=1)[0]; v = torch.rand(100, 12, device=DEV)
+    assert spn.ops.searchsorted(a, v, out) is out
+    np.testing.assert_array_equal(N(out), np.stack([np.searchsorted(N(a)[r], N(v)[r]) for r in range(100)], 0))
+    with pytest.raises(AssertionError):
+        spn.ops.searchsorted(torch.zeros(3, 4, device=DEV), torch.zeros(2, 4, device=DEV))
+
+
+@pytest.mark.parametrize("tag", ["depths", "c2w_patch", "staticcam", "rgb_net", "no_coarse"])
+def test_render_call_variants_match_reference_fp32(tag):
+    """render()'s other call forms against the unmodified reference (tests/golden/render_variants.npz): a depth column
+    (12-column ray matrix), rays from c2w with a patch window, c2w_staticcam, a NeRF_RGB fine network over a frozen density
+    provider (operator-level composition, run_nerf.py:680-692), --no_coarse.  Same tolerances as the main render parity test."""
+    from conftest import load_golden
+    g = load_golden("render_variants")
+    H, W, f = 12, 16, 14.4
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    kw = dict(chunk=32768, retraw=True, use_viewdirs=True, network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64,
+              N_importance=64, ndc=False, lindisp=True, white_bkgd=True, perturb=0., raw_noise_std=0., near=1.2, far=8.0)
+    if tag in ("rgb_net", "no_coarse"):
+        pr = O.init_params(13)
+        rgb_net = spn.NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, alpha_model=netf)
+        sd = {k: torch.from_numpy(v.copy()) for k, v in pr.items() if not k.startswith("alpha_linear")}
+        sd.update({"alpha_model." + k: v for k, v in netf.state_dict().items()})
+        rgb_net.load_state_dict(sd)
+        rgb_net = rgb_net.to(DEV); rgb_net.precision = spn.PREC_FP32; rgb_net.alpha_model.precision = spn.PREC_FP32
+        kw.update(network_fine=rgb_net, network_fn=None if tag == "no_coarse" else netc, need_alpha=(tag == "rgb_net"))
+    if tag == "depths":
+        kw.update(rays=T(g["rays"]), depths=T(g["depths"]))
+    elif tag == "c2w_patch":
+        kw.update(c2w=T(g["pose_a"]), patch=(3, 5, 6, 8))
+    elif tag == "staticcam":
+        kw.update(c2w=T(g["pose_a"]), c2w_staticcam=T(g["pose_b"]))
+    else:
+        kw.update(rays=T(g["rays"]))
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, **kw)
+    G = lambda k: g[f"{tag}__{k}"]
+    assert tuple(rgb.shape) == G("rgb").shape
+    close_mostly(rgb, G("rgb"), rtol=0, atol=2e-4); close_mostly(acc, G("acc"), rtol=0, atol=2e-4)
+    close_mostly(depth, G("depth"), rtol=2e-4, atol=2e-4); close_mostly(disp, G("disp"), rtol=5e-4, atol=0)
+    np.testing.assert_allclose(N(ex["rgb0"]), G("rgb0"), rtol=1e-5, atol=2e-4)
+    np.testing.assert_allclose(N(ex["disp0"]), G("disp0"), rtol=5e-4, atol=1e-6)
+    close_mostly(ex["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
+    if tag in ("depths", "rgb_net", "no_coarse"):
+        close_mostly(ex["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
+        close_mostly(ex["raw"], G("raw"), rtol=1e-3, atol=1e-3)
+        close_mostly(ex["weights"], G("weights"), rtol=0, atol=2e-4)
+    if tag == "rgb_net":
+        close_mostly(ex["alpha"], G("alpha"), rtol=0, atol=2e-4)
+        np.testing.assert_allclose(N(ex["alpha0"]), G("alpha0"), rtol=0, atol=2e-4)
+
+
+def test_render_path_frames_and_dumps(tmp_path):
+    """render_path (run_nerf.py:168-307) through the asynchronous frame sink: the returned stacks and the dumped arrays are
+    the per-frame render() outputs, in order, for more frames than staging buffers and several chunks per frame."""
+    netc, netf = make_net(11, spn.PREC_BF16), make_net(12, spn.PREC_BF16)
+    kw = render_kwargs(netc, netf)
+    P = poses(5)
+    gt = np.random.default_rng(2).uniform(0, 1, (5, 24, 32, 3)).astype(np.float32)
+    d = str(tmp_path)
+    rgbs, disps, (Xs, Ys) = spn.render_path(P, list(HWF), 200, kw, gt_imgs=gt, savedir=d, need_alpha=True)
+    assert rgbs.shape == (5, 24, 32, 3) and disps.shape == (5, 24, 32) and rgbs.dtype == np.float32 and Xs == [] and Ys == []
+    for i in range(5):
+        with torch.no_grad():
+            rgb, disp, acc, depth, ex = spn.render(*HWF, chunk=200, c2w=T(P[i, :3, :4]), retraw=True, need_alpha=True, **kw)
+        np.testing.assert_allclose(rgbs[i], N(rgb), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(disps[i], N(disp), rtol=1e-6, atol=1e-6)
+        name = "{:06d}".format(i)
+        for sub, ref in (("depth", depth), ("disp", disp), ("weight", ex["weights"]), ("z", ex["z_vals"]), ("alpha", ex["alpha"])):
+            a = np.load(os.path.join(d, sub, name + ".npy"))
+            assert a.shape == tuple(ref.shape)
+            np.testing.assert_allclose(a, N(ref), rtol=1e-6, atol=1e-6)
+        assert os.path.isfile(os.path.join(d, "rgb", name + ".png")) and os.path.isfile(os.path.join(d, "images", name + ".png"))
+        pose = np.loadtxt(os.path.join(d, "pose", name + ".txt"))
+        np.testing.assert_allclose(pose[:3], P[i, :3, :4], rtol=1e-6)
+    # half-resolution pass without dumps (render_factor, run_nerf.py:172-176)
+    rgbs2, disps2, _ = spn.render_path(P[:2], list(HWF), 32768, kw, render_factor=2)
+    assert rgbs2.shape == (2, 12, 16, 3) and np.isfinite(rgbs2).all()
+
+
+
+def test_trainer_step_with_sparse_depth_rays_matches_reference_fp32():
+    """Trainer.step with the fourth ray group of `--colmap_depth --depth_loss` against the unmodified reference's four
+    render() calls + autograd (tests/golden/train_step_depth.npz): loss and both networks' gradients."""
+    import importlib.util
+    from conftest import GOLDEN, load_golden
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    spec = importlib.util.spec_from_file_location("make_depth_step_golden", os.path.join(GOLDEN, "make_depth_step_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = load_golden("train_step_depth")
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    tr = trainer_mod.Trainer(netc, netf, lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.0,
+                             raw_noise_std=0.0, near=gen.NEAR, far=gen.FAR)
+    (r1, t1), (r2, t2), (r3, t3), (r4, t4) = [(T(r), T(t)) for r, t in gen.problem()]
+    loss, _ = tr.step(r1, t1, r2, t2, r3, t3, rays_depth=r4, target_depth=t4, depth_lambda=gen.DEPTH_LAMBDA)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-4 * float(gold["loss"]), (float(loss), float(gold["loss"]))
+    names = [n for n, _ in netc.named_parameters()]
+    for nm, net, flat in (("c", netc, tr.grads[0]), ("f", netf, tr.grads[1])):
+        for k, o, p in zip(names, net._offsets, net._flat_params()):
+            gv = N(flat[o:o + p.numel()])
+            ref_abs = float(gold[f"g_abs__{nm}__{k}"])
+            assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
+            sub, ref = gv.reshape(-1)[::997], gold[f"g_sub__{nm}__{k}"]
+            err = np.abs(sub - ref); tol = 1e-3 * np.abs(gv).max() + 1e-9 + 1e-2 * np.abs(ref)
+            assert np.mean(err > tol) <= 0.03, (nm, k, err.max())
+
+
+def test_prepare_stage_step_without_disparity_rays_matches_autograd_fp32():
+    """Stage A (`--prepare`) renders no inpainted-disparity rays (run_nerf.py:1469-1473, 1515): Trainer.step with an EMPTY third
+    group against the same two render calls + four MSE terms differentiated by autograd through render()."""
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    rng = np.random.default_rng(8)
+    ro, rd = O.get_rays(24, 32, 28.8, poses(1)[0, :, :4])
+    rays = np.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    r1, r2 = T(rays[:, rng.permutation(768)[:72]]), T(rays[:, rng.permutation(768)[:56]])
+    t1, t2 = T(rng.uniform(0, 1, (72, 3)).astype(np.float32)), T(rng.uniform(0, 1, (56, 3)).astype(np.float32))
+    tr, _, _ = trainer(spn.PREC_FP32, 0.0)
+    loss, psnr = tr.step(r1, t1, r2, t2, r1[:, :0], t1[:0, 0], _apply=False)
+    torch.cuda.synchronize()
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    kw = render_kwargs(netc, netf)
+    mse = lambda a, b: torch.mean((a - b) ** 2)
+    rgb, _, _, _, ex = spn.render(*HWF, chunk=32768, rays=r1, retraw=True, **kw)
+    rgb_c, _, _, _, ex_c = spn.render(*HWF, chunk=32768, rays=r2, retraw=True, detach_weights=True, **kw)
+    ref = mse(rgb, t1) + mse(rgb_c, t2) + mse(ex_c["rgb0"], t2) + mse(ex["rgb0"], t1)
+    ref.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref.detach())) <= 1e-5 * float(ref.detach())
+    assert abs(float(psnr) + 10.0 * np.log10(float(mse(rgb, t1).detach()))) <= 1e-3
+    for flat, net in ((tr.grads[0], netc), (tr.grads[1], netf)):
+        want = np.concatenate([N(p.grad).reshape(-1) for p in net._flat_params()])
+        assert np.abs(want).max() > 0 and np.abs(N(flat) - want).max() <= 1e-4 * np.abs(want).max()
+
+
 def test_lpips_patch_backward_matches_autograd_render():
     """Trainer.lpips_patch_backward (one fused chunk for all patches, no autograd around the renderer) against the
     reference's formulation (run_nerf.py:1541-1559): one render(c2w=..., patch=..., detach_weights=True) per view with
@@ -177,163 +338,3 @@ def test_training_reaches_the_references_psnr(prec_name):
     print(f"{prec_name}: PSNR over the last 20 of {gen.K} steps: ours {ours:.2f} dB, reference {ref:.2f} dB")
     assert abs(ours - ref) <= psnr_tol, (ours, ref)
     assert ours > float(gold["psnr"][:20].mean()) + 15.0          # and it did train (reference: +21 dB)
-
-
-def test_trainer_step_with_sparse_depth_rays_matches_reference_fp32():
-    """Trainer.step with the fourth ray group of `--colmap_depth --depth_loss` against the unmodified reference's four
-    render() calls + autograd (tests/golden/train_step_depth.npz): loss and both networks' gradients."""
-    import importlib.util
-    from conftest import GOLDEN, load_golden
-    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
-    spec = importlib.util.spec_from_file_location("make_depth_step_golden", os.path.join(GOLDEN, "make_depth_step_golden.py"))
-    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
-    gold = load_golden("train_step_depth")
-    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
-    tr = trainer_mod.Trainer(netc, netf, lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.0,
-                             raw_noise_std=0.0, near=gen.NEAR, far=gen.FAR)
-    (r1, t1), (r2, t2), (r3, t3), (r4, t4) = [(T(r), T(t)) for r, t in gen.problem()]
-    loss, _ = tr.step(r1, t1, r2, t2, r3, t3, rays_depth=r4, target_depth=t4, depth_lambda=gen.DEPTH_LAMBDA)
-    torch.cuda.synchronize()
-    assert abs(float(loss) - float(gold["loss"])) <= 2e-4 * float(gold["loss"]), (float(loss), float(gold["loss"]))
-    names = [n for n, _ in netc.named_parameters()]
-    for nm, net, flat in (("c", netc, tr.grads[0]), ("f", netf, tr.grads[1])):
-        for k, o, p in zip(names, net._offsets, net._flat_params()):
-            gv = N(flat[o:o + p.numel()])
-            ref_abs = float(gold[f"g_abs__{nm}__{k}"])
-            assert abs(np.abs(gv).sum(dtype=np.float64) - ref_abs) <= 5e-3 * ref_abs + 1e-7, (nm, k)
-            sub, ref = gv.reshape(-1)[::997], gold[f"g_sub__{nm}__{k}"]
-            err = np.abs(sub - ref); tol = 1e-3 * np.abs(gv).max() + 1e-9 + 1e-2 * np.abs(ref)
-            assert np.mean(err > tol) <= 0.03, (nm, k, err.max())
-
-
-def test_prepare_stage_step_without_disparity_rays_matches_autograd_fp32():
-    """Stage A (`--prepare`) renders no inpainted-disparity rays (run_nerf.py:1469-1473, 1515): Trainer.step with an EMPTY third
-    group against the same two render calls + four MSE terms differentiated by autograd through render()."""
-    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
-    rng = np.random.default_rng(8)
-    ro, rd = O.get_rays(24, 32, 28.8, poses(1)[0, :, :4])
-    rays = np.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
-    r1, r2 = T(rays[:, rng.permutation(768)[:72]]), T(rays[:, rng.permutation(768)[:56]])
-    t1, t2 = T(rng.uniform(0, 1, (72, 3)).astype(np.float32)), T(rng.uniform(0, 1, (56, 3)).astype(np.float32))
-    tr, _, _ = trainer(spn.PREC_FP32, 0.0)
-    loss, psnr = tr.step(r1, t1, r2, t2, r1[:, :0], t1[:0, 0], _apply=False)
-    torch.cuda.synchronize()
-    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
-    kw = render_kwargs(netc, netf)
-    mse = lambda a, b: torch.mean((a - b) ** 2)
-    rgb, _, _, _, ex = spn.render(*HWF, chunk=32768, rays=r1, retraw=True, **kw)
-    rgb_c, _, _, _, ex_c = spn.render(*HWF, chunk=32768, rays=r2, retraw=True, detach_weights=True, **kw)
-    ref = mse(rgb, t1) + mse(rgb_c, t2) + mse(ex_c["rgb0"], t2) + mse(ex["rgb0"], t1)
-    ref.backward()
-    torch.cuda.synchronize()
-    assert abs(float(loss) - float(ref.detach())) <= 1e-5 * float(ref.detach())
-    assert abs(float(psnr) + 10.0 * np.log10(float(mse(rgb, t1).detach()))) <= 1e-3
-    for flat, net in ((tr.grads[0], netc), (tr.grads[1], netf)):
-        want = np.concatenate([N(p.grad).reshape(-1) for p in net._flat_params()])
-        assert np.abs(want).max() > 0 and np.abs(N(flat) - want).max() <= 1e-4 * np.abs(want).max()
-
-
-def test_searchsorted_matches_numpy_on_the_references_grid():
-    """The reference's only unit test (DS_NeRF/torchsearchsorted/test/test_searchsorted.py:9-44): row-wise np.searchsorted is
-    the oracle, over its parameter grid (Ba, Bv in {1,100,200}, A in {1,50,500}, V in {1,12,120}, both sides), integer-exact."""
-    from itertools import product
-    rng = np.random.default_rng(0)
-    for Ba, Bv, A, V, side in product([1, 100, 200], [1, 100, 200], [1, 50, 500], [1, 12, 120], ['left', 'right']):
-        if Ba > 1 and Bv > 1 and Ba != Bv:
-            continue
-        for rep in range(3):
-            a = np.sort(rng.uniform(0, 1, (Ba, A)).astype(np.float32), axis=1)
-            v = rng.uniform(0, 1, (Bv, V)).astype(np.float32)
-            if rep == 2 and A > 1:
-                v[:, ::2] = a[:, rng.integers(0, A, v[:, ::2].shape[1])][:Bv] if Ba >= Bv else a[0, rng.integers(0, A, v[:, ::2].shape)]   # exact ties
-            nrow = max(Ba, Bv)
-            want = np.stack([np.searchsorted(a[0 if Ba == 1 else r], v[0 if Bv == 1 else r], side=side) for r in range(nrow)], 0)
-            got = spn.ops.searchsorted(T(a), T(v), side=side)
-            assert got.dtype == torch.long and tuple(got.shape) == (nrow, V)
-            np.testing.assert_array_equal(N(got), want)
-    out = torch.empty((100, 12), dtype=torch.long, device=DEV)          # caller-provided output (test_searchsorted_output_dtype)
-    a = torch.sort(torch.rand(100, 50, device=DEV), dim=1)[0]; v = torch.rand(100, 12, device=DEV)
-    assert spn.ops.searchsorted(a, v, out) is out
-    np.testing.assert_array_equal(N(out), np.stack([np.searchsorted(N(a)[r], N(v)[r]) for r in range(100)], 0))
-    with pytest.raises(AssertionError):
-        spn.ops.searchsorted(torch.zeros(3, 4, device=DEV), torch.zeros(2, 4, device=DEV))
-
-
-def close_mostly(a, b, rtol, atol, max_frac=0.01, hard=5e-2):
-    a = np.asarray(N(a) if torch.is_tensor(a) else a, np.float64); b = np.asarray(b, np.float64)
-    err = np.abs(a - b); tol = atol + rtol * np.abs(b)
-    assert np.mean(err > tol) <= max_frac, (np.mean(err > tol), err.max())
-    assert err.max() <= hard * max(1.0, np.abs(b).max()), err.max()
-
-
-@pytest.mark.parametrize("tag", ["depths", "c2w_patch", "staticcam", "rgb_net", "no_coarse"])
-def test_render_call_variants_match_reference_fp32(tag):
-    """render()'s other call forms against the unmodified reference (tests/golden/render_variants.npz): a depth column
-    (12-column ray matrix), rays from c2w with a patch window, c2w_staticcam, a NeRF_RGB fine network over a frozen density
-    provider (operator-level composition, run_nerf.py:680-692), --no_coarse.  Same tolerances as the main render parity test."""
-    from conftest import load_golden
-    g = load_golden("render_variants")
-    H, W, f = 12, 16, 14.4
-    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
-    kw = dict(chunk=32768, retraw=True, use_viewdirs=True, network_query_fn=None, network_fn=netc, network_fine=netf, N_samples=64,
-              N_importance=64, ndc=False, lindisp=True, white_bkgd=True, perturb=0., raw_noise_std=0., near=1.2, far=8.0)
-    if tag in ("rgb_net", "no_coarse"):
-        pr = O.init_params(13)
-        rgb_net = spn.NeRF_RGB(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, alpha_model=netf)
-        sd = {k: torch.from_numpy(v.copy()) for k, v in pr.items() if not k.startswith("alpha_linear")}
-        sd.update({"alpha_model." + k: v for k, v in netf.state_dict().items()})
-        rgb_net.load_state_dict(sd)
-        rgb_net = rgb_net.to(DEV); rgb_net.precision = spn.PREC_FP32; rgb_net.alpha_model.precision = spn.PREC_FP32
-        kw.update(network_fine=rgb_net, network_fn=None if tag == "no_coarse" else netc, need_alpha=(tag == "rgb_net"))
-    if tag == "depths":
-        kw.update(rays=T(g["rays"]), depths=T(g["depths"]))
-    elif tag == "c2w_patch":
-        kw.update(c2w=T(g["pose_a"]), patch=(3, 5, 6, 8))
-    elif tag == "staticcam":
-        kw.update(c2w=T(g["pose_a"]), c2w_staticcam=T(g["pose_b"]))
-    else:
-        kw.update(rays=T(g["rays"]))
-    with torch.no_grad():
-        rgb, disp, acc, depth, ex = spn.render(H, W, f, **kw)
-    G = lambda k: g[f"{tag}__{k}"]
-    assert tuple(rgb.shape) == G("rgb").shape
-    close_mostly(rgb, G("rgb"), rtol=0, atol=2e-4); close_mostly(acc, G("acc"), rtol=0, atol=2e-4)
-    close_mostly(depth, G("depth"), rtol=2e-4, atol=2e-4); close_mostly(disp, G("disp"), rtol=5e-4, atol=0)
-    np.testing.assert_allclose(N(ex["rgb0"]), G("rgb0"), rtol=1e-5, atol=2e-4)
-    np.testing.assert_allclose(N(ex["disp0"]), G("disp0"), rtol=5e-4, atol=1e-6)
-    close_mostly(ex["z_std"], G("z_std"), rtol=1e-3, atol=1e-4)
-    if tag in ("depths", "rgb_net", "no_coarse"):
-        close_mostly(ex["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
-        close_mostly(ex["raw"], G("raw"), rtol=1e-3, atol=1e-3)
-        close_mostly(ex["weights"], G("weights"), rtol=0, atol=2e-4)
-    if tag == "rgb_net":
-        close_mostly(ex["alpha"], G("alpha"), rtol=0, atol=2e-4)
-        np.testing.assert_allclose(N(ex["alpha0"]), G("alpha0"), rtol=0, atol=2e-4)
-
-
-def test_render_path_frames_and_dumps(tmp_path):
-    """render_path (run_nerf.py:168-307) through the asynchronous frame sink: the returned stacks and the dumped arrays are
-    the per-frame render() outputs, in order, for more frames than staging buffers and several chunks per frame."""
-    netc, netf = make_net(11, spn.PREC_BF16), make_net(12, spn.PREC_BF16)
-    kw = render_kwargs(netc, netf)
-    P = poses(5)
-    gt = np.random.default_rng(2).uniform(0, 1, (5, 24, 32, 3)).astype(np.float32)
-    d = str(tmp_path)
-    rgbs, disps, (Xs, Ys) = spn.render_path(P, list(HWF), 200, kw, gt_imgs=gt, savedir=d, need_alpha=True)
-    assert rgbs.shape == (5, 24, 32, 3) and disps.shape == (5, 24, 32) and rgbs.dtype == np.float32 and Xs == [] and Ys == []
-    for i in range(5):
-        with torch.no_grad():
-            rgb, disp, acc, depth, ex = spn.render(*HWF, chunk=200, c2w=T(P[i, :3, :4]), retraw=True, need_alpha=True, **kw)
-        np.testing.assert_allclose(rgbs[i], N(rgb), rtol=0, atol=1e-6)
-        np.testing.assert_allclose(disps[i], N(disp), rtol=1e-6, atol=1e-6)
-        name = "{:06d}".format(i)
-        for sub, ref in (("depth", depth), ("disp", disp), ("weight", ex["weights"]), ("z", ex["z_vals"]), ("alpha", ex["alpha"])):
-            a = np.load(os.path.join(d, sub, name + ".npy"))
-            assert a.shape == tuple(ref.shape)
-            np.testing.assert_allclose(a, N(ref), rtol=1e-6, atol=1e-6)
-        assert os.path.isfile(os.path.join(d, "rgb", name + ".png")) and os.path.isfile(os.path.join(d, "images", name + ".png"))
-        pose = np.loadtxt(os.path.join(d, "pose", name + ".txt"))
-        np.testing.assert_allclose(pose[:3], P[i, :3, :4], rtol=1e-6)
-    # half-resolution pass without dumps (render_factor, run_nerf.py:172-176)
-    rgbs2, disps2, _ = spn.render_path(P[:2], list(HWF), 32768, kw, render_factor=2)
-    assert rgbs2.shape == (2, 12, 16, 3) and np.isfinite(rgbs2).all()
