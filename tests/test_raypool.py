@@ -207,13 +207,19 @@ def test_run_nerf_fused_cli_dry_run(tmp_path):
                    "depth_lambda = 0.1\nno_ndc = True\nlindisp = True\nrender_factor = 1\ni_feat = 2000\ni_video = 2000\n"
                    "feat_weight = 0.1\nlrate = 0.03\nlrate_decay = 10\nwhite_bkgd = True\n" % (tmp_path / "logs"))
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
-                        "--lpips", "--no_tcnn", "--dry_run"], capture_output=True, text=True, timeout=300)
+                        "--lpips", "--no_tcnn", "--N_gt", "0", "--dry_run"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-3000:]
     assert "sparse-depth rays" in p.stdout and "dry run: stopping before the first GPU call" in p.stdout
     written = (tmp_path / "logs" / "t" / "args.txt").read_text()
     assert "lrate = 0.03" in written and "colmap_depth = True" in written and "N_rand = 64" in written
+    held = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
+                           "--N_gt", "2", "--dry_run"], capture_output=True, text=True, timeout=300)
+    assert held.returncode == 0 and "4 training views" in held.stdout          # 6 views, the first 2 held out
+    none_left = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
+                                "--dry_run"], capture_output=True, text=True, timeout=300)    # the config's N_gt = 40
+    assert none_left.returncode != 0 and "leaves no training view" in (none_left.stdout + none_left.stderr)
     bad = subprocess.run([sys.executable, os.path.join(root, "tools", "run_nerf_fused.py"), "--config", str(cfg), "--datadir", scene,
-                          "--sigma_loss", "--dry_run"], capture_output=True, text=True, timeout=300)
+                          "--N_gt", "0", "--sigma_loss", "--dry_run"], capture_output=True, text=True, timeout=300)
     assert bad.returncode != 0 and "outside the fused hot path" in (bad.stdout + bad.stderr)
 
 

@@ -90,6 +90,10 @@ def main(argv=None):
     hwf = (int(poses[0, 0, 4]), int(poses[0, 1, 4]), float(poses[0, 2, 4]))
     i_test = list(np.arange(images.shape[0])[::args.llffhold]) if args.llffhold > 0 else [int(i_test)]
     i_train = list(range(images.shape[0]))
+    if args.N_gt > 0:        # the first N_gt views are held-out ground truth (run_nerf.py:1030-1035; the README runs use --N_gt 0)
+        i_test, i_train = i_train[:args.N_gt], i_train[args.N_gt:]
+        if not i_train:
+            raise SystemExit(f"run_nerf_fused: --N_gt {args.N_gt} leaves no training view out of {images.shape[0]}")
     if args.no_ndc:
         near, far = float(np.ndarray.min(bds) * .9), float(np.ndarray.max(bds) * 1.)
     else:
@@ -108,7 +112,7 @@ def main(argv=None):
     with open(os.path.join(logdir, 'args.txt'), 'w') as f:                                     # run_nerf.py:1133-1137
         for arg in sorted(vars(args)):
             f.write('{} = {}\n'.format(arg, getattr(args, arg)))
-    say(f"{len(images)} views {hwf[0]}x{hwf[1]}, near/far {near:.3f}/{far:.3f}, pool {len(pools.label)} rays (unmasked "
+    say(f"{len(images)} views ({len(i_train)} training views) {hwf[0]}x{hwf[1]}, near/far {near:.3f}/{far:.3f}, pool {len(pools.label)} rays (unmasked "
           f"{len(pools.idx_clf)}, masked {len(pools.idx_rgb)}, inpainted {len(pools.idx_inp)})"
           + (f", {depth_pool[1].shape[0]} sparse-depth rays" if depth_pool is not None else ""))
     if args.dry_run:
