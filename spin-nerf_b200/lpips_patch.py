@@ -73,7 +73,9 @@ def draw_origins(boxes, views, patch_len, rand=_random):
 
 def resize_targets(images, Hs, Ws):
     """[V,H,W,3] frames in [0,1] -> [V,3,Hs,Ws] in [-1,1], resized like torchvision.transforms.Resize((Hs, Ws)) applied
-    to the (x-0.5)*2 NCHW tensor (run_nerf.py:1537-1539, 1553-1557): bilinear, antialiased, half-pixel centres."""
+    to the (x-0.5)*2 NCHW tensor (run_nerf.py:1537-1539, 1553-1557): bilinear, antialiased, half-pixel centres — what Resize
+    does to a float tensor in torchvision >= 0.17 (antialias on by default; older releases did not antialias tensors, so the
+    reference's own targets depend on the installed torchvision; the fixture pins this image's 0.26)."""
     x = torch.as_tensor(images, dtype=torch.float32)
     x = ((x - 0.5) * 2).permute(0, 3, 1, 2)
     if tuple(x.shape[-2:]) == (int(Hs), int(Ws)):
