@@ -52,11 +52,14 @@ class MaskBoxes:
             nz = masks[v] != 0
             rows, cols = np.flatnonzero(nz.any(1)), np.flatnonzero(nz.any(0))
             if rows.size == 0:
-                raise ValueError(f"view {v} has an empty mask: the reference's np.where(...).min() raises here too")
+                boxes[v] = -1          # e.g. a held-out ground-truth view: only an error if a patch is ever drawn from it
+                continue
             boxes[v] = (rows[0] // rf, rows[-1] // rf, cols[0] // rf, cols[-1] // rf)
         self.boxes = boxes
 
     def __getitem__(self, v):
+        if self.boxes[v][0] < 0:
+            raise ValueError(f"view {v} has an empty mask: the reference's np.where(...).min() raises here too")
         return tuple(int(b) for b in self.boxes[v])
 
 
