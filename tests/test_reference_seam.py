@@ -94,3 +94,21 @@ def test_unmodified_reference_trainer_sparse_depth_step_over_the_dropin():
     res = json.loads([l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1][5:])
     render = ["spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points", "spn_raw2outputs_fwd"]
     assert res["calls"] == (render * 4 + ["spn_raw2outputs_bwd", "spn_mlp_bwd"] * 7) * 2
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/DS_NeRF/run_nerf.py"), reason="reference checkout not present")
+@pytest.mark.timeout(600)
+def test_unmodified_reference_render_only_over_the_dropin():
+    """`--render_only --render_test` (run_nerf.py:1168-1220): the reference's own render_path with need_alpha and per-frame
+    dumps over the drop-in's get_rays / NeRF / raw2outputs / sample_pdf, mp4 export through the imageio shim."""
+    env = dict(os.environ, PYTHONSAFEPATH="1", OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "seam_driver.py"), "2", "100000", "--render_only", "--render_test",
+                        "--render_factor", "2"], capture_output=True, text=True, env=env, timeout=580)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("SEAM ")][-1][5:])
+    d = "renderonly_test_000000/"
+    for f in ("rgb.mp4", "disp.mp4", "intrinsics.txt", "rgb/000000.png", "images/000000.png", "depth/000000.npy", "disp/000000.npy",
+              "weight/000000.npy", "z/000000.npy", "alpha/000000.npy", "pose/000000.txt"):
+        assert d + f in res["files"], f
+    assert res["calls"] == ["spn_get_rays", "spn_mlp_fwd_points", "spn_raw2outputs_fwd", "spn_sample_pdf_cdf", "spn_mlp_fwd_points",
+                            "spn_raw2outputs_fwd"]                 # one held-out view, no optimisation step
