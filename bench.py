@@ -436,7 +436,7 @@ def main():
                     help="weak (default, what the driver's 1/2/4/8 series measures): --n_rand rays per render call PER GPU; strong: "
                          "--n_rand_global rays per render call in total, split over the ranks (BASELINE configs[3]: 8192 over 8 GPUs)")
     ap.add_argument("--n_rand_global", type=int, default=8192)
-    ap.add_argument("--cpu_rays", type=int, default=128, help="rays per render call in the CPU sample")
+    ap.add_argument("--cpu_rays", type=int, default=1024, help="rays per render call in the CPU sample (default: the GPU arm's N_rand, same config)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "train_lpips", "render"],
                     help="train = BASELINE configs[1] (the headline line, default); train_lpips = configs[2] (N_rand=4096 + 4 LPIPS "
@@ -607,8 +607,13 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    # a timed region of seconds runs under the power cap (cuBLAS settles at ~1350 MHz there): sustained peak; a short region
+    # (the default 100 x 3.3 ms) runs at boost clocks: the burst peak is the honest denominator
+    long_run = step_ms >= 4000.0
+    pk_key = "bf16_tflops_sustained" if long_run else "bf16_tflops"
+    peak = float(peaks.get(pk_key, 1400.0 if long_run else 1590.0))
+    peak_src = (f"MEASURED_PEAKS.json {pk_key} ({'timed region >= 4 s: power-capped steady state' if long_run else 'timed region < 4 s: boost clocks'})"
+                if peaks else f"fallback {'1.4' if long_run else '1.59'} PFLOP/s (B200_PROFILING.md)")
     evals_per_rank_step = RENDERS_PER_STEP * n_rand * EVALS_PER_RAY
     fwd_n, fwd_ms = prof["mlp_fwd"]
     kern = {}
@@ -628,18 +633,19 @@ def main():
         else:
             k.update(bound="tensor", achieved=k["tflops"], peak=peak, unit="TFLOP/s", frac=k["tflops"] / peak)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom)
+        traffic_src = f"static: profiles/traffic.json from ncu capture {tj.get('_source')} (dram bytes per launch, mean of the coarse and fine launch; not measured in this run)"
     except Exception:
         pass
     roofline = None
     if dom:
         d = kern[dom]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": traffic,
-                    "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if d["bound"] == "hbm" else "bf16_tflops_sustained (kernel timed inside a long step)"))
-                                   if peaks else "fallback (B200_PROFILING.md)",
+                    "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)") if d["bound"] == "hbm" else peak_src,
                     "algorithmic_units": "wgrad: 76 x 16 KB stash/dstash atoms per 128-sample tile; fwd/dgrad: 1 186 816 / 1 115 392 FLOP per MLP evaluation",
                     "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}

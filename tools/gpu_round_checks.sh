@@ -25,8 +25,8 @@ run bench_n1       420 python bench.py --gpus 1
 run bench_ref      420 python bench.py --impl reference --steps 3 --warmup 1
 run bench_render   300 python bench.py --workload render --steps 6 --warmup 3
 run bench_lpips    300 python bench.py --workload train_lpips --steps 30 --warmup 5
-run searchsorted   120 python tools/bench_searchsorted.py
-run example        300 python tools/train_synthetic.py --steps 340 --lpips --lpips_from 300 --video "/tmp/${TAG}_video"   # per-sample dumps are large: keep them out of gpurun_out (64 MiB)
+run bench_sustained 300 python bench.py --gpus 1 --steps 2000 --warmup 5 --no_cpu_baseline
+run bench_strong1  300 python bench.py --gpus 1 --scaling strong --n_rand_global 8192 --steps 20 --warmup 5 --no_cpu_baseline
 run ncu_launches   420 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 250 --csv \
                        --log-file "$OUT/${TAG}_launches.csv" python bench.py --steps 8 --warmup 3 --no_cpu_baseline --deadline 0
 run ncu_full       600 ncu --set full --clock-control none --import-source on -k 'regex:mlp_(fwd|dgrad|wgrad)_kernel' -s 18 -c 6 \

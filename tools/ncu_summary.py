@@ -50,5 +50,30 @@ def launch_list(path):
     print(f"total {total / 1e6:.3f} ms over {sum(cnt.values())} launches")
 
 
+def traffic(path, out_json="profiles/traffic.json"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the three MLP kernels (mean over the captured launches: one
+    step = the coarse and the fine launch of each) -> profiles/traffic.json, which bench.py quotes as roofline.traffic together
+    with the name of the capture it came from."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    acc = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].split("<")[0].replace("void ", "").replace("spn::", "").replace("_kernel", "")
+        acc[name].append(float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]])
+    res = {k: sum(v) / len(v) for k, v in acc.items()}
+    res["_per_launch"] = {k: v for k, v in acc.items()}
+    res["_source"] = os.path.basename(path)
+    res["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, mean of the step's "
+                    "coarse (64 samples/ray) and fine (128 samples/ray) launch of each kernel; static: measured once per kernel change "
+                    "under ncu (tools/gpu_round_checks.sh), not in the timed bench run")
+    json.dump(res, open(out_json, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "list": launch_list, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
