@@ -159,6 +159,9 @@ int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K,
 
 /* Diagnostic: cycles (clock64, written to cycles_dev[0]) for `reps` back-to-back tcgen05.mma M=128 x N x K=16 with
  * K-major (0) or MN-major (1) shared-memory operands — the measurement behind DESIGN.md's wgrad layout choice. */
+/* CTA-pair (cta_group::2, M = 256) MMA rate: ts = 1 takes the A operand from tensor memory; nacc accumulators in turn;
+ * ld_warps warps per CTA generate epilogue-like tcgen05.ld / tcgen05.st traffic meanwhile.  out_dev[0] = cycles for reps MMAs. */
+int spn_tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out_dev, void* stream);
 int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream);
 /* Diagnostic: TMEM -> register drain rate.  `nwarps` (1..16) warps each read 128 accumulator columns of their lane quarter
  * `reps` times with tcgen05.ld 32x32b.x32; with_mma != 0 keeps M=128 N=256 MMAs running on the same SM meanwhile.

@@ -133,6 +133,9 @@ extern "C" int spn_tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long
   return tc_tmem_ld_rate(nwarps, reps, with_mma, out_dev, as_stream(stream));
 }
 
+extern "C" int spn_tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out_dev, void* stream) {
+  return tc_mma_rate_pair(ts, n, reps, nacc, ld_warps, out_dev, as_stream(stream));
+}
 extern "C" int spn_tc_mma_rate(int a_mn_major, int b_mn_major, int n, int reps, long long* cycles_dev, void* stream) {
   SPN_CHECK_ARG(cycles_dev && reps > 0 && (n == 64 || n == 128 || n == 256), "spn_tc_mma_rate: bad arguments");
   return tc_mma_rate(a_mn_major, b_mn_major, n, reps, cycles_dev, as_stream(stream));

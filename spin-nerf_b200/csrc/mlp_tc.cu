@@ -159,6 +159,7 @@ struct FwdParams {
   uint8_t* stash;   // nullable
   int num_quads;    // groups of 4 tiles: one round of a CTA pair (2 tile slots per CTA)
   long long* trace; // diagnostic (spn_tc_set_trace): clock64 stamps of CTA 0's pipeline events, NULL = off
+  int debug;        // SPN_FWD_DEBUG (timing experiments, results are wrong): 1 = no wait for the stash copies, 2 = no mask stores, 4 = no stash copies
 };
 
 // sin/cos for the bf16 encodings: two-constant Cody-Waite reduction to [-pi, pi] (exact product via fma) followed by
@@ -342,19 +343,61 @@ __device__ __forceinline__ uint32_t epi_final32(const uint32_t (&v)[32], const i
   return mb;
 }
 
-// CTA pairs (cta_group::2).  Two CTAs on neighbouring SMs form a cluster; each owns two 128-sample tile slots that
-// ping-pong as before, but every tcgen05.mma spans the pair (M = 256: slot t of both CTAs), so each SM reads only ITS
-// half of the weight chunk from shared memory (128 of the 256 output rows) and loads only that half from L2: per-SM
-// shared-memory traffic per layer drops from 336 KB to 224 KB (operand reads 192 -> 128, weight writes 80 -> 32), which
-// is what bounded the single-CTA version (tools/trace_fwd.py: MMAs ran at ~190 instead of 128 cycles with the
-// 128 B/cycle/SM shared-memory pipe saturated).  With 16 KB half-chunks the 96 KB ring holds 6 of them: a layer's four
-// chunks are loaded ONCE per round and stay resident for both tile slots, the rest prefetches the next layer (see the
-// ring / barrier comment inside the kernel; tests/test_ring_protocol_model.py is an executable model of the protocol).
+// values [I0, I0 + CNT) of [v, sin(2^k v), cos(2^k v)]_k (helpers:28-52 order; entries past 3 + 6 NFREQ are zero padding) as
+// CNT / 2 packed bf16 pairs: one quarter of gamma(pts) (L = 10, 16 values) or of gamma(dir) (L = 4, 8 values) per thread
+template <int NFREQ, int I0, int CNT>
+__device__ __forceinline__ void encode_range(const float v[3], uint32_t (&w)[CNT / 2]) {
+  float vals[CNT];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) vals[i] = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (a >= I0 && a < I0 + CNT) vals[(a - I0) % CNT] = v[a];
+#pragma unroll
+  for (int k = 0; k < NFREQ; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int is = 3 + 6 * k + a, ic = is + 3;
+      const bool ns = is >= I0 && is < I0 + CNT, nc = ic >= I0 && ic < I0 + CNT;
+      if (ns || nc) {
+        float sn, cs;
+        fast_sincos(__fmul_rn(v[a], (float)(1 << k)), sn, cs);
+        if (ns) vals[(is - I0) % CNT] = sn;
+        if (nc) vals[(ic - I0) % CNT] = cs;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CNT / 2; ++i) w[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
+}
+__device__ __forceinline__ void encode_pts_quarter(const int cq, const float v[3], uint32_t (&w)[8]) {
+  if (cq == 0) encode_range<10, 0, 16>(v, w);
+  else if (cq == 1) encode_range<10, 16, 16>(v, w);
+  else if (cq == 2) encode_range<10, 32, 16>(v, w);
+  else encode_range<10, 48, 16>(v, w);
+}
+__device__ __forceinline__ void encode_dir_quarter(const int cq, const float v[3], uint32_t (&w)[4]) {
+  if (cq == 0) encode_range<4, 0, 8>(v, w);
+  else if (cq == 1) encode_range<4, 8, 8>(v, w);
+  else if (cq == 2) encode_range<4, 16, 8>(v, w);
+  else encode_range<4, 24, 8>(v, w);
+}
+
+// CTA pairs (cta_group::2).  Two CTAs on neighbouring SMs form a cluster; each owns two 128-sample tile slots and every
+// tcgen05.mma spans the pair (M = 256: slot t of both CTAs), so each SM reads only ITS half of the weight chunk from
+// shared memory (128 of the 256 output rows) and loads only that half from L2.  With 16 KB half-chunks the 96 KB ring
+// holds 6 of them: a layer's four chunks are loaded ONCE per round and stay resident for both tile slots, the rest
+// prefetches the next layer (ring / barrier comment inside the kernel; tests/test_ring_protocol_model.py models it).
 //   leader CTA (cluster rank 0): warp 1 lane 0 issues the MMAs and the multicast commits (ring slot free / accumulator
 //     ready arrive on the same barrier offsets in both CTAs)
 //   peer CTA: warp 1 lane 0 relays "my halves of this weight group have landed" to the leader's group barrier
-//   both: warp 0 loads the CTA's halves; the 16 epilogue warps signal "A tile written" to the leader's act barrier
-//     (one elected lane per warp; remote arrive from the peer)
+//   both: warp 0 lanes 0-5 load the CTA's weight halves; lanes 8-15 stream finished layer tiles to the stash (training)
+//   warps 2-17: ALL SIXTEEN epilogue warps work on tile slot 0, then on tile slot 1, of every step (4 TMEM lane quarters x
+//     4 column quarters of 64).  Round-1 gave each slot its own 8 warps: an epilogue then took 2.3-3.0 k cycles, longer
+//     than the other slot's 2 k cycles of MMAs, so the chain MMA -> epilogue -> MMA of a slot was exposed (tensor pipe
+//     busy 37 % of a round, profiles/r01b_trace_fwd_training.txt).  The epilogue is latency-bound (TMEM drain is ~530
+//     cycles, profiles/r01b_probe_tmem_drain.txt), so twice the warps on half the columns halve it, and because slot 0's
+//     epilogue runs while slot 1's MMAs execute and vice versa the two never compete for the warps.
 template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -370,6 +413,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   // barriers: group_full[2][4]  group g of step s uses barrier [g][s % 4] — the ring never holds groups of two steps that
   //             are 4 apart.  Armed by the local producer and, on the leader, by the peer's relay as well (count 2).
   //           empty[3] (one multicast commit per group, after tile slot 1 has used it)   acc_full[2], act_ready[2]
+  //           tile_written[2] / tile_free[2] (training): all 16 warps have written slot t's layer output -> the four
+  //             store lanes copy it to the stash -> the copies have finished READING the tile, it may be overwritten
   // The MMA-issuing thread is the scarce resource (tools/trace_fwd.py): tcgen05.mma issue blocks once a few MMAs are
   // queued, a tcgen05.commit costs it ~130 cycles and even a satisfied mbarrier wait 200-400, during which the tensor
   // pipe drains.  Hence few, merged barriers: per layer it waits on group 0 (before the A tile, off the critical path),
@@ -377,13 +422,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   static_assert(kNumSteps % 4 == 0, "group barrier phase bookkeeping assumes a multiple of 4 steps per round");
   const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 64;
   const uint32_t bar_acc = bar_empty + 8 * kSlots, bar_act = bar_acc + 16;
+  const uint32_t bar_written = bar_act + 16, bar_free = bar_written + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
   const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) mbar_init(bar_empty + 8 * s, 1);
     for (int b = 0; b < 8; ++b) mbar_init(bar_full + 8 * b, rank == 0 ? 2 : 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, 2 * kEpiWarps); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_acc + 8 * t, 1);
+      mbar_init(bar_act + 8 * t, 2 * kFwdEpiWarps);
+      mbar_init(bar_written + 8 * t, kFwdEpiWarps);
+      mbar_init(bar_free + 8 * t, 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators, in both CTAs of the pair
@@ -405,37 +456,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
 
   if (warp == 0) {
-    // ================= weight producer (this CTA's half of every chunk) =================
-    // One 16 KB (8 KB for the 128-wide views layer) bulk copy per chunk; the two chunks of a group are issued by two
-    // different lanes (slot, slot + 3): a thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py).
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < my_rounds; ++it) {
-      const uint8_t* src = p.packed;
-      for (int s = 0; s < kNumSteps; ++s) {
-        const uint32_t half = (uint32_t)c_step_n[s] * 64u;       // bytes of this CTA's half chunk
-        const int nch = c_step_chunks[s];
-        for (int g = 0; 2 * g < nch; ++g) {
-          const int in_group = nch - 2 * g < 2 ? nch - 2 * g : 2;
-          const int sub = lane >= kSlots ? 1 : 0;                // which chunk of the group this lane copies
-          if (lane == (int)stage || lane == (int)stage + kSlots) {
-            const uint32_t gbar = bar_full + 8 * (s & 3) + 32 * g;
-            // BOTH lanes of the slot wait for every one of its releases, also when the group has a single chunk: a lane
-            // that skipped a revolution would find its next parity wait satisfied by the release before last
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (sub == 0) {
-              mbar_arrive_expect_tx(gbar, (uint32_t)in_group * half);
-              if (g == 0 && nch <= 2) mbar_arrive(gbar + 32);   // no second group: its barrier still advances one phase per step
-              if (tracing) trace_stamp(p.trace, it, s, 0, 12 + g);
+    if (lane < 2 * kSlots) {
+      // ================= weight producer (this CTA's half of every chunk) =================
+      // One 16 KB (8 KB for the 128-wide views layer) bulk copy per chunk; the two chunks of a group are issued by two
+      // different lanes (slot, slot + 3): a thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py).
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_rounds; ++it) {
+        const uint8_t* src = p.packed;
+        for (int s = 0; s < kNumSteps; ++s) {
+          const uint32_t half = (uint32_t)c_step_n[s] * 64u;       // bytes of this CTA's half chunk
+          const int nch = c_step_chunks[s];
+          for (int g = 0; 2 * g < nch; ++g) {
+            const int in_group = nch - 2 * g < 2 ? nch - 2 * g : 2;
+            const int sub = lane >= kSlots ? 1 : 0;                // which chunk of the group this lane copies
+            if (lane == (int)stage || lane == (int)stage + kSlots) {
+              const uint32_t gbar = bar_full + 8 * (s & 3) + 32 * g;
+              // BOTH lanes of the slot wait for every one of its releases, also when the group has a single chunk: a lane
+              // that skipped a revolution would find its next parity wait satisfied by the release before last
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              if (sub == 0) {
+                mbar_arrive_expect_tx(gbar, (uint32_t)in_group * half);
+                if (g == 0 && nch <= 2) mbar_arrive(gbar + 32);   // no second group: its barrier still advances one phase per step
+                if (tracing) trace_stamp(p.trace, it, s, 0, 12 + g);
+              }
+              const int c = 2 * g + sub;
+              if (sub < in_group)
+                bulk_g2s(sbase + SM_RING + stage * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)c * 2 * half + (size_t)rank * half,
+                         half, gbar);
             }
-            const int c = 2 * g + sub;
-            if (sub < in_group)
-              bulk_g2s(sbase + SM_RING + stage * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)c * 2 * half + (size_t)rank * half,
-                       half, gbar);
+            if (++stage == kSlots) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kSlots) { stage = 0; phase ^= 1; }
+          src += (size_t)nch * 2 * half;
         }
-        src += (size_t)nch * 2 * half;
       }
+    } else if (kTrain && lane >= 8 && lane < 16) {
+      // ================= stash store lanes: lane 8 + 4 t + a copies atom a of tile slot t after every stashed layer =================
+      const int t = (lane - 8) >> 2, a = (lane - 8) & 3;
+      uint32_t wph = 0;
+      for (int it = 0; it < my_rounds; ++it) {
+        const int64_t tile = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank + t;
+        uint8_t* stash_tile = p.stash + (size_t)tile * kStashTileBytes;
+        for (int s = 0; s < kNumSteps; ++s) {
+          const int atom = c_step_stash_atom[s];
+          if (atom < 0 || c_step_epi[s] == EPI_FINAL) continue;   // hv goes out with plain stores from the FINAL epilogue
+          mbar_wait(bar_written + 8 * t, wph);
+          wph ^= 1;
+          bulk_s2g(stash_tile + (size_t)(atom + a) * kAtomBytes, sbase + SM_ACT + t * kActBytes + a * kAtomBytes, kAtomBytes);
+          bulk_commit();
+          bulk_wait_read0();                                      // the copy has finished READING the tile
+          mbar_arrive(bar_free + 8 * t);
+        }
+      }
+      bulk_wait0();                                               // every stash store has landed before the kernel exits
     }
   } else if (warp == 1 && rank != 0) {
     // ================= peer CTA: relay "my half landed" to the leader =================
@@ -498,145 +570,647 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
       }
     }
   } else {
-    // ================= prologue + epilogue warps: 8 per tile =================
-    // warp (q, cg): TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column half cg (columns 128cg..128cg+127)
+    // ================= prologue + epilogue warps: all 16 on tile slot 0, then on tile slot 1 =================
+    // warp (q, cq): TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq (columns 64cq..64cq+63 = atom cq)
     const int ew = warp - 2;
-    const int t = ew >> 3;                               // tile slot 0/1
-    const int cg = (ew >> 2) & 1;
+    const int cq = ew >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;                         // row inside the tile
-    const int tix = cg * 128 + r;                        // 0..255 inside the tile's epilogue group
-    uint8_t* act = smem + SM_ACT + t * kActBytes;
-    const uint32_t act_a = sbase + SM_ACT + t * kActBytes;
+    const int tix = cq * 128 + r;                        // 0..511 inside the epilogue group
     const uint32_t rx = (uint32_t)(r & 7) << 4;
-    const uint32_t row_a = act_a + (uint32_t)cg * 2u * kAtomBytes + (uint32_t)r * 128u;   // this thread's row, its column half
-    const uint32_t bias_row = sbase + SM_BIAS + (uint32_t)t * 1024u;
-    const uint32_t wa_a = sbase + SM_WA + (uint32_t)cg * 256u;
-    const uint32_t wr_a = act_a + 2 * kAtomBytes;        // FINAL step: Wr [3][128] fp32 staged in the (dead) tile
-    float4* xchg = reinterpret_cast<float4*>(act + 3 * kAtomBytes);   // FINAL-step scratch (tile is dead by then)
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-    const bool store_lane = kTrain && lane == 0 && cg == 0;          // issues this warp's 16 KB stash stores
-    const uint32_t act_leader = mapa_cluster(bar_act + 8 * t, 0);    // the leader's "A tile written" barrier for slot t
-    uint32_t acc_phase = 0;
-    for (int it = 0; it < my_rounds; ++it) {
-      const int64_t tile = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank + t;
-      const int64_t row = tile * kTileM + r;
-      const bool live = row < p.m;
-      uint8_t* stash_tile = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
-      // ---- prologue: sample point -> gamma(pts) -> A atom 0, one 32-element half per column half.
-      //      Only the 3-D point / direction stay in registers; encodings are re-derived when a pass needs them.
-      float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
-      if (live) fetch_sample(p.src, row, pt, dir);
-      {
-        uint32_t w[16];
-        if (cg == 0) encode_pts_half<0>(pt, w); else encode_pts_half<1>(pt, w);
-        store_enc_chunks<16, 4, kTrain>(w, 4 * cg, live, act_a, stash_tile + (size_t)SA_ENC * kAtomBytes, r);
+    const uint32_t bias_base = sbase + SM_BIAS;          // 512 floats: bias row of step s at (s & 1) * 1024; FINAL: Wr [3][128] + bv [128]
+    const uint32_t wa_a = sbase + SM_WA + (uint32_t)cq * 128u;
+    const uint32_t act_leader = mapa_cluster(bar_act, 0);            // the leader's "A tile written" barriers
+    // per-slot state as bit t of a word (the slot loop is not unrolled: one copy of the epilogue code)
+    uint32_t acc_ph = 0, free_ph = 0, pend = 0;          // pend: a stash copy of slot t's tile may still be reading it
+    float alpha0 = 0.0f, alpha1 = 0.0f;                  // this column quarter's partial of the sigma head, per slot
+    auto wait_tile_free = [&](const int t) {
+      if (kTrain && ((pend >> t) & 1u)) {
+        mbar_wait(bar_free + 8 * t, (free_ph >> t) & 1u);
+        free_ph ^= 1u << t;
+        pend &= ~(1u << t);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(act_leader);
-      float alpha = 0.0f;                                // this half's partial of the sigma head
-      int pending_atom = -1;                             // stash atom of the layer output still to be streamed out
+    };
+    for (int it = 0; it < my_rounds; ++it) {
+      const int64_t tile0 = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank;
+      // ---- prologue: sample point -> gamma(pts) -> A atom 0 of both slots, one quarter (16 values, 2 chunks) per thread.
+      //      Nothing of the sample stays in registers: the second passes re-fetch the 24 bytes and re-derive their encoding.
+      //      Step 0's bias row is staged here (row 0 was last read by the previous round's FINAL, which ends in a barrier).
+      if (tix < 256) sts32f(bias_base + 4 * tix, __ldg(cst + c_step_bias[0] + tix));
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int64_t row = (tile0 + t) * kTileM + r;
+        const bool live = row < p.m;
+        float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+        if (live) fetch_sample(p.src, row, pt, dir);
+        uint32_t w[8];
+        encode_pts_quarter(cq, pt, w);
+        wait_tile_free(t);
+        store_enc_chunks<8, 2, kTrain>(w, 2 * cq, live, sbase + SM_ACT + t * kActBytes,
+                                       kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes + (size_t)SA_ENC * kAtomBytes : nullptr, r);
+        tcgen05_fence_before_sync();                     // the previous round's FINAL read this slot's accumulator
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(act_leader + 8 * t);
+      }
+      alpha0 = 0.0f; alpha1 = 0.0f;
+#pragma unroll 1
       for (int s = 0; s < kNumSteps; ++s) {
         const int epi = c_step_epi[s];
-        // (1) the whole group has finished the previous epilogue: its bias row is free, its output tile complete
-        named_bar_sync(1 + t, kEpiThreads);
-        if (kTrain && pending_atom >= 0 && store_lane) {      // one 16 KB atom per warp: bulk-copy issue is serialised per thread
-          bulk_s2g(stash_tile + (size_t)(pending_atom + q) * kAtomBytes, act_a + q * kAtomBytes, kAtomBytes);
-          bulk_commit();
+        // (1) once per step: every warp has finished the previous step's epilogues, so the bias row of step s+1 (which
+        //     shares its buffer with step s-1) may be staged; it becomes visible with the barrier of step s+1.  There is
+        //     no L1 left with 227 KB carved out, so reading biases straight from global would cost an L2 trip per value.
+        named_bar_sync(1, kFwdEpiThreads);
+        if (s + 1 < kNumSteps) {
+          const int en = c_step_epi[s + 1];
+          if (en == EPI_FINAL) {                          // both rows: Wr [3][128] at 0, bv [128] at 384 (step 10 reads no bias)
+            sts32f(bias_base + 4 * tix, __ldg(cst + (tix < 384 ? C_WR + tix : C_BV + (tix - 384))));
+          } else if (en == EPI_RELU || en == EPI_RELU_ALPHA || en == EPI_LINEAR) {
+            if (tix < 256) sts32f(bias_base + (uint32_t)((s + 1) & 1) * 1024u + 4 * tix, __ldg(cst + c_step_bias[s + 1] + tix));
+          }
         }
-        // (2) everything that can be done while this step's MMAs are still running: bias row -> shared memory (there
-        //     is no L1 left with 227 KB carved out, so a __ldg costs an L2 round trip), encodings, head weights
-        uint32_t encw[16];
-        float wr0 = 0.f, wr1 = 0.f;
-        float4 brba = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (epi == EPI_WRITE_ENC) {
-          if (cg == 0) encode_pts_half<0>(pt, encw); else encode_pts_half<1>(pt, encw);
-        } else if (epi == EPI_WRITE_DENC) {
-          if (cg == 1) encode_point<4, 16>(dir, encw);
-        } else {
-          sts32f(bias_row + 4 * tix, __ldg(cst + c_step_bias[s] + (epi == EPI_FINAL ? (tix & 127) : tix)));
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t act_a = sbase + SM_ACT + t * kActBytes;
+          const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+          uint8_t* const stash_tile = kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes : nullptr;
+          if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
+            // second-pass operand: re-derived while pass 1 runs, written over atom 0 once pass 1 has finished reading the tile
+            const int64_t row = (tile0 + t) * kTileM + r;
+            const bool live = row < p.m;
+            float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+            if (live) fetch_sample(p.src, row, pt, dir);
+            uint32_t encw[8];
+            if (epi == EPI_WRITE_ENC) {
+              encode_pts_quarter(cq, pt, encw);
+            } else {
+              uint32_t dw[4];
+              encode_dir_quarter(cq, dir, dw);
+              encw[0] = dw[0]; encw[1] = dw[1]; encw[2] = dw[2]; encw[3] = dw[3];
+            }
+            mbar_wait(bar_acc + 8 * t, (acc_ph >> t) & 1u);
+            acc_ph ^= 1u << t;
+            tcgen05_fence_after_sync();
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
+            wait_tile_free(t);
+            if (epi == EPI_WRITE_ENC) {
+              store_enc_chunks<8, 2, false>(encw, 2 * cq, live, act_a, nullptr, r);
+            } else {
+              const uint32_t dw[4] = {encw[0], encw[1], encw[2], encw[3]};
+              store_enc_chunks<4, 1, kTrain>(dw, cq, live, act_a, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
+              if (kTrain)   // wgrad reads all 64 columns of the stashed atom: columns 32..63 are zero padding
+                *reinterpret_cast<uint4*>(stash_tile + (size_t)SA_DENC * kAtomBytes + sw128_off((uint32_t)r, (uint32_t)(4 + cq))) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(act_leader + 8 * t);
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
+            continue;
+          }
+          mbar_wait(bar_acc + 8 * t, (acc_ph >> t) & 1u);
+          acc_ph ^= 1u << t;
+          tcgen05_fence_after_sync();
+          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
           if (epi == EPI_FINAL) {
-            wr0 = __ldg(cst + C_WR + tix);
-            if (tix < 128) wr1 = __ldg(cst + C_WR + 256 + tix);
-            if (cg == 0) brba = make_float4(__ldg(cst + C_BR), __ldg(cst + C_BR + 1), __ldg(cst + C_BR + 2), __ldg(cst + C_BA));
+            // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123); 32 columns per quarter
+            float rgb[3] = {0.f, 0.f, 0.f};
+            uint32_t va[32];
+            tmem_ld32(tmem_lane + cq * 32, va);
+            tmem_ld_wait_dep(va);
+            const uint32_t m0 = epi_final32<kTrain>(va, cq * 32, bias_base + 4 * 384, bias_base, rgb, stash_tile, r);
+            if (kTrain) reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff)[(8 * 128 + r) * 8 + cq] = m0;
+            // partials of the four column quarters meet in the (dead) tile: atoms 1-3 were last read by step 10's MMAs
+            float4* xchg = reinterpret_cast<float4*>(smem + SM_ACT + t * kActBytes + kAtomBytes);
+            const float al = t ? alpha1 : alpha0;
+            if (cq != 0) xchg[(cq - 1) * 128 + r] = make_float4(rgb[0], rgb[1], rgb[2], al);
+            tcgen05_fence_before_sync();
+            named_bar_sync(1, kFwdEpiThreads);
+            const int64_t row = (tile0 + t) * kTileM + r;
+            if (cq == 0 && row < p.m) {
+              const float4 o1 = xchg[r], o2 = xchg[128 + r], o3 = xchg[256 + r];
+              *reinterpret_cast<float4*>(p.raw + row * 4) =
+                  make_float4(rgb[0] + o1.x + o2.x + o3.x + __ldg(cst + C_BR), rgb[1] + o1.y + o2.y + o3.y + __ldg(cst + C_BR + 1),
+                              rgb[2] + o1.z + o2.z + o3.z + __ldg(cst + C_BR + 2), al + o1.w + o2.w + o3.w + __ldg(cst + C_BA));
+            }
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
+            continue;   // next arrival on act_ready comes from the next round's prologue
           }
-        }
-        if (store_lane && pending_atom >= 0) bulk_wait_read0();   // the stash store has finished READING the tile
-        pending_atom = -1;
-        named_bar_sync(1 + t, kEpiThreads);                   // bias row visible, tile free to overwrite after the MMAs
-        mbar_wait(bar_acc + 8 * t, acc_phase);
-        acc_phase ^= 1;
-        tcgen05_fence_after_sync();
-        if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
-        if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
-          // pass 1 has finished reading the tile: overwrite atom 0 with the second-pass operand
-          if (epi == EPI_WRITE_ENC) store_enc_chunks<16, 4, false>(encw, 4 * cg, live, act_a, nullptr, r);
-          else if (cg == 1) store_enc_chunks<16, 8, kTrain>(encw, 0, live, act_a, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
-          fence_proxy_async_smem();
+          // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
+          uint32_t mk0, mk1;
+          {
+            const uint32_t my_bias = bias_base + (uint32_t)(s & 1) * 1024u + (uint32_t)cq * 256u;
+            const uint32_t my_tmem = tmem_lane + (uint32_t)cq * 64u;
+            const uint32_t row_a = act_a + (uint32_t)cq * kAtomBytes + (uint32_t)r * 128u;   // this thread's row of atom cq
+            long long* etr = (tix == 0 && tracing && it < kTraceRounds) ? p.trace + ((it * 12 + s) * 2 + t) * kTraceEvents : nullptr;
+            uint32_t va[32], vb[32];
+            tmem_ld32(my_tmem, va);
+            tmem_ld32(my_tmem + 32, vb);
+            tmem_ld_wait_dep(va);
+            tmem_ld_wait_dep(vb);
+            if (etr) etr[16] = clock64();
+            wait_tile_free(t);
+            float al = 0.0f;
+            if (epi == EPI_RELU) {
+              mk0 = epi_cols32<kTrain, 0>(va, 0, my_bias, wa_a, al, row_a, rx);
+              mk1 = epi_cols32<kTrain, 0>(vb, 32, my_bias, wa_a, al, row_a, rx);
+            } else if (epi == EPI_RELU_ALPHA) {
+              mk0 = epi_cols32<kTrain, 1>(va, 0, my_bias, wa_a, al, row_a, rx);
+              mk1 = epi_cols32<kTrain, 1>(vb, 32, my_bias, wa_a, al, row_a, rx);
+              if (t) alpha1 = al; else alpha0 = al;
+            } else {
+              mk0 = epi_cols32<kTrain, 2>(va, 0, my_bias, wa_a, al, row_a, rx);
+              mk1 = epi_cols32<kTrain, 2>(vb, 32, my_bias, wa_a, al, row_a, rx);
+            }
+            if (etr) etr[18] = clock64();
+            tcgen05_fence_before_sync();
+            fence_proxy_async_smem();
+            if (etr) etr[19] = clock64();
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(act_leader);
-          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-          continue;
-        }
-        if (epi == EPI_FINAL) {
-          // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123); 64 columns per half
-          sts32f(wr_a + 4 * tix, wr0);
-          if (tix < 128) sts32f(wr_a + 4 * (256 + tix), wr1);
-          named_bar_sync(1 + t, kEpiThreads);
-          float rgb[3] = {0.f, 0.f, 0.f};
-          const int c0 = cg * 64;
-          uint32_t va[32], vb[32];
-          tmem_ld32(tmem_lane + c0, va);
-          tmem_ld32(tmem_lane + c0 + 32, vb);
-          tmem_ld_wait_dep(va);
-          tmem_ld_wait_dep(vb);
-          const uint32_t m0 = epi_final32<kTrain>(va, c0, bias_row, wr_a, rgb, stash_tile, r);
-          const uint32_t m1 = epi_final32<kTrain>(vb, c0 + 32, bias_row, wr_a, rgb, stash_tile, r);
-          if (kTrain) {
-            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (8 * 128 + r) * 8 + cg * 2;
-            *reinterpret_cast<uint2*>(mrow) = make_uint2(m0, m1);
+          if (lane == 0) {
+            mbar_arrive_cluster(act_leader + 8 * t);
+            if (kTrain) mbar_arrive(bar_written + 8 * t);
           }
-          if (cg == 1) xchg[r] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
-          tcgen05_fence_before_sync();
-          named_bar_sync(1 + t, kEpiThreads);
-          if (cg == 0 && live) {
-            const float4 o = xchg[r];
-            *reinterpret_cast<float4*>(p.raw + row * 4) =
-                make_float4(rgb[0] + o.x + brba.x, rgb[1] + o.y + brba.y, rgb[2] + o.z + brba.z, alpha + o.w + brba.w);
-          }
+          if (kTrain) pend |= 1u << t;
           if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-          continue;   // next arrival on act_ready comes from the next tile's prologue
+          // the mask words go out AFTER the hand-over: a global store in front of it sat ~900 cycles on the critical path
+          if (kTrain && c_step_mask_slot[s] >= 0)
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cq * 2) =
+                make_uint2(mk0, mk1);
         }
-        // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
-        uint32_t mk[4];
-        const uint32_t my_bias = bias_row + (uint32_t)cg * 512u;
-        const uint32_t my_tmem = tmem_lane + (uint32_t)cg * 128u;
-        long long* etr = (tix == 0 && tracing && it < kTraceRounds) ? p.trace + ((it * 12 + s) * 2 + t) * kTraceEvents : nullptr;
-        if (epi == EPI_RELU) epi_layer<kTrain, 0>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
-        else if (epi == EPI_RELU_ALPHA) epi_layer<kTrain, 1>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
-        else epi_layer<kTrain, 2>(my_tmem, my_bias, wa_a, alpha, row_a, rx, mk, etr);
-        tcgen05_fence_before_sync();
-        if (etr) etr[22] = clock64();
-        fence_proxy_async_smem();
-        if (etr) etr[23] = clock64();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(act_leader);
-        if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-        // the mask words go out AFTER the hand-over: a global store in front of it sat ~900 cycles on the critical path
-        if (kTrain && c_step_mask_slot[s] >= 0) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cg * 4;
-          *reinterpret_cast<uint4*>(mrow) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-        }
-        if (kTrain) pending_atom = c_step_stash_atom[s];
       }
     }
-    if (store_lane) bulk_wait0();   // every stash store has landed before the kernel exits
   }
 
   __syncwarp();                     // single-lane roles rejoin their warp before the aligned cluster barrier
   tcgen05_fence_before_sync();
   cluster_sync_all();               // nobody signals into a CTA that has exited; all MMAs of the pair have completed
+  if (warp == 1) {
+    tcgen05_fence_after_sync();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================================
+// "TS" forward kernel: activations never touch shared memory.
+//
+// What bounded the kernel above (profiles/r02b_trace_*.txt): with both operands in shared memory every MMA reads 8 KB per SM
+// (A 4 KB + its half of B 4 KB = 64 B/cycle), the epilogue writes the next A tile back (64 KB per tile and layer) and reads the
+// bias row, the ring is refilled and — in training — the TMA store reads the tile once more: ~2050 (inference) / ~2560 (training)
+// cycles of the 128 B/cycle shared-memory pipe per tile and layer against 2048 cycles of MMA, so the MMAs ran at ~178 instead of
+// 128 cycles however the epilogue was organised.  Here the A operand lives in TENSOR MEMORY (tcgen05.mma with A in TMEM): the
+// epilogue writes relu(acc + b) as packed bf16 straight back to TMEM with tcgen05.st and the next layer's MMAs read it from
+// there.  Shared memory carries only the weights (B: 32 B/cycle), the 64-wide encodings and, in training, the staging of the
+// stash copies.  TMEM budget (512 columns): two 128x128 fp32 accumulators X, Y (N is split in halves so that an accumulator
+// half drains while the other half's MMAs run) + the two tile slots' activations A0, A1 (256 bf16 per row = 128 columns each).
+//
+// Per 256-wide layer the tensor pipe runs four batches back to back: (slot 0, half a) -> X, (0, b) -> Y, (1, a) -> X, (1, b) -> Y,
+// each 16 MMAs of M = 256 (pair) x N = 128 x K = 16.  All 16 epilogue warps follow the same order:
+//   acc_full[X]: tcgen05.ld 32 columns -> arrive acc_free[X] at once (the accumulator is in registers) -> bias/ReLU/pack -> keep
+//   acc_full[Y] (all MMAs that read the slot's old activations are done): tcgen05.st both halves into A_t -> arrive a_ready[t]
+// so every hand-over has a full batch (1024 cycles) of slack.  With the round-1 weight packing (each CTA holds output rows
+// 128c..128c+127 of a chunk) half h takes rows 64h..64h+63 of both CTAs: accumulator column j of half h is output feature
+// 64h + (j & 63) + 128 (j >> 6) — a permutation the epilogue undoes when it picks bias, TMEM columns and stash atoms.
+// =====================================================================================================================
+constexpr int kTsSlots = 4;                                  // ring: 4 groups of two 16 KB half-chunks = 2 layers resident
+constexpr int TS_RING = 0;
+constexpr int TS_GAMMA = kTsSlots * kSlotBytes;              // 2 x 16 KB: gamma(pts) / gamma(dir) atom of each tile slot (SS operand)
+constexpr int TS_STAGE = TS_GAMMA + 2 * kAtomBytes;          // training: 2 x 32 KB staging of a half layer (2 atoms) for the stash copies
+constexpr int TS_BAR = TS_STAGE + 4 * kAtomBytes;            // = 229376
+constexpr int TS_TMEMPTR = TS_BAR + 240;
+constexpr int TS_BIAS = TS_BAR + 256;                        // 2 rows of 256 floats (layer parity)
+constexpr int TS_WA = TS_BIAS + 2048;                        // sigma-head weights, 256 x bf16
+constexpr int kTsSmemBytes = TS_WA + 512;                    // 232192
+static_assert(kTsSmemBytes <= 232448, "shared memory budget");
+constexpr int kTsLayers = 10;
+__constant__ int c_l_step0[kTsLayers] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10};     // first step (mlp step table) of each layer
+__constant__ int c_l_parts[kTsLayers] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 2};      // layer 5 = h part + gamma(pts) part, views = feature part + gamma(dir) part
+// weight groups of a round in ring order (two 64-wide K chunks each); three empty groups pad the sequence to 6 revolutions of
+// the 4-slot ring so that every layer starts in slot 0 or 2:  L0 | - | L1 L1 | L2 L2 | L3 L3 | L4 L4 | L5 L5 | L5g | - | L6 L6 |
+// L7 L7 | feat feat | views views | views-dir | -
+constexpr int kTsGroups = 24;
+__constant__ int c_g_nch[kTsGroups] = {1, 0, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 0, 2, 2, 2, 2, 2, 2, 2, 2, 1, 0};
+__constant__ int c_g_half[kTsGroups] = {16384, 0, 16384, 16384, 16384, 16384, 16384, 16384, 16384, 16384, 16384, 16384, 16384, 0,
+                                        16384, 16384, 16384, 16384, 16384, 16384, 8192, 8192, 8192, 0};
+enum TsLayerKind : int { LK_L0 = 0, LK_WIDE = 1, LK_L5 = 2, LK_VIEWS = 3 };
+__constant__ int c_l_kind[kTsLayers] = {LK_L0, LK_WIDE, LK_WIDE, LK_WIDE, LK_WIDE, LK_L5, LK_WIDE, LK_WIDE, LK_WIDE, LK_VIEWS};
+__constant__ int c_l_group0[kTsLayers] = {0, 2, 4, 6, 8, 10, 14, 16, 18, 20};   // first group of the layer in the round's sequence
+
+// 32 accumulator columns = 32 consecutive output features: h = acc + bias (ReLU), packed bf16 -> out[16] (the TMEM image of the
+// next A operand) and, in training, the staging tile of the stash copy; returns the 32 ReLU mask bits (relu_mask_push layout).
+// MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
+template <bool kTrain, int MODE>
+__device__ __forceinline__ uint32_t epi32_ts(const uint32_t (&v)[32], const uint32_t bias_a, const uint32_t wa_a, float& alpha,
+                                             uint32_t (&out)[16], const uint32_t stage_row, const uint32_t chunk0, const uint32_t rx) {
+  uint32_t mb = 0;
+  float4 nb0 = lds128f(bias_a), nb1 = lds128f(bias_a + 16);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = g * 8;
+    const float4 b0 = nb0, b1 = nb1;
+    if (g < 3) { nb0 = lds128f(bias_a + (c + 8) * 4); nb1 = lds128f(bias_a + (c + 8) * 4 + 16); }
+    const float2 h01 = __fadd2_rn(make_float2(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1])), make_float2(b0.x, b0.y));
+    const float2 h23 = __fadd2_rn(make_float2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), make_float2(b0.z, b0.w));
+    const float2 h45 = __fadd2_rn(make_float2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])), make_float2(b1.x, b1.y));
+    const float2 h67 = __fadd2_rn(make_float2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])), make_float2(b1.z, b1.w));
+    float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
+    if (MODE == 1) {
+      const uint4 wq = lds128u(wa_a + c * 2);       // 8 bf16 sigma weights
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        h[e] = fmaxf(h[e], 0.f); h[e + 1] = fmaxf(h[e + 1], 0.f);
+        alpha = fmaf(h[e], __uint_as_float(ww[e / 2] << 16), alpha);
+        alpha = fmaf(h[e + 1], __uint_as_float(ww[e / 2] & 0xffff0000u), alpha);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      out[4 * g + e] = (MODE == 0) ? pack_relu_bf16(h[2 * e], h[2 * e + 1]) : pack_bf16(h[2 * e], h[2 * e + 1]);
+    if (kTrain) {
+      if (MODE != 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mb = relu_mask_push(mb, out[4 * g + e]);
+      }
+      sts128(stage_row + (((chunk0 + (uint32_t)g) << 4) ^ rx), out[4 * g], out[4 * g + 1], out[4 * g + 2], out[4 * g + 3]);
+    }
+  }
+  return mb;
+}
+
+template <bool kTrain>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp_fwd_ts_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index the compiler can prove uniform
+  const uint32_t rank = uniform_u32(cluster_ctarank());   // 0: leader (issues the pair's MMAs)
+  if (smem != smem_raw) __trap();                   // no alignment slack in kTsSmemBytes
+  // barriers: full[4] / empty[4] per ring slot (slot s is used once per revolution: parity = revolution & 1),
+  //   acc_full[2] (commit after each batch), acc_free[2] (32 warps: accumulator loaded into registers, leader only),
+  //   a_ready[2] (32 warps: slot t's activations / gamma atom written, leader only),
+  //   written[2] / free[2] (training: staging buffer h filled by the 16 warps / copied out by its two store lanes)
+  const uint32_t bar_full = sbase + TS_BAR, bar_empty = bar_full + 8 * kTsSlots;
+  const uint32_t bar_accfull = bar_empty + 8 * kTsSlots, bar_accfree = bar_accfull + 16, bar_aready = bar_accfree + 16;
+  const uint32_t bar_written = bar_aready + 16, bar_free = bar_written + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + TS_TMEMPTR);
+  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTsSlots; ++s) { mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_full + 8 * s, rank == 0 ? 2 : 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_accfull + 8 * t, 1);
+      mbar_init(bar_accfree + 8 * t, 2 * kFwdEpiWarps);
+      mbar_init(bar_aready + 8 * t, 2 * kFwdEpiWarps);
+      mbar_init(bar_written + 8 * t, kFwdEpiWarps);
+      mbar_init(bar_free + 8 * t, 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc2(smem_u32(tmem_ptr_smem), 512); tmem_relinquish2(); }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // sigma-head weights as bf16, read by the layer-7 epilogues
+    const int i = threadIdx.x - 64;
+    const __nv_bfloat16 w = __float2bfloat16_rn(__ldg(cst + C_WA + i));
+    sts16(sbase + TS_WA + 2 * i, *reinterpret_cast<const uint16_t*>(&w));
+  }
+  tcgen05_fence_before_sync();
+  cluster_sync_all();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kAccCols = 128, kA0 = 256;     // X at +0, Y at +128, A_t at +256 + 128 t
+
+  const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+  const int my_rounds = (p.num_quads - cid + ncl - 1) / ncl;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+
+  if (warp == 0) {
+    if (lane < 2 * kTsSlots) {
+      // ================= weight producer: this CTA's half of every chunk, groups of two chunks per ring slot =================
+      // The group sequence of a round is padded to 24 (c_g_nch: three empty groups), so every group sits in a ring slot that is
+      // known at compile time (the MMA issuer addresses the ring with immediates) and slot s is used once per revolution.
+      const int slot = lane & 3, sub = lane >> 2;                  // lane (slot, sub) copies chunk `sub` of the groups in `slot`
+      for (int it = 0; it < my_rounds; ++it) {
+        const uint8_t* src = p.packed;
+        for (int g = 0; g < kTsGroups; ++g) {
+          const int nch = c_g_nch[g];
+          const uint32_t half = (uint32_t)c_g_half[g];
+          if ((g & 3) == slot) {
+            const uint32_t rev = (uint32_t)(it * (kTsGroups / 4) + (g >> 2));
+            mbar_wait(bar_empty + 8 * slot, (rev & 1u) ^ 1u);      // both lanes of the slot wait for every release
+            if (sub == 0) {
+              if (nch) mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)nch * half);
+              else mbar_arrive(bar_full + 8 * slot);               // empty group: the barrier still advances one phase per revolution
+            }
+            if (sub < nch)
+              bulk_g2s(sbase + TS_RING + slot * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)sub * 2 * half + (size_t)rank * half, half,
+                       bar_full + 8 * slot);
+          }
+          src += (size_t)nch * 2 * half;
+        }
+      }
+    } else if (kTrain && lane >= 8 && lane < 12) {
+      // ================= stash store lanes: lane 8 + 2 h + sa copies staging atom sa of buffer h after every half epilogue =================
+      const int h = (lane - 8) >> 1, sa = (lane - 8) & 1;
+      uint32_t wph = 0;
+      for (int it = 0; it < my_rounds; ++it) {
+        const int64_t tile0 = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank;
+        for (int L = 0; L < kTsLayers - 1; ++L) {
+          const int atom0 = c_step_stash_atom[c_l_step0[L] + c_l_parts[L] - 1];
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(bar_written + 8 * h, wph);
+            wph ^= 1;
+            if (!(p.debug & 4)) {
+              bulk_s2g(p.stash + (size_t)(tile0 + t) * kStashTileBytes + (size_t)(atom0 + 2 * sa + h) * kAtomBytes,
+                       sbase + TS_STAGE + (uint32_t)(2 * h + sa) * kAtomBytes, kAtomBytes);
+              bulk_commit();
+              if (!(p.debug & 1)) bulk_wait_read0();
+            }
+            mbar_arrive(bar_free + 8 * h);
+          }
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp == 1 && rank != 0) {
+    if (lane == 0) {   // ================= peer CTA: relay "my halves landed" to the leader =================
+      const uint32_t full_leader = mapa_cluster(bar_full, 0);
+      for (int it = 0; it < my_rounds; ++it)
+        for (int g = 0; g < kTsGroups; ++g) {
+          mbar_wait(bar_full + 8 * (g & 3), (uint32_t)(it * (kTsGroups / 4) + (g >> 2)) & 1u);
+          mbar_arrive_cluster(full_leader + 8 * (g & 3));
+        }
+    }
+  } else if (warp == 1) {
+    // ================= leader CTA: MMA issuer for the pair — the whole warp, uniform control flow (tc_common.cuh: elect_one) =================
+    // Ring slots, chunk offsets and TMEM columns are immediates relative to three uniform bases (ring descriptor, gamma-atom
+    // descriptor, TMEM base): an MMA costs two uniform adds.
+    uint32_t batch = 0, ar_ph = 0, af_n0 = 0, af_n1 = 0;
+    const uint32_t idesc = make_idesc(2 * kTileM, 128, 0, 0);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t ring_desc = make_smem_desc(sbase + TS_RING, 16, 1024);     // slot s: + 2048 s, chunk c of a group: + 1024 c, half h: + 512 h
+    const uint64_t gam_desc = make_smem_desc(sbase + TS_GAMMA, 16, 1024);     // tile slot t: + 1024 t
+    auto full_wait = [&](const int slot, const uint32_t rev) {
+      mbar_wait_cluster(bar_full + 8 * slot, rev & 1u);
+      tcgen05_fence_after_sync();
+    };
+    auto empty_commit = [&](const int slot) {
+      if (elect_one()) umma_commit_2cta(bar_empty + 8 * slot, 3);
+    };
+    for (int it = 0; it < my_rounds; ++it) {
+      const uint32_t rev0 = (uint32_t)(it * (kTsGroups / 4));
+#pragma unroll 1
+      for (int L = 0; L < kTsLayers; ++L) {
+        const int kind = c_l_kind[L];
+        const int g0 = c_l_group0[L];
+        const int s0 = g0 & 3;                               // first ring slot of the layer (0 or 2)
+        const uint32_t rev = rev0 + (uint32_t)(g0 >> 2);
+        const int nb = kind == LK_VIEWS ? 2 : 4;
+        full_wait(s0, rev);                                  // the layer's first group, prefetched a layer ahead
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+          const int t = kind == LK_VIEWS ? b : (b >> 1), h = kind == LK_VIEWS ? 0 : (b & 1);
+          const bool first = b == 0, last = b == nb - 1;
+          const uint32_t acc = batch & 1u;
+          ++batch;
+          if (h == 0) {                                      // slot t's activations (and gamma atom) of both CTAs are written
+            mbar_wait_cluster(bar_aready + 8 * t, (ar_ph >> t) & 1u);
+            ar_ph ^= 1u << t;
+          }
+          {                                                  // accumulator `acc` is in the epilogue's registers
+            const uint32_t n = acc ? af_n1 : af_n0;
+            mbar_wait_cluster(bar_accfree + 8 * acc, (n & 1u) ^ 1u);
+            if (acc) ++af_n1; else ++af_n0;
+          }
+          tcgen05_fence_after_sync();
+          if (tracing && lane == 0) trace_stamp(p.trace, it, c_l_step0[L] + c_l_parts[L] - 1, t, h);
+          const uint32_t d_tmem = tmem_u + acc * kAccCols;
+          const uint32_t a_tmem = tmem_u + kA0 + (uint32_t)t * 128u;
+          const uint64_t a_gam = gam_desc + (uint64_t)(1024 * t);
+          const uint64_t b_desc = ring_desc + (uint64_t)(2048 * s0 + 512 * h);
+          if (kind == LK_L0) {
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+            }
+            if (last) { empty_commit(0); empty_commit(1); }
+          } else {
+            // four 64-wide K chunks from the slot's activations in TMEM: two ring slots of two chunks
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                umma_bf16_ts_2cta(d_tmem, a_tmem + (uint32_t)(8 * j), b_desc + (uint64_t)(1024 * (j >> 2) + 2 * (j & 3)), idesc, j ? 1u : 0u);
+            }
+            if (last) empty_commit(s0);
+            if (first) full_wait(s0 + 1, rev);
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                umma_bf16_ts_2cta(d_tmem, a_tmem + (uint32_t)(64 + 8 * j), b_desc + (uint64_t)(2048 + 1024 * (j >> 2) + 2 * (j & 3)), idesc, 1u);
+            }
+            if (last) empty_commit(s0 + 1);
+            if (kind == LK_L5) {                             // + gamma(pts) part of the skip layer: ring slot 0 of the next revolution
+              if (first) full_wait(0, rev + 1);
+              const uint64_t bg = ring_desc + (uint64_t)(512 * h);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), bg + (uint64_t)(2 * k), idesc, 1u);
+              }
+              if (last) { empty_commit(0); empty_commit(1); }
+            } else if (kind == LK_VIEWS) {                   // + gamma(dir) part (K = 32): ring slot 2
+              if (first) full_wait(2, rev);
+              const uint64_t bg = ring_desc + (uint64_t)(2048 * 2);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), bg + (uint64_t)(2 * k), idesc, 1u);
+              }
+              if (last) { empty_commit(2); empty_commit(3); }
+            }
+          }
+          if (elect_one()) umma_commit_2cta(bar_accfull + 8 * acc, 3);
+          if (tracing && lane == 0) trace_stamp(p.trace, it, c_l_step0[L] + c_l_parts[L] - 1, t, 2 + h);
+        }
+      }
+    }
+  } else {
+    // ================= prologue + epilogue warps (all 16 follow the batch order of the tensor pipe) =================
+    // warp (q, cq): TMEM lane quarter q = warp % 4 (rows 32q..32q+31), accumulator columns 32cq..32cq+31 of every half
+    const int ew = warp - 2;
+    const int cq = ew >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int tix = cq * 128 + r;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t bias_base = sbase + TS_BIAS;
+    const uint32_t accfree_leader = mapa_cluster(bar_accfree, 0), aready_leader = mapa_cluster(bar_aready, 0);
+    const int fsub = 32 * (cq & 1) + 128 * (cq >> 1);    // output feature of this thread's first column: 64 h + fsub
+    uint32_t full_ph = 0, free_ph = 0, pend = 0, batch = 0;
+    for (int it = 0; it < my_rounds; ++it) {
+      const int64_t tile0 = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank;
+      // ---- prologue: gamma(pts) -> the slot's gamma atom (SS operand of layers 0 and 5), one quarter per thread; layer 0's bias row.
+      //      The previous round's FINAL used the gamma atoms as scratch: everybody is through with it first.
+      if (it > 0) named_bar_sync(1, kFwdEpiThreads);
+      if (tix < 256) sts32f(bias_base + 4 * tix, __ldg(cst + c_step_bias[0] + tix));
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int64_t row = (tile0 + t) * kTileM + r;
+        const bool live = row < p.m;
+        float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+        if (live) fetch_sample(p.src, row, pt, dir);
+        uint32_t w[8];
+        encode_pts_quarter(cq, pt, w);
+        store_enc_chunks<8, 2, kTrain>(w, 2 * cq, live, sbase + TS_GAMMA + t * kAtomBytes,
+                                       kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes + (size_t)SA_ENC * kAtomBytes : nullptr, r);
+        tcgen05_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(aready_leader + 8 * t);
+      }
+      float alpha0 = 0.0f, alpha1 = 0.0f;
+#pragma unroll 1
+      for (int L = 0; L < kTsLayers; ++L) {
+        const int sl = c_l_step0[L] + c_l_parts[L] - 1;   // the layer's last step carries its epilogue / bias / stash entries
+        const int epi = c_step_epi[sl];
+        // once per layer: all warps are through the previous layer's epilogues -> the next layer's bias row (parity buffer) may be staged
+        named_bar_sync(1, kFwdEpiThreads);
+        if (L + 1 < kTsLayers) {
+          const int sn = c_l_step0[L + 1] + c_l_parts[L + 1] - 1;
+          if (tix < (L + 1 == kTsLayers - 1 ? 128 : 256))
+            sts32f(bias_base + (uint32_t)((L + 1) & 1) * 1024u + 4 * tix, __ldg(cst + c_step_bias[sn] + tix));
+        }
+        const uint32_t bias_row = bias_base + (uint32_t)(L & 1) * 1024u;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          uint8_t* const stash_tile = kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes : nullptr;
+          const uint32_t a_tmem = tmem_base + lane_off + kA0 + (uint32_t)t * 128u;
+          if (epi == EPI_FINAL) {
+            // ---- views layer (N = 128, one batch per slot): hv = relu(acc + bv); rgb = Wr hv + br; raw = [rgb, alpha] (helpers:117-123)
+            const uint32_t acc = batch & 1u;
+            ++batch;
+            mbar_wait(bar_accfull + 8 * acc, (full_ph >> acc) & 1u);
+            full_ph ^= 1u << acc;
+            tcgen05_fence_after_sync();
+            // the slot's gamma atom is dead now: Wr [3][128] fp32 is staged in its first 1.5 KB, the partial exchange behind it
+            const uint32_t wr_a = sbase + TS_GAMMA + t * kAtomBytes;
+            if (tix < 384) sts32f(wr_a + 4 * tix, __ldg(cst + C_WR + tix));
+            uint32_t va[32];
+            tmem_ld32(tmem_base + lane_off + acc * kAccCols + cq * 32, va);
+            tmem_ld_wait_dep(va);
+            tcgen05_fence_before_sync();
+            named_bar_sync(1, kFwdEpiThreads);
+            if (lane == 0) mbar_arrive_cluster(accfree_leader + 8 * acc);
+            float rgb[3] = {0.f, 0.f, 0.f};
+            const uint32_t m0 = epi_final32<kTrain>(va, cq * 32, bias_row, wr_a, rgb, stash_tile, r);
+            if (kTrain) reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff)[(8 * 128 + r) * 8 + cq] = m0;
+            float4* xchg = reinterpret_cast<float4*>(smem + TS_GAMMA + t * kAtomBytes + 2048);
+            const float al = t ? alpha1 : alpha0;
+            if (cq != 0) xchg[(cq - 1) * 128 + r] = make_float4(rgb[0], rgb[1], rgb[2], al);
+            named_bar_sync(1, kFwdEpiThreads);
+            const int64_t row = (tile0 + t) * kTileM + r;
+            if (cq == 0 && row < p.m) {
+              const float4 o1 = xchg[r], o2 = xchg[128 + r], o3 = xchg[256 + r];
+              *reinterpret_cast<float4*>(p.raw + row * 4) =
+                  make_float4(rgb[0] + o1.x + o2.x + o3.x + __ldg(cst + C_BR), rgb[1] + o1.y + o2.y + o3.y + __ldg(cst + C_BR + 1),
+                              rgb[2] + o1.z + o2.z + o3.z + __ldg(cst + C_BR + 2), al + o1.w + o2.w + o3.w + __ldg(cst + C_BA));
+            }
+            continue;   // the slot's next a_ready arrival comes from the next round's prologue
+          }
+          // ---- 256-wide layer: half a (accumulator X), then half b (accumulator Y)
+          uint32_t ra[16], rb[16];
+          uint32_t mka, mkb;
+          float al = t ? alpha1 : alpha0;
+          {
+            const uint32_t acc = batch & 1u;
+            ++batch;
+            mbar_wait(bar_accfull + 8 * acc, (full_ph >> acc) & 1u);
+            full_ph ^= 1u << acc;
+            tcgen05_fence_after_sync();
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 4);
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_off + acc * kAccCols + cq * 32, v);
+            tmem_ld_wait_dep(v);
+            tcgen05_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(accfree_leader + 8 * acc);      // the accumulator may be overwritten
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 8);
+            if (kTrain && (pend & 1u)) { mbar_wait(bar_free, free_ph & 1u); free_ph ^= 1u; pend &= ~1u; }
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 9);
+            const uint32_t stage_row = sbase + TS_STAGE + (uint32_t)(cq >> 1) * kAtomBytes + (uint32_t)r * 128u;
+            const uint32_t ba = bias_row + 4u * (uint32_t)fsub, wa = sbase + TS_WA + 2u * (uint32_t)fsub;
+            if (epi == EPI_RELU) mka = epi32_ts<kTrain, 0>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
+            else if (epi == EPI_RELU_ALPHA) mka = epi32_ts<kTrain, 1>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
+            else mka = epi32_ts<kTrain, 2>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 6);
+            if (kTrain) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_written);
+              pend |= 1u;
+            }
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 10);
+          }
+          {
+            const uint32_t acc = batch & 1u;
+            ++batch;
+            mbar_wait(bar_accfull + 8 * acc, (full_ph >> acc) & 1u);   // every MMA that read the slot's old activations has completed
+            full_ph ^= 1u << acc;
+            tcgen05_fence_after_sync();
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 5);
+            tmem_st16(a_tmem + (uint32_t)(fsub >> 1), ra);
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_off + acc * kAccCols + cq * 32, v);
+            tmem_ld_wait_dep(v);
+            tcgen05_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(accfree_leader + 8 * acc);
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 11);
+            if (kTrain && (pend & 2u)) { mbar_wait(bar_free + 8, (free_ph >> 1) & 1u); free_ph ^= 2u; pend &= ~2u; }
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 12);
+            const uint32_t stage_row = sbase + TS_STAGE + (uint32_t)(2 + (cq >> 1)) * kAtomBytes + (uint32_t)r * 128u;
+            const uint32_t ba = bias_row + 4u * (uint32_t)(64 + fsub), wa = sbase + TS_WA + 2u * (uint32_t)(64 + fsub);
+            if (epi == EPI_RELU) mkb = epi32_ts<kTrain, 0>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
+            else if (epi == EPI_RELU_ALPHA) mkb = epi32_ts<kTrain, 1>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
+            else mkb = epi32_ts<kTrain, 2>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
+            tmem_st16(a_tmem + (uint32_t)((64 + fsub) >> 1), rb);
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 13);
+            if (epi == EPI_RELU_ALPHA) { if (t) alpha1 = al; else alpha0 = al; }
+            if (sl == 6) {
+              // the skip layer's MMAs of this slot are done: gamma(pts) -> gamma(dir) in the slot's gamma atom (views layer, K = 32)
+              const int64_t row = (tile0 + t) * kTileM + r;
+              const bool live = row < p.m;
+              float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+              if (live) fetch_sample(p.src, row, pt, dir);
+              uint32_t dw[4];
+              encode_dir_quarter(cq, dir, dw);
+              store_enc_chunks<4, 1, kTrain>(dw, cq, live, sbase + TS_GAMMA + t * kAtomBytes, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
+              if (kTrain)   // wgrad reads all 64 columns of the stashed atom: columns 32..63 are zero padding
+                *reinterpret_cast<uint4*>(stash_tile + (size_t)SA_DENC * kAtomBytes + sw128_off((uint32_t)r, (uint32_t)(4 + cq))) = make_uint4(0, 0, 0, 0);
+            }
+            tmem_st_wait();
+            tcgen05_fence_before_sync();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_cluster(aready_leader + 8 * t);
+              if (kTrain) mbar_arrive(bar_written + 8);
+            }
+            if (kTrain) pend |= 2u;
+            if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 7);
+          }
+          // mask words after the hand-over: word w covers features 32w..32w+31
+          if (kTrain && c_step_mask_slot[sl] >= 0 && !(p.debug & 2)) {
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[sl] * 128 + r) * 8;
+            mrow[fsub >> 5] = mka;
+            mrow[(64 + fsub) >> 5] = mkb;
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before_sync();
+  cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after_sync();
     tmem_dealloc2(tmem_base, 512);
@@ -667,16 +1241,21 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   int64_t tiles = (m + kTileM - 1) / kTileM;
   p.num_quads = (int)((tiles + 3) / 4);
   p.trace = g_trace;
+  static const int fwd_debug = getenv("SPN_FWD_DEBUG") ? atoi(getenv("SPN_FWD_DEBUG")) : 0;
+  p.debug = fwd_debug;
   const int pairs = sm_count() / 2;
   int grid = 2 * (p.num_quads < pairs ? p.num_quads : pairs);
-  auto kern = stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>;
+  // SPN_FWD_TS=0 selects the round-1 organisation (both operands in shared memory) for A/B timing; default: A operand in TMEM
+  static const bool use_ts = !(getenv("SPN_FWD_TS") && atoi(getenv("SPN_FWD_TS")) == 0);
+  auto kern = use_ts ? (stash ? mlp_fwd_ts_kernel<true> : mlp_fwd_ts_kernel<false>) : (stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>);
+  const int smem_bytes = use_ts ? kTsSmemBytes : kSmemBytes;
   static bool attr_set[2] = {false, false};
   if (!attr_set[stash ? 1 : 0]) {
-    SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[stash ? 1 : 0] = true;
   }
   prof_begin(PROF_MLP_FWD, st);
-  kern<<<grid, kPairThreads, kSmemBytes, st>>>(p);
+  kern<<<grid, kPairThreads, smem_bytes, st>>>(p);
   prof_end(PROF_MLP_FWD, st);
   SPN_LAUNCH_CHECK("mlp_fwd_kernel");
   return SPN_OK;
@@ -834,6 +1413,79 @@ __global__ void __launch_bounds__(17 * 32, 1) tmem_ld_rate_kernel(int nwarps, in
     if (!with_mma) out[1] = 0;
   }
   if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- diagnostic: rate of CTA-pair MMAs (cta_group::2, M = 256) with A from shared memory (ts = 0) or from TMEM (ts = 1), -------
+// round-robin over `nacc` accumulators; `ld_warps` warps of both CTAs meanwhile drain / refill OTHER TMEM columns the way
+// the TS epilogue does (tcgen05.ld 32 columns, tcgen05.st 16 columns).  out[0] = cycles for `reps` MMAs (leader thread).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(17 * 32, 1)
+mma_rate_pair_kernel(int ts, int n, int reps, int nacc, int ld_warps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t bar = sbase + 64 * 1024;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 64 * 1024 + 64);
+  volatile int* stop = reinterpret_cast<volatile int*>(smem + 64 * 1024 + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); *stop = 0; }
+  if (warp == 0) { tmem_alloc2(smem_u32(tptr), 512); tmem_relinquish2(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before_sync();
+  cluster_sync_all();
+  tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  if (warp == 16) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(256, n, 0, 0);
+      const uint64_t a0 = make_smem_desc(sbase, 16, 1024), b0 = make_smem_desc(sbase + 32768, 16, 1024);
+      const long long t0 = clock64();
+      for (int i = 0; i < reps; ++i) {
+        const uint32_t d = tmem_base + (uint32_t)(i % nacc) * (uint32_t)n;
+        if (ts) umma_bf16_ts_2cta(d, tmem_base + 384u + (uint32_t)(8 * (i & 15)), b0 + (uint64_t)(2 * (i & 3)), idesc, 1);
+        else umma_bf16_2cta(d, a0 + (uint64_t)(2 * (i & 3)), b0 + (uint64_t)(2 * (i & 3)), idesc, 1);
+      }
+      umma_commit_2cta(bar, 3);
+      mbar_wait(bar, 0);
+      out[0] = clock64() - t0;
+      *stop = 1;
+      *reinterpret_cast<volatile int*>(smem + 64 * 1024 + 132) = 1;
+    } else if (lane == 0) {
+      mbar_wait(bar, 0);
+      *stop = 1;
+    }
+  } else if (warp < ld_warps) {
+    // epilogue-like TMEM traffic on columns 256..383 (never touched by the MMAs above when n * nacc <= 256)
+    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + (uint32_t)((warp >> 2) & 3) * 32u;
+    uint32_t acc = 0;
+    while (!*stop) {
+      uint32_t v[32], w[16];
+      tmem_ld32(ta, v);
+      tmem_ld_wait_dep(v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { w[j] = v[2 * j] + v[2 * j + 1]; acc ^= w[j]; }
+      tmem_st16(ta, w);
+      tmem_st_wait();
+    }
+    if (acc == 0x1234567u) out[1] = 1;
+  }
+  __syncwarp();
+  tcgen05_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) { tcgen05_fence_after_sync(); tmem_dealloc2(tmem_base, 512); }
+}
+
+int tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != SPN_OK) return rc;
+  SPN_CHECK_ARG(out && reps > 0 && (n == 64 || n == 128 || n == 256) && nacc >= 1 && n * nacc <= 256 && ld_warps >= 0 && ld_warps <= 16,
+                "spn_tc_mma_rate_pair: bad arguments");
+  const int smem_bytes = 64 * 1024 + 256 + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(mma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  mma_rate_pair_kernel<<<2, 17 * 32, smem_bytes, st>>>(ts, n, reps, nacc, ld_warps, out);
+  SPN_LAUNCH_CHECK("mma_rate_pair_kernel");
+  return SPN_OK;
 }
 
 int tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long* out, cudaStream_t st) {

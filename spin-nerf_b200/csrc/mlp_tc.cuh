@@ -30,7 +30,9 @@ constexpr int kActBytes = 4 * kAtomBytes;       // 256-wide activation tile = 64
 constexpr int kStages = 3;
 constexpr int kEpiWarps = 8;                               // epilogue warps per tile (2 column halves x 4 lane quarters)
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 32 * (2 + 2 * kEpiWarps);         // producer + MMA issuer + 2 tiles x 8 epilogue warps = 576
+constexpr int kThreads = 32 * (2 + 2 * kEpiWarps);         // producer + MMA issuer + 16 epilogue warps = 576
+constexpr int kFwdEpiWarps = 2 * kEpiWarps;                // forward: all 16 epilogue warps serve tile slot 0, then tile slot 1
+constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
 constexpr int SM_ACT = 0;                                  // 2 tiles x 64 KB
 constexpr int SM_RING = 2 * kActBytes;                     // 3 x 32 KB
 constexpr int SM_BAR = SM_RING + kStages * kChunkBig;      // mbarriers (<= 24 x 8 B)

@@ -122,6 +122,27 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 
+// ---- warp-uniform issue of tcgen05 instructions -----------------------------------------------------------
+// tcgen05.mma / commit take their operands from UNIFORM registers.  Issued from inside `if (lane == 0)` the compiler cannot
+// use the uniform datapath (divergent region): every MMA then costs ~19 scalar instructions including an ELECT / R2UR.BROADCAST
+// waterfall loop — 150-190 cycles per MMA, which is what bounded all round-1 kernels (tools/mma_rate_pair.py: 194 cycles per
+// MMA for N = 64, 128 and 256 alike).  The issuing WARP therefore runs its loops with all 32 lanes in uniform control flow,
+// keeps descriptors in values the compiler can prove uniform (uniform_u32 below for anything loaded per thread) and predicates
+// only the tcgen05 instruction itself on elect_one().  elect.sync picks the same lane every time for a full mask, so the
+// commits see the MMAs of "the executing thread".
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- proxies / fences ----------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -298,6 +319,33 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc,
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// CTA-pair MMA with the A operand in TENSOR MEMORY ("TS" form): D[256 x N] (+)= A[256 x 16] * B[N x 16]^T where each CTA's 128
+// rows of A sit in its own TMEM, lane = row, as packed bf16 pairs (K = 16 elements = 8 consecutive 32-bit columns starting at
+// a_tmem; element 2j in the low half of column j) — written there by the epilogue with tcgen05.st.  No shared-memory traffic for
+// A at all.  The eight mask registers are the disable-output-lane mask (none disabled).
+__device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (base + i), 16 consecutive 32-bit columns (32 packed bf16)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // commit of the pair's MMAs: arrives on the mbarrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
