@@ -173,53 +173,6 @@ __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
   c = __cosf(r);
 }
 
-// packs [v, sin(2^k v), cos(2^k v)]_k (helpers:28-52 order) as bf16 pairs; unused tail = 0
-template <int NFREQ, int NWORDS>
-__device__ __forceinline__ void encode_point(const float v[3], uint32_t (&out)[NWORDS]) {
-  float vals[2 * NWORDS];
-#pragma unroll
-  for (int i = 0; i < 2 * NWORDS; ++i) vals[i] = 0.0f;
-  vals[0] = v[0]; vals[1] = v[1]; vals[2] = v[2];
-#pragma unroll
-  for (int k = 0; k < NFREQ; ++k) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float s, c;
-      fast_sincos(__fmul_rn(v[a], (float)(1 << k)), s, c);
-      vals[3 + 6 * k + a] = s;
-      vals[3 + 6 * k + 3 + a] = c;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NWORDS; ++i) out[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
-}
-
-// One 32-element half (HALF = 0: elements 0..31, 1: elements 32..63) of gamma(pts) (L = 10, 63 values + zero pad) as
-// 16 packed bf16 pairs.  The two column halves of a tile's epilogue group each build one half: 15 / 16 sincos per thread.
-template <int HALF>
-__device__ __forceinline__ void encode_pts_half(const float v[3], uint32_t (&w)[16]) {
-  float vals[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-  if (HALF == 0) { vals[0] = v[0]; vals[1] = v[1]; vals[2] = v[2]; }
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int is = 3 + 6 * k + a, ic = 6 + 6 * k + a;
-      const bool ns = (is >> 5) == HALF, nc = (ic >> 5) == HALF;
-      if (ns || nc) {
-        float sn, cs;
-        fast_sincos(__fmul_rn(v[a], (float)(1 << k)), sn, cs);
-        if (ns) vals[is & 31] = sn;
-        if (nc) vals[ic & 31] = cs;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(vals[2 * i], vals[2 * i + 1]);
-}
-
 // 16-byte chunks [j0, j0+NJ) of row r of a [128 x 64] swizzled atom <- packed words (zeros for dead rows / beyond the words)
 template <int NW, int NJ, bool kStash>
 __device__ __forceinline__ void store_enc_chunks(const uint32_t (&w)[NW], int j0, bool live, uint32_t atom_a, uint8_t* stash_atom,
@@ -240,74 +193,6 @@ __device__ __forceinline__ void store_enc_chunks(const uint32_t (&w)[NW], int j0
 // per pair instead of a compare + select + or per element.  relu_mask_bit(c) is where column c of the block ends up.
 __device__ __forceinline__ uint32_t relu_mask_push(uint32_t acc, uint32_t packed_pair) {
   return (acc >> 1) | ((packed_pair + 0x7FFF7FFFu) & 0x80008000u);
-}
-
-// 32 accumulator columns of a hidden layer: h = acc + bias (ReLU), bf16, swizzled store into the A tile; returns the 32
-// ReLU mask bits (layout: relu_mask_push).  MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
-//   bias_a: shared address of this thread's first bias entry (column cl = 0)    wa_a: bf16 sigma weights, same origin
-//   row_a:  shared address of (this tile, this column half, row r, chunk 0)     rx: (r & 7) << 4
-template <bool kTrain, int MODE>
-__device__ __forceinline__ uint32_t epi_cols32(const uint32_t (&v)[32], const int cl, const uint32_t bias_a, const uint32_t wa_a,
-                                               float& alpha, const uint32_t row_a, const uint32_t rx) {
-  uint32_t mb = 0;
-  // the bias row is read one 8-column group ahead: the shared-memory latency hides behind the previous group's math
-  float4 nb0 = lds128f(bias_a + cl * 4), nb1 = lds128f(bias_a + cl * 4 + 16);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int c = cl + g * 8;                       // column inside this thread's 128 (compile-time after unrolling)
-    const float4 b0 = nb0, b1 = nb1;
-    if (g < 3) { nb0 = lds128f(bias_a + (c + 8) * 4); nb1 = lds128f(bias_a + (c + 8) * 4 + 16); }
-    const float2 h01 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])), make_float2(b0.x, b0.y));
-    const float2 h23 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])), make_float2(b0.z, b0.w));
-    const float2 h45 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])), make_float2(b1.x, b1.y));
-    const float2 h67 = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])), make_float2(b1.z, b1.w));
-    float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
-    if (MODE == 1) {
-      const uint4 wq = lds128u(wa_a + c * 2);       // 8 bf16 sigma weights
-      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
-#pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        h[e] = fmaxf(h[e], 0.f); h[e + 1] = fmaxf(h[e + 1], 0.f);
-        alpha = fmaf(h[e], __uint_as_float(ww[e / 2] << 16), alpha);
-        alpha = fmaf(h[e + 1], __uint_as_float(ww[e / 2] & 0xffff0000u), alpha);
-      }
-    }
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      o[e] = (MODE == 0) ? pack_relu_bf16(h[2 * e], h[2 * e + 1]) : pack_bf16(h[2 * e], h[2 * e + 1]);
-    if (kTrain && MODE != 2) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) mb = relu_mask_push(mb, o[e]);
-    }
-    sts128(row_a + (uint32_t)(c / 64) * kAtomBytes + ((uint32_t)(((c % 64) / 8) << 4) ^ rx), o[0], o[1], o[2], o[3]);
-  }
-  return mb;
-}
-
-// one 256-wide layer epilogue for this thread: 128 columns as four 32-column TMEM loads, two in flight
-template <bool kTrain, int MODE>
-__device__ __forceinline__ void epi_layer(const uint32_t tmem_a, const uint32_t bias_a, const uint32_t wa_a, float& alpha,
-                                          const uint32_t row_a, const uint32_t rx, uint32_t (&mk)[4], long long* tr) {
-  uint32_t va[32], vb[32];
-  tmem_ld32(tmem_a, va);
-  tmem_ld32(tmem_a + 32, vb);
-  tmem_ld_wait_dep(va);
-  tmem_ld_wait_dep(vb);
-  if (tr) tr[16] = clock64();
-  mk[0] = epi_cols32<kTrain, MODE>(va, 0, bias_a, wa_a, alpha, row_a, rx);
-  if (tr) tr[17] = clock64();
-  tmem_ld32(tmem_a + 64, va);
-  mk[1] = epi_cols32<kTrain, MODE>(vb, 32, bias_a, wa_a, alpha, row_a, rx);
-  if (tr) tr[18] = clock64();
-  tmem_ld32(tmem_a + 96, vb);
-  tmem_ld_wait_dep(va);
-  tmem_ld_wait_dep(vb);
-  if (tr) tr[19] = clock64();
-  mk[2] = epi_cols32<kTrain, MODE>(va, 64, bias_a, wa_a, alpha, row_a, rx);
-  if (tr) tr[20] = clock64();
-  mk[3] = epi_cols32<kTrain, MODE>(vb, 96, bias_a, wa_a, alpha, row_a, rx);
-  if (tr) tr[21] = clock64();
 }
 
 // 32 columns of the views layer: hv = relu(acc + bv), rgb += Wr[:, col] hv (fp32 partial), hv stashed in training.
@@ -383,374 +268,6 @@ __device__ __forceinline__ void encode_dir_quarter(const int cq, const float v[3
   else encode_range<4, 24, 8>(v, w);
 }
 
-// CTA pairs (cta_group::2).  Two CTAs on neighbouring SMs form a cluster; each owns two 128-sample tile slots and every
-// tcgen05.mma spans the pair (M = 256: slot t of both CTAs), so each SM reads only ITS half of the weight chunk from
-// shared memory (128 of the 256 output rows) and loads only that half from L2.  With 16 KB half-chunks the 96 KB ring
-// holds 6 of them: a layer's four chunks are loaded ONCE per round and stay resident for both tile slots, the rest
-// prefetches the next layer (ring / barrier comment inside the kernel; tests/test_ring_protocol_model.py models it).
-//   leader CTA (cluster rank 0): warp 1 lane 0 issues the MMAs and the multicast commits (ring slot free / accumulator
-//     ready arrive on the same barrier offsets in both CTAs)
-//   peer CTA: warp 1 lane 0 relays "my halves of this weight group have landed" to the leader's group barrier
-//   both: warp 0 lanes 0-5 load the CTA's weight halves; lanes 8-15 stream finished layer tiles to the stash (training)
-//   warps 2-17: ALL SIXTEEN epilogue warps work on tile slot 0, then on tile slot 1, of every step (4 TMEM lane quarters x
-//     4 column quarters of 64).  Round-1 gave each slot its own 8 warps: an epilogue then took 2.3-3.0 k cycles, longer
-//     than the other slot's 2 k cycles of MMAs, so the chain MMA -> epilogue -> MMA of a slot was exposed (tensor pipe
-//     busy 37 % of a round, profiles/r01b_trace_fwd_training.txt).  The epilogue is latency-bound (TMEM drain is ~530
-//     cycles, profiles/r01b_probe_tmem_drain.txt), so twice the warps on half the columns halve it, and because slot 0's
-//     epilogue runs while slot 1's MMAs execute and vice versa the two never compete for the warps.
-template <bool kTrain>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp_fwd_kernel(const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // 0: leader (issues the pair's MMAs)
-
-  if (smem != smem_raw) __trap();   // kSmemBytes has no alignment slack: the dynamic window must start 1024-aligned
-  // Weight ring: 3 slots, each one GROUP = two 16 KB half-chunks (chunks 2g, 2g+1 of a layer).  Every chunk is loaded
-  // once per round and used by BOTH tile slots; a layer occupies two slots, the third prefetches group 0 of the next
-  // layer, whose group 1 follows as soon as tile slot 1 is through group 0 of the current one.  FIFO.
-  // barriers: group_full[2][4]  group g of step s uses barrier [g][s % 4] — the ring never holds groups of two steps that
-  //             are 4 apart.  Armed by the local producer and, on the leader, by the peer's relay as well (count 2).
-  //           empty[3] (one multicast commit per group, after tile slot 1 has used it)   acc_full[2], act_ready[2]
-  //           tile_written[2] / tile_free[2] (training): all 16 warps have written slot t's layer output -> the four
-  //             store lanes copy it to the stash -> the copies have finished READING the tile, it may be overwritten
-  // The MMA-issuing thread is the scarce resource (tools/trace_fwd.py): tcgen05.mma issue blocks once a few MMAs are
-  // queued, a tcgen05.commit costs it ~130 cycles and even a satisfied mbarrier wait 200-400, during which the tensor
-  // pipe drains.  Hence few, merged barriers: per layer it waits on group 0 (before the A tile, off the critical path),
-  // the two A tiles and group 1 (mid-layer, tile slot 0 only), and commits 4 times.
-  static_assert(kNumSteps % 4 == 0, "group barrier phase bookkeeping assumes a multiple of 4 steps per round");
-  const uint32_t bar_full = sbase + SM_BAR, bar_empty = bar_full + 64;
-  const uint32_t bar_acc = bar_empty + 8 * kSlots, bar_act = bar_acc + 16;
-  const uint32_t bar_written = bar_act + 16, bar_free = bar_written + 16;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
-  const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kSlots; ++s) mbar_init(bar_empty + 8 * s, 1);
-    for (int b = 0; b < 8; ++b) mbar_init(bar_full + 8 * b, rank == 0 ? 2 : 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_acc + 8 * t, 1);
-      mbar_init(bar_act + 8 * t, 2 * kFwdEpiWarps);
-      mbar_init(bar_written + 8 * t, kFwdEpiWarps);
-      mbar_init(bar_free + 8 * t, 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators, in both CTAs of the pair
-    tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
-    tmem_relinquish2();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // sigma-head weights as bf16, read by the layer-7 epilogues
-    const int i = threadIdx.x - 64;
-    const __nv_bfloat16 w = __float2bfloat16_rn(__ldg(cst + C_WA + i));
-    sts16(sbase + SM_WA + 2 * i, *reinterpret_cast<const uint16_t*>(&w));
-  }
-  tcgen05_fence_before_sync();
-  cluster_sync_all();               // barriers of both CTAs initialised before anyone signals across the pair
-  tcgen05_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
-  const int my_rounds = (p.num_quads - cid + ncl - 1) / ncl;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-
-  if (warp == 0) {
-    if (lane < 2 * kSlots) {
-      // ================= weight producer (this CTA's half of every chunk) =================
-      // One 16 KB (8 KB for the 128-wide views layer) bulk copy per chunk; the two chunks of a group are issued by two
-      // different lanes (slot, slot + 3): a thread retires at most one cp.async.bulk per ~700 cycles (tools/bulk_rate.py).
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_rounds; ++it) {
-        const uint8_t* src = p.packed;
-        for (int s = 0; s < kNumSteps; ++s) {
-          const uint32_t half = (uint32_t)c_step_n[s] * 64u;       // bytes of this CTA's half chunk
-          const int nch = c_step_chunks[s];
-          for (int g = 0; 2 * g < nch; ++g) {
-            const int in_group = nch - 2 * g < 2 ? nch - 2 * g : 2;
-            const int sub = lane >= kSlots ? 1 : 0;                // which chunk of the group this lane copies
-            if (lane == (int)stage || lane == (int)stage + kSlots) {
-              const uint32_t gbar = bar_full + 8 * (s & 3) + 32 * g;
-              // BOTH lanes of the slot wait for every one of its releases, also when the group has a single chunk: a lane
-              // that skipped a revolution would find its next parity wait satisfied by the release before last
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              if (sub == 0) {
-                mbar_arrive_expect_tx(gbar, (uint32_t)in_group * half);
-                if (g == 0 && nch <= 2) mbar_arrive(gbar + 32);   // no second group: its barrier still advances one phase per step
-                if (tracing) trace_stamp(p.trace, it, s, 0, 12 + g);
-              }
-              const int c = 2 * g + sub;
-              if (sub < in_group)
-                bulk_g2s(sbase + SM_RING + stage * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)c * 2 * half + (size_t)rank * half,
-                         half, gbar);
-            }
-            if (++stage == kSlots) { stage = 0; phase ^= 1; }
-          }
-          src += (size_t)nch * 2 * half;
-        }
-      }
-    } else if (kTrain && lane >= 8 && lane < 16) {
-      // ================= stash store lanes: lane 8 + 4 t + a copies atom a of tile slot t after every stashed layer =================
-      const int t = (lane - 8) >> 2, a = (lane - 8) & 3;
-      uint32_t wph = 0;
-      for (int it = 0; it < my_rounds; ++it) {
-        const int64_t tile = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank + t;
-        uint8_t* stash_tile = p.stash + (size_t)tile * kStashTileBytes;
-        for (int s = 0; s < kNumSteps; ++s) {
-          const int atom = c_step_stash_atom[s];
-          if (atom < 0 || c_step_epi[s] == EPI_FINAL) continue;   // hv goes out with plain stores from the FINAL epilogue
-          mbar_wait(bar_written + 8 * t, wph);
-          wph ^= 1;
-          bulk_s2g(stash_tile + (size_t)(atom + a) * kAtomBytes, sbase + SM_ACT + t * kActBytes + a * kAtomBytes, kAtomBytes);
-          bulk_commit();
-          bulk_wait_read0();                                      // the copy has finished READING the tile
-          mbar_arrive(bar_free + 8 * t);
-        }
-      }
-      bulk_wait0();                                               // every stash store has landed before the kernel exits
-    }
-  } else if (warp == 1 && rank != 0) {
-    // ================= peer CTA: relay "my half landed" to the leader =================
-    if (lane == 0) {
-      const uint32_t full_leader = mapa_cluster(bar_full, 0);
-      for (int it = 0; it < my_rounds; ++it)
-        for (int s = 0; s < kNumSteps; ++s) {
-          const uint32_t lph = (uint32_t)(it * (kNumSteps / 4) + (s >> 2)) & 1u;
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(bar_full + 32 * g + 8 * (s & 3), lph);
-            mbar_arrive_cluster(full_leader + 32 * g + 8 * (s & 3));
-          }
-        }
-    }
-  } else if (warp == 1) {
-    // ================= leader CTA: MMA issuer for the pair =================
-    if (lane == 0) {
-      uint32_t grp = 0;                                     // groups consumed so far: group i sits in ring slot i % 3
-      uint32_t act_phase[2] = {0, 0};
-      for (int it = 0; it < my_rounds; ++it) {
-        for (int s = 0; s < kNumSteps; ++s) {
-          const int nch = c_step_chunks[s], n = c_step_n[s], ksteps = c_step_ksteps[s];
-          const uint32_t idesc = make_idesc(2 * kTileM, n, 0, 0);
-          const uint32_t lph = (uint32_t)(it * (kNumSteps / 4) + (s >> 2)) & 1u;
-          const uint32_t gbar = bar_full + 8 * (s & 3);
-          mbar_wait_cluster(gbar, lph);                       // group 0 of both CTAs (prefetched a layer ahead)
-          if (tracing) trace_stamp(p.trace, it, s, 0, 1);
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait_cluster(bar_act + 8 * t, act_phase[t]);   // A operands of both CTAs written, accumulators drained
-            act_phase[t] ^= 1;
-            tcgen05_fence_after_sync();
-            if (tracing) trace_stamp(p.trace, it, s, t, 0);
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            uint32_t accumulate = (uint32_t)c_step_acc[s];
-            for (int c = 0; c < nch; ++c) {
-              const uint32_t stage = (grp + (uint32_t)(c >> 1)) % kSlots;
-              if (t == 0 && c == 2) {                           // group 1: landed while group 0 ran (tile slot 1 follows slot 0)
-                mbar_wait_cluster(gbar + 32, lph);
-                tcgen05_fence_after_sync();
-                if (tracing) trace_stamp(p.trace, it, s, 0, 2);
-              }
-              if (tracing) trace_stamp(p.trace, it, s, t, 8 + c);
-              const uint32_t a_addr = sbase + SM_ACT + t * kActBytes + (nch == 1 ? 0 : c) * kAtomBytes;
-              const uint32_t b_addr = sbase + SM_RING + stage * kSlotBytes + (c & 1) * (kSlotBytes / 2);
-              const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024);
-              const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024);
-              for (int k = 0; k < ksteps; ++k) {
-                // +32 bytes (16 bf16) along K inside the 128-byte swizzle atom: start-address field += 2
-                umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
-                accumulate = 1;
-              }
-              // group free in both CTAs once tile slot 1's MMAs have read it
-              if (t == 1 && ((c & 1) || c == nch - 1)) umma_commit_2cta(bar_empty + 8 * stage, 3);
-            }
-            umma_commit_2cta(bar_acc + 8 * t, 3);            // accumulators complete -> epilogues of slot t in both CTAs
-            if (tracing) trace_stamp(p.trace, it, s, t, 3);
-          }
-          grp += (uint32_t)((nch + 1) >> 1);
-        }
-      }
-    }
-  } else {
-    // ================= prologue + epilogue warps: all 16 on tile slot 0, then on tile slot 1 =================
-    // warp (q, cq): TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq (columns 64cq..64cq+63 = atom cq)
-    const int ew = warp - 2;
-    const int cq = ew >> 2;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                         // row inside the tile
-    const int tix = cq * 128 + r;                        // 0..511 inside the epilogue group
-    const uint32_t rx = (uint32_t)(r & 7) << 4;
-    const uint32_t bias_base = sbase + SM_BIAS;          // 512 floats: bias row of step s at (s & 1) * 1024; FINAL: Wr [3][128] + bv [128]
-    const uint32_t wa_a = sbase + SM_WA + (uint32_t)cq * 128u;
-    const uint32_t act_leader = mapa_cluster(bar_act, 0);            // the leader's "A tile written" barriers
-    // per-slot state as bit t of a word (the slot loop is not unrolled: one copy of the epilogue code)
-    uint32_t acc_ph = 0, free_ph = 0, pend = 0;          // pend: a stash copy of slot t's tile may still be reading it
-    float alpha0 = 0.0f, alpha1 = 0.0f;                  // this column quarter's partial of the sigma head, per slot
-    auto wait_tile_free = [&](const int t) {
-      if (kTrain && ((pend >> t) & 1u)) {
-        mbar_wait(bar_free + 8 * t, (free_ph >> t) & 1u);
-        free_ph ^= 1u << t;
-        pend &= ~(1u << t);
-      }
-    };
-    for (int it = 0; it < my_rounds; ++it) {
-      const int64_t tile0 = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank;
-      // ---- prologue: sample point -> gamma(pts) -> A atom 0 of both slots, one quarter (16 values, 2 chunks) per thread.
-      //      Nothing of the sample stays in registers: the second passes re-fetch the 24 bytes and re-derive their encoding.
-      //      Step 0's bias row is staged here (row 0 was last read by the previous round's FINAL, which ends in a barrier).
-      if (tix < 256) sts32f(bias_base + 4 * tix, __ldg(cst + c_step_bias[0] + tix));
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int64_t row = (tile0 + t) * kTileM + r;
-        const bool live = row < p.m;
-        float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
-        if (live) fetch_sample(p.src, row, pt, dir);
-        uint32_t w[8];
-        encode_pts_quarter(cq, pt, w);
-        wait_tile_free(t);
-        store_enc_chunks<8, 2, kTrain>(w, 2 * cq, live, sbase + SM_ACT + t * kActBytes,
-                                       kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes + (size_t)SA_ENC * kAtomBytes : nullptr, r);
-        tcgen05_fence_before_sync();                     // the previous round's FINAL read this slot's accumulator
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(act_leader + 8 * t);
-      }
-      alpha0 = 0.0f; alpha1 = 0.0f;
-#pragma unroll 1
-      for (int s = 0; s < kNumSteps; ++s) {
-        const int epi = c_step_epi[s];
-        // (1) once per step: every warp has finished the previous step's epilogues, so the bias row of step s+1 (which
-        //     shares its buffer with step s-1) may be staged; it becomes visible with the barrier of step s+1.  There is
-        //     no L1 left with 227 KB carved out, so reading biases straight from global would cost an L2 trip per value.
-        named_bar_sync(1, kFwdEpiThreads);
-        if (s + 1 < kNumSteps) {
-          const int en = c_step_epi[s + 1];
-          if (en == EPI_FINAL) {                          // both rows: Wr [3][128] at 0, bv [128] at 384 (step 10 reads no bias)
-            sts32f(bias_base + 4 * tix, __ldg(cst + (tix < 384 ? C_WR + tix : C_BV + (tix - 384))));
-          } else if (en == EPI_RELU || en == EPI_RELU_ALPHA || en == EPI_LINEAR) {
-            if (tix < 256) sts32f(bias_base + (uint32_t)((s + 1) & 1) * 1024u + 4 * tix, __ldg(cst + c_step_bias[s + 1] + tix));
-          }
-        }
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t act_a = sbase + SM_ACT + t * kActBytes;
-          const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-          uint8_t* const stash_tile = kTrain ? p.stash + (size_t)(tile0 + t) * kStashTileBytes : nullptr;
-          if (epi == EPI_WRITE_ENC || epi == EPI_WRITE_DENC) {
-            // second-pass operand: re-derived while pass 1 runs, written over atom 0 once pass 1 has finished reading the tile
-            const int64_t row = (tile0 + t) * kTileM + r;
-            const bool live = row < p.m;
-            float pt[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
-            if (live) fetch_sample(p.src, row, pt, dir);
-            uint32_t encw[8];
-            if (epi == EPI_WRITE_ENC) {
-              encode_pts_quarter(cq, pt, encw);
-            } else {
-              uint32_t dw[4];
-              encode_dir_quarter(cq, dir, dw);
-              encw[0] = dw[0]; encw[1] = dw[1]; encw[2] = dw[2]; encw[3] = dw[3];
-            }
-            mbar_wait(bar_acc + 8 * t, (acc_ph >> t) & 1u);
-            acc_ph ^= 1u << t;
-            tcgen05_fence_after_sync();
-            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
-            wait_tile_free(t);
-            if (epi == EPI_WRITE_ENC) {
-              store_enc_chunks<8, 2, false>(encw, 2 * cq, live, act_a, nullptr, r);
-            } else {
-              const uint32_t dw[4] = {encw[0], encw[1], encw[2], encw[3]};
-              store_enc_chunks<4, 1, kTrain>(dw, cq, live, act_a, stash_tile + (size_t)SA_DENC * kAtomBytes, r);
-              if (kTrain)   // wgrad reads all 64 columns of the stashed atom: columns 32..63 are zero padding
-                *reinterpret_cast<uint4*>(stash_tile + (size_t)SA_DENC * kAtomBytes + sw128_off((uint32_t)r, (uint32_t)(4 + cq))) = make_uint4(0, 0, 0, 0);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(act_leader + 8 * t);
-            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-            continue;
-          }
-          mbar_wait(bar_acc + 8 * t, (acc_ph >> t) & 1u);
-          acc_ph ^= 1u << t;
-          tcgen05_fence_after_sync();
-          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 4);
-          if (epi == EPI_FINAL) {
-            // hv = relu(acc + bv) [128];  rgb = Wr hv + br;  raw = [rgb, alpha]   (helpers:117-123); 32 columns per quarter
-            float rgb[3] = {0.f, 0.f, 0.f};
-            uint32_t va[32];
-            tmem_ld32(tmem_lane + cq * 32, va);
-            tmem_ld_wait_dep(va);
-            const uint32_t m0 = epi_final32<kTrain>(va, cq * 32, bias_base + 4 * 384, bias_base, rgb, stash_tile, r);
-            if (kTrain) reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff)[(8 * 128 + r) * 8 + cq] = m0;
-            // partials of the four column quarters meet in the (dead) tile: atoms 1-3 were last read by step 10's MMAs
-            float4* xchg = reinterpret_cast<float4*>(smem + SM_ACT + t * kActBytes + kAtomBytes);
-            const float al = t ? alpha1 : alpha0;
-            if (cq != 0) xchg[(cq - 1) * 128 + r] = make_float4(rgb[0], rgb[1], rgb[2], al);
-            tcgen05_fence_before_sync();
-            named_bar_sync(1, kFwdEpiThreads);
-            const int64_t row = (tile0 + t) * kTileM + r;
-            if (cq == 0 && row < p.m) {
-              const float4 o1 = xchg[r], o2 = xchg[128 + r], o3 = xchg[256 + r];
-              *reinterpret_cast<float4*>(p.raw + row * 4) =
-                  make_float4(rgb[0] + o1.x + o2.x + o3.x + __ldg(cst + C_BR), rgb[1] + o1.y + o2.y + o3.y + __ldg(cst + C_BR + 1),
-                              rgb[2] + o1.z + o2.z + o3.z + __ldg(cst + C_BR + 2), al + o1.w + o2.w + o3.w + __ldg(cst + C_BA));
-            }
-            if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-            continue;   // next arrival on act_ready comes from the next round's prologue
-          }
-          // ---- bias (+ReLU) -> bf16 -> swizzled in-place store; layer 7 also accumulates sigma from fp32 h7
-          uint32_t mk0, mk1;
-          {
-            const uint32_t my_bias = bias_base + (uint32_t)(s & 1) * 1024u + (uint32_t)cq * 256u;
-            const uint32_t my_tmem = tmem_lane + (uint32_t)cq * 64u;
-            const uint32_t row_a = act_a + (uint32_t)cq * kAtomBytes + (uint32_t)r * 128u;   // this thread's row of atom cq
-            long long* etr = (tix == 0 && tracing && it < kTraceRounds) ? p.trace + ((it * 12 + s) * 2 + t) * kTraceEvents : nullptr;
-            uint32_t va[32], vb[32];
-            tmem_ld32(my_tmem, va);
-            tmem_ld32(my_tmem + 32, vb);
-            tmem_ld_wait_dep(va);
-            tmem_ld_wait_dep(vb);
-            if (etr) etr[16] = clock64();
-            wait_tile_free(t);
-            float al = 0.0f;
-            if (epi == EPI_RELU) {
-              mk0 = epi_cols32<kTrain, 0>(va, 0, my_bias, wa_a, al, row_a, rx);
-              mk1 = epi_cols32<kTrain, 0>(vb, 32, my_bias, wa_a, al, row_a, rx);
-            } else if (epi == EPI_RELU_ALPHA) {
-              mk0 = epi_cols32<kTrain, 1>(va, 0, my_bias, wa_a, al, row_a, rx);
-              mk1 = epi_cols32<kTrain, 1>(vb, 32, my_bias, wa_a, al, row_a, rx);
-              if (t) alpha1 = al; else alpha0 = al;
-            } else {
-              mk0 = epi_cols32<kTrain, 2>(va, 0, my_bias, wa_a, al, row_a, rx);
-              mk1 = epi_cols32<kTrain, 2>(vb, 32, my_bias, wa_a, al, row_a, rx);
-            }
-            if (etr) etr[18] = clock64();
-            tcgen05_fence_before_sync();
-            fence_proxy_async_smem();
-            if (etr) etr[19] = clock64();
-          }
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_cluster(act_leader + 8 * t);
-            if (kTrain) mbar_arrive(bar_written + 8 * t);
-          }
-          if (kTrain) pend |= 1u << t;
-          if (tix == 0 && tracing) trace_stamp(p.trace, it, s, t, 6);
-          // the mask words go out AFTER the hand-over: a global store in front of it sat ~900 cycles on the critical path
-          if (kTrain && c_step_mask_slot[s] >= 0)
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(stash_tile + kStashMaskOff) + (c_step_mask_slot[s] * 128 + r) * 8 + cq * 2) =
-                make_uint2(mk0, mk1);
-        }
-      }
-    }
-  }
-
-  __syncwarp();                     // single-lane roles rejoin their warp before the aligned cluster barrier
-  tcgen05_fence_before_sync();
-  cluster_sync_all();               // nobody signals into a CTA that has exited; all MMAs of the pair have completed
-  if (warp == 1) {
-    tcgen05_fence_after_sync();
-    tmem_dealloc2(tmem_base, 512);
-  }
-}
-
 // =====================================================================================================================
 // "TS" forward kernel: activations never touch shared memory.
 //
@@ -775,7 +292,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
 constexpr int kTsSlots = 4;                                  // ring: 4 groups of two 16 KB half-chunks = 2 layers resident
 constexpr int TS_RING = 0;
 constexpr int TS_GAMMA = kTsSlots * kSlotBytes;              // 2 x 16 KB: gamma(pts) / gamma(dir) atom of each tile slot (SS operand)
-constexpr int TS_STAGE = TS_GAMMA + 2 * kAtomBytes;          // training: 2 x 32 KB staging of a half layer (2 atoms) for the stash copies
+constexpr int TS_STAGE = TS_GAMMA + 2 * kAtomBytes;          // training: 4 x 16 KB staging of a half layer's E4M3 stash atom (buffer 2 t + h)
 constexpr int TS_BAR = TS_STAGE + 4 * kAtomBytes;            // = 229376
 constexpr int TS_TMEMPTR = TS_BAR + 240;
 constexpr int TS_BIAS = TS_BAR + 256;                        // 2 rows of 256 floats (layer parity)
@@ -797,12 +314,13 @@ __constant__ int c_l_kind[kTsLayers] = {LK_L0, LK_WIDE, LK_WIDE, LK_WIDE, LK_WID
 __constant__ int c_l_group0[kTsLayers] = {0, 2, 4, 6, 8, 10, 14, 16, 18, 20};   // first group of the layer in the round's sequence
 
 // 32 accumulator columns = 32 consecutive output features: h = acc + bias (ReLU), packed bf16 -> out[16] (the TMEM image of the
-// next A operand) and, in training, the staging tile of the stash copy; returns the 32 ReLU mask bits (relu_mask_push layout).
-// MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear (feature layer).
+// next A operand) and, in training, E4M3 -> the staging tile of the stash copy (32 bytes: chunks chunk0, chunk0 + 1 of the row);
+// returns the 32 ReLU mask bits (relu_mask_push layout).  MODE 0: ReLU, 1: ReLU + sigma-head partial from the fp32 h, 2: linear.
 template <bool kTrain, int MODE>
 __device__ __forceinline__ uint32_t epi32_ts(const uint32_t (&v)[32], const uint32_t bias_a, const uint32_t wa_a, float& alpha,
                                              uint32_t (&out)[16], const uint32_t stage_row, const uint32_t chunk0, const uint32_t rx) {
   uint32_t mb = 0;
+  uint32_t q8[4];
   float4 nb0 = lds128f(bias_a), nb1 = lds128f(bias_a + 16);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -832,7 +350,11 @@ __device__ __forceinline__ uint32_t epi32_ts(const uint32_t (&v)[32], const uint
 #pragma unroll
         for (int e = 0; e < 4; ++e) mb = relu_mask_push(mb, out[4 * g + e]);
       }
-      sts128(stage_row + (((chunk0 + (uint32_t)g) << 4) ^ rx), out[4 * g], out[4 * g + 1], out[4 * g + 2], out[4 * g + 3]);
+      // the stash copy is E4M3 of the fp32 value (MODE 0: the ReLU rides on the conversion)
+      const uint32_t w0 = (MODE == 0) ? pack_relu_e4m3x4(h[0], h[1], h[2], h[3]) : pack_e4m3x4(h[0], h[1], h[2], h[3]);
+      const uint32_t w1 = (MODE == 0) ? pack_relu_e4m3x4(h[4], h[5], h[6], h[7]) : pack_e4m3x4(h[4], h[5], h[6], h[7]);
+      q8[(2 * g) & 3] = w0; q8[(2 * g + 1) & 3] = w1;
+      if (g & 1) sts128(stage_row + (((chunk0 + (uint32_t)(g >> 1)) << 4) ^ rx), q8[0], q8[1], q8[2], q8[3]);
     }
   }
   return mb;
@@ -849,10 +371,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   // barriers: full[4] / empty[4] per ring slot (slot s is used once per revolution: parity = revolution & 1),
   //   acc_full[2] (commit after each batch), acc_free[2] (32 warps: accumulator loaded into registers, leader only),
   //   a_ready[2] (32 warps: slot t's activations / gamma atom written, leader only),
-  //   written[2] / free[2] (training: staging buffer h filled by the 16 warps / copied out by its two store lanes)
+  //   written[4] / free[4] (training: staging buffer 2 t + h filled by the 16 warps / copied out by its store lane)
   const uint32_t bar_full = sbase + TS_BAR, bar_empty = bar_full + 8 * kTsSlots;
   const uint32_t bar_accfull = bar_empty + 8 * kTsSlots, bar_accfree = bar_accfull + 16, bar_aready = bar_accfree + 16;
-  const uint32_t bar_written = bar_aready + 16, bar_free = bar_written + 16;
+  const uint32_t bar_written = bar_aready + 16, bar_free = bar_written + 32;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + TS_TMEMPTR);
   const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
 
@@ -862,9 +384,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
       mbar_init(bar_accfull + 8 * t, 1);
       mbar_init(bar_accfree + 8 * t, 2 * kFwdEpiWarps);
       mbar_init(bar_aready + 8 * t, 2 * kFwdEpiWarps);
-      mbar_init(bar_written + 8 * t, kFwdEpiWarps);
-      mbar_init(bar_free + 8 * t, 2);
     }
+    for (int b = 0; b < 4; ++b) { mbar_init(bar_written + 8 * b, kFwdEpiWarps); mbar_init(bar_free + 8 * b, 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc2(smem_u32(tmem_ptr_smem), 512); tmem_relinquish2(); }
@@ -908,27 +429,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
           src += (size_t)nch * 2 * half;
         }
       }
-    } else if (kTrain && lane >= 8 && lane < 12) {
-      // ================= stash store lanes: lane 8 + 2 h + sa copies staging atom sa of buffer h after every half epilogue =================
-      const int h = (lane - 8) >> 1, sa = (lane - 8) & 1;
-      uint32_t wph = 0;
+    } else if (kTrain && lane == 8) {
+      // ================= stash store lane: copies the E4M3 atom of every half epilogue (staging buffer 2 t + h) to the stash =================
+      // One lane, buffers in the order the epilogue fills them (0, 1, 2, 3, 0, ...); bulk groups complete their reads in order,
+      // so after committing copy k "at most one group pending" means copy k - 1 has finished reading its buffer.
+      uint32_t k = 0;
       for (int it = 0; it < my_rounds; ++it) {
         const int64_t tile0 = 4 * ((int64_t)cid + (int64_t)it * ncl) + 2 * (int64_t)rank;
         for (int L = 0; L < kTsLayers - 1; ++L) {
-          const int atom0 = c_step_stash_atom[c_l_step0[L] + c_l_parts[L] - 1];
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(bar_written + 8 * h, wph);
-            wph ^= 1;
+          for (int b = 0; b < 4; ++b, ++k) {
+            mbar_wait(bar_written + 8 * b, (k >> 2) & 1u);
             if (!(p.debug & 4)) {
-              bulk_s2g(p.stash + (size_t)(tile0 + t) * kStashTileBytes + (size_t)(atom0 + 2 * sa + h) * kAtomBytes,
-                       sbase + TS_STAGE + (uint32_t)(2 * h + sa) * kAtomBytes, kAtomBytes);
+              bulk_s2g(p.stash + (size_t)(tile0 + (b >> 1)) * kStashTileBytes + (size_t)stash_x_atom(L, b & 1) * kAtomBytes,
+                       sbase + TS_STAGE + (uint32_t)b * kAtomBytes, kAtomBytes);
               bulk_commit();
-              if (!(p.debug & 1)) bulk_wait_read0();
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             }
-            mbar_arrive(bar_free + 8 * h);
+            if (k > 0) mbar_arrive(bar_free + 8 * ((b + 3) & 3));      // buffer of copy k - 1
           }
         }
       }
+      bulk_wait_read0();
+      if (k > 0) mbar_arrive(bar_free + 8 * 3);
       bulk_wait0();
     }
   } else if (warp == 1 && rank != 0) {
@@ -1133,19 +655,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(accfree_leader + 8 * acc);      // the accumulator may be overwritten
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 8);
-            if (kTrain && (pend & 1u)) { mbar_wait(bar_free, free_ph & 1u); free_ph ^= 1u; pend &= ~1u; }
+            const uint32_t sb = 2u * (uint32_t)t;                 // staging buffer of (slot t, half a)
+            if (kTrain && ((pend >> sb) & 1u)) { mbar_wait(bar_free + 8 * sb, (free_ph >> sb) & 1u); free_ph ^= 1u << sb; pend &= ~(1u << sb); }
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 9);
-            const uint32_t stage_row = sbase + TS_STAGE + (uint32_t)(cq >> 1) * kAtomBytes + (uint32_t)r * 128u;
+            const uint32_t stage_row = sbase + TS_STAGE + sb * kAtomBytes + (uint32_t)r * 128u;
             const uint32_t ba = bias_row + 4u * (uint32_t)fsub, wa = sbase + TS_WA + 2u * (uint32_t)fsub;
-            if (epi == EPI_RELU) mka = epi32_ts<kTrain, 0>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
-            else if (epi == EPI_RELU_ALPHA) mka = epi32_ts<kTrain, 1>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
-            else mka = epi32_ts<kTrain, 2>(v, ba, wa, al, ra, stage_row, 4u * (cq & 1), rx);
+            if (epi == EPI_RELU) mka = epi32_ts<kTrain, 0>(v, ba, wa, al, ra, stage_row, 2u * cq, rx);
+            else if (epi == EPI_RELU_ALPHA) mka = epi32_ts<kTrain, 1>(v, ba, wa, al, ra, stage_row, 2u * cq, rx);
+            else mka = epi32_ts<kTrain, 2>(v, ba, wa, al, ra, stage_row, 2u * cq, rx);
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 6);
             if (kTrain) {
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_written);
-              pend |= 1u;
+              if (lane == 0) mbar_arrive(bar_written + 8 * sb);
+              pend |= 1u << sb;
             }
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 10);
           }
@@ -1164,13 +687,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(accfree_leader + 8 * acc);
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 11);
-            if (kTrain && (pend & 2u)) { mbar_wait(bar_free + 8, (free_ph >> 1) & 1u); free_ph ^= 2u; pend &= ~2u; }
+            const uint32_t sb = 2u * (uint32_t)t + 1u;            // staging buffer of (slot t, half b)
+            if (kTrain && ((pend >> sb) & 1u)) { mbar_wait(bar_free + 8 * sb, (free_ph >> sb) & 1u); free_ph ^= 1u << sb; pend &= ~(1u << sb); }
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 12);
-            const uint32_t stage_row = sbase + TS_STAGE + (uint32_t)(2 + (cq >> 1)) * kAtomBytes + (uint32_t)r * 128u;
+            const uint32_t stage_row = sbase + TS_STAGE + sb * kAtomBytes + (uint32_t)r * 128u;
             const uint32_t ba = bias_row + 4u * (uint32_t)(64 + fsub), wa = sbase + TS_WA + 2u * (uint32_t)(64 + fsub);
-            if (epi == EPI_RELU) mkb = epi32_ts<kTrain, 0>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
-            else if (epi == EPI_RELU_ALPHA) mkb = epi32_ts<kTrain, 1>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
-            else mkb = epi32_ts<kTrain, 2>(v, ba, wa, al, rb, stage_row, 4u * (cq & 1), rx);
+            if (epi == EPI_RELU) mkb = epi32_ts<kTrain, 0>(v, ba, wa, al, rb, stage_row, 2u * cq, rx);
+            else if (epi == EPI_RELU_ALPHA) mkb = epi32_ts<kTrain, 1>(v, ba, wa, al, rb, stage_row, 2u * cq, rx);
+            else mkb = epi32_ts<kTrain, 2>(v, ba, wa, al, rb, stage_row, 2u * cq, rx);
             tmem_st16(a_tmem + (uint32_t)((64 + fsub) >> 1), rb);
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 13);
             if (epi == EPI_RELU_ALPHA) { if (t) alpha1 = al; else alpha0 = al; }
@@ -1192,9 +716,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
             __syncwarp();
             if (lane == 0) {
               mbar_arrive_cluster(aready_leader + 8 * t);
-              if (kTrain) mbar_arrive(bar_written + 8);
+              if (kTrain) mbar_arrive(bar_written + 8 * sb);
             }
-            if (kTrain) pend |= 2u;
+            if (kTrain) pend |= 1u << sb;
             if (tix == 0 && tracing) trace_stamp(p.trace, it, sl, t, 7);
           }
           // mask words after the hand-over: word w covers features 32w..32w+31
@@ -1245,10 +769,8 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   p.debug = fwd_debug;
   const int pairs = sm_count() / 2;
   int grid = 2 * (p.num_quads < pairs ? p.num_quads : pairs);
-  // SPN_FWD_TS=0 selects the round-1 organisation (both operands in shared memory) for A/B timing; default: A operand in TMEM
-  static const bool use_ts = !(getenv("SPN_FWD_TS") && atoi(getenv("SPN_FWD_TS")) == 0);
-  auto kern = use_ts ? (stash ? mlp_fwd_ts_kernel<true> : mlp_fwd_ts_kernel<false>) : (stash ? mlp_fwd_kernel<true> : mlp_fwd_kernel<false>);
-  const int smem_bytes = use_ts ? kTsSmemBytes : kSmemBytes;
+  auto kern = stash ? mlp_fwd_ts_kernel<true> : mlp_fwd_ts_kernel<false>;
+  const int smem_bytes = kTsSmemBytes;
   static bool attr_set[2] = {false, false};
   if (!attr_set[stash ? 1 : 0]) {
     SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1257,7 +779,7 @@ int mlp_tc_fwd(const void* packed, const SampleSource& src, int64_t m, float* ra
   prof_begin(PROF_MLP_FWD, st);
   kern<<<grid, kPairThreads, smem_bytes, st>>>(p);
   prof_end(PROF_MLP_FWD, st);
-  SPN_LAUNCH_CHECK("mlp_fwd_kernel");
+  SPN_LAUNCH_CHECK("mlp_fwd_ts_kernel");
   return SPN_OK;
 }
 

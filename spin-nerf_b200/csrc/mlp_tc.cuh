@@ -46,17 +46,22 @@ constexpr int kPairThreads = kThreads;
 constexpr int kSlots = 3;            // ring slots: one GROUP (two half-chunks) each
 constexpr int kSlotBytes = 32768;
 
-// ---- per-tile forward stash (training): bf16 SWIZZLE_128B images, 16 KB atoms -----------------------------
-//   atom 0      gamma(pts) (63 + pad)            atoms 1..32   h0..h7 (4 atoms each)
-//   atoms 33-36 feature                          atoms 37-38   hv (128 wide)
-//   atom 39     gamma(viewdir) (27 + pad)
+// ---- per-tile forward stash (training), 16 KB atoms -------------------------------------------------------------
+//   atom 0        gamma(pts) (63 + pad), bf16 SWIZZLE_128B image [128 rows x 64]
+//   atoms 1..18   the nine 256-wide layer outputs h0..h7, feature as E4M3 (fp8) — two atoms per layer, atom h = the 128 output
+//                 features the forward epilogue handles in accumulator half h: row r = 128 bytes, 16-byte chunk j' stored at
+//                 position j' ^ (r & 7), chunk j' = features 64 h + 16 (j' & 3) + 128 (j' >> 2) ... + 15, one byte each.
+//                 The weight-gradient GEMM is the only reader: it widens them to bf16 in shared memory (exact) for its MMAs.  Halves the bytes of the training step's largest HBM stream (round 1 stashed bf16).
+//   atoms 19-20   hv (128 wide), bf16 image        atom 21   gamma(viewdir) (27 + pad), bf16 image
 // followed by ReLU masks: 9 slots (h0..h7, hv) x 128 rows x 8 words; word w covers columns 32w..32w+31 with column
 // 32w + c at bit relu_mask_bit(c) (pairs are pushed as packed bf16x2 words, see relu_mask_push in mlp_tc.cu)
 __host__ __device__ constexpr int relu_mask_bit(int c) { return ((c & 1) << 4) | (c >> 1); }
-constexpr int kStashAtoms = 40;
-constexpr int SA_ENC = 0, SA_H0 = 1, SA_FEAT = 33, SA_HV = 37, SA_DENC = 39;
+constexpr int kStashAtoms = 22;
+constexpr int SA_ENC = 0, SA_X0 = 1, SA_HV = 19, SA_DENC = 21;
+__host__ __device__ constexpr int stash_x_atom(int layer, int half) { return SA_X0 + 2 * layer + half; }   // layer 0..7 = h0..h7, 8 = feature
+__host__ __device__ constexpr int stash_x_feature(int half, int chunk) { return 64 * half + 16 * (chunk & 3) + 128 * (chunk >> 2); }
 constexpr size_t kStashMaskOff = (size_t)kStashAtoms * kAtomBytes;
-constexpr size_t kStashTileBytes = kStashMaskOff + 9 * 128 * 32;   // 692224 B per 128 samples
+constexpr size_t kStashTileBytes = kStashMaskOff + 9 * 128 * 32;   // 397312 B per 128 samples (round 1: 692224)
 
 // ---- per-tile backward stash (dgrad -> wgrad): d(pre-activation) as bf16 images -----------------------------
 //   atoms 0-1  d_hv (128 wide)    atoms 2-5  d_feat     atoms 6+4*(7-i) .. : d_h{i} for i = 7..0

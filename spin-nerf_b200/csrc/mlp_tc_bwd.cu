@@ -12,6 +12,7 @@
 //                      shared-memory slabs by otherwise idle warps.
 //   mlp_heads_wgrad_kernel   the 3x128 rgb / 1x256 sigma heads on CUDA cores.
 // No gradient flows to the sampled points (z_samples are detached, run_nerf.py:700).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -313,17 +314,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
 // =====================================================================================================
 // wgrad
 // =====================================================================================================
+// dW[out, in] = sum over samples of dpre[sample, out] * x[sample, in]: a split-K GEMM with K = sample.  A = dpre slabs from the
+// dstash (bf16 SWIZZLE_128B images, used MN-major), B = the layer input.  The nine 256-wide inputs (h0..h7, feature) are
+// stashed as E4M3 (mlp_tc.cuh): four otherwise idle warps widen each 64-sample slab to bf16 (exact) in the MN-major SWIZZLE_128B
+// image the tensor core reads, while the previous slab's MMAs run (a bf16 x f16 MMA would save half the conversion work, but
+// kind::f16 with different A and B formats raised "illegal instruction" on the B200).  The 64-wide encodings stay bf16 and are
+// used as they land.
 constexpr int kWgUnits = 12;
-#ifndef SPN_WG_SLAB_ROWS
-#define SPN_WG_SLAB_ROWS 64   // 8 KB bulk pieces: 2.54 -> 2.18 ms per 2^20 samples vs 32-row slabs (tools/bench_bwd.py)
-#endif
-constexpr int kWgSlabRows = SPN_WG_SLAB_ROWS;   // samples per pipeline stage
-constexpr int kWgStages = 192 / kWgSlabRows;    // 192 KB ring
-constexpr int kWgSlabBytes = kWgSlabRows * 128; // one atom's slab: 4 KB
-constexpr int kWgStageBytes = 8 * kWgSlabBytes; // 4 A slabs + 4 B slabs = 32 KB
+constexpr int kWgSlabRows = 64;                 // samples per pipeline stage
+constexpr int kWgStages = 3;
+constexpr int kWgSlabBytes = kWgSlabRows * 128; // one atom's slab: 8 KB
+constexpr int kWgStageBytes = 6 * kWgSlabBytes; // A: 4 slabs (32 KB) at +0;  B as it lands: 2 E4M3 slabs or 1 bf16 slab at +32 KB
+constexpr int WG_B16 = kWgStages * kWgStageBytes;          // 2 x 32 KB: the widened (bf16) B operand, double-buffered
+constexpr int WG_BAR = WG_B16 + 2 * 4 * kWgSlabBytes;
 constexpr int kWgThreads = 192;
-constexpr int WG_BAR = kWgStages * kWgStageBytes;
 constexpr int kWgSmemBytes = WG_BAR + 256 + 1024;
+static_assert(kWgSmemBytes <= 232448, "wgrad shared memory budget");
 
 struct WgUnit {
   int d_atom;      // first atom of dpre inside the dstash tile
@@ -334,7 +340,8 @@ struct WgUnit {
   int w_off;       // float offset of dW[0][0] in the flat gradient
   int ld;          // row stride of dW
   int b_off;       // float offset of the bias gradient, -1 if another unit owns it
-  int cost;        // relative CTA time per tile (138 = a 256x256 unit)
+  int cost;        // relative CTA time per tile
+  int b_fp8;       // 1: the input is the two-atom E4M3 image of a 256-wide layer output, 0: a 64-wide bf16 encoding atom
 };
 struct WgTable { WgUnit u[kWgUnits]; int total_cost; };
 
@@ -344,19 +351,19 @@ static WgTable build_wg_table() {
   auto W = [&](int i) { return (int)po.off[2 * i]; };
   auto B = [&](int i) { return (int)po.off[2 * i + 1]; };
   auto DH = [&](int i) { return DA_H7 + 4 * (7 - i); };
-  auto H = [&](int i) { return SA_H0 + 4 * i; };
+  auto X = [&](int layer) { return stash_x_atom(layer, 0); };
   int n = 0;
-  // cost = measured CTA-cycles per tile (tools/trace_wgrad.py, 64-sample slabs): HBM bytes plus the per-slab copy round —
-  // the narrow units are slower than their byte share — relative to 138 for a 256x256 unit
-  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 115};
-  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, H(i - 1), 256, 256, W(i), kW, B(i), 138};
-  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 104};
-  t.u[n++] = WgUnit{DH(5), 256, H(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 138};
-  t.u[n++] = WgUnit{DH(6), 256, H(5), 256, 256, W(6), kW, B(6), 138};
-  t.u[n++] = WgUnit{DH(7), 256, H(6), 256, 256, W(7), kW, B(7), 138};
-  t.u[n++] = WgUnit{DA_FEAT, 256, H(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 138};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_FEAT, 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 113};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 88};
+  // cost ~ CTA-cycles per tile (HBM bytes of a slab plus the per-slab copy round): 64 KB slabs measured 138 in round 1
+  // (tools/trace_wgrad.py); the E4M3 input makes a wide unit's slab 48 KB
+  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 115, 0};
+  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, X(i - 1), 256, 256, W(i), kW, B(i), 120, 1};
+  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 104, 0};
+  t.u[n++] = WgUnit{DH(5), 256, X(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 120, 1};
+  t.u[n++] = WgUnit{DH(6), 256, X(5), 256, 256, W(6), kW, B(6), 120, 1};
+  t.u[n++] = WgUnit{DH(7), 256, X(6), 256, 256, W(7), kW, B(7), 120, 1};
+  t.u[n++] = WgUnit{DA_FEAT, 256, X(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 120, 1};
+  t.u[n++] = WgUnit{DA_HV, 128, X(8), 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 95, 1};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 88, 0};
   t.total_cost = 0;
   for (int i = 0; i < kWgUnits; ++i) t.total_cost += t.u[i].cost;
   return t;
@@ -380,15 +387,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const uint32_t bar_full = sbase + WG_BAR, bar_empty = bar_full + 8 * kWgStages;
   const uint32_t bar_acc_full = bar_empty + 8 * kWgStages, bar_acc_empty = bar_acc_full + 8;
+  const uint32_t bar_conv = bar_acc_empty + 8, bar_b16free = bar_conv + 16;     // [2] each: widened B ready / consumed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + WG_BAR + 192);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + 128); }
     mbar_init(bar_acc_full, 1);
     mbar_init(bar_acc_empty, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_conv + 8 * b, 128); mbar_init(bar_b16free + 8 * b, 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
@@ -397,22 +406,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
   tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // one (unit, tile range) segment per CTA: the host gave every unit a CTA count proportional to its tensor cost
+  // one (unit, tile range) segment per CTA: the host gave every unit a CTA count proportional to its cost
   const int64_t T = p.tiles;
   uint32_t stage = 0, phase = 0;          // ring position: every role walks the same sequence
   uint32_t seg_phase = 0;
+  uint32_t nconv = 0;                     // widened slabs so far (buffer = nconv & 1, use = nconv >> 1)
   for (int ui = 0; ui < kWgUnits; ++ui) {
     if ((int)blockIdx.x < p.cta_begin[ui] || (int)blockIdx.x >= p.cta_begin[ui + 1]) continue;
     const WgUnit u = p.tab.u[ui];
     const int64_t gu = p.cta_begin[ui + 1] - p.cta_begin[ui], ju = (int)blockIdx.x - p.cta_begin[ui];
     const int64_t t0 = T * ju / gu, t1 = T * (ju + 1) / gu;
-    const int a_atoms = u.m_out / 64, b_atoms = u.n_in / 64;
-    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_atoms) * kWgSlabBytes;
+    const int a_atoms = u.m_out / 64, b_pieces = u.b_fp8 ? 2 : 1;
+    const uint32_t stage_bytes = (uint32_t)(a_atoms + b_pieces) * kWgSlabBytes;
     const int64_t nslabs = (t1 - t0) * (kTileM / kWgSlabRows);
     const long long seg_t0 = clock64();
 
     if (warp == 0) {
-      // ---- producer: 32-sample slabs of dpre (A) and layer input (B).  Each of the <= 8 slab copies of a stage is
+      // ---- producer: 64-sample slabs of dpre (A) and of the layer input (B).  Each of the <= 6 slab copies of a stage is
       //      issued by its own lane (one thread retires at most one cp.async.bulk per ~700 cycles, tools/bulk_rate.py)
       for (int64_t sl = 0; sl < nslabs; ++sl) {
         const int64_t tile = t0 + sl / (kTileM / kWgSlabRows);
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
         } else if (lane < a_atoms) {
           const uint8_t* dsrc = p.dstash + (size_t)tile * kDstashTileBytes + (size_t)(u.d_atom + lane) * kAtomBytes + j * kWgSlabBytes;
           bulk_g2s(dstA + lane * kWgSlabBytes, dsrc, kWgSlabBytes, bar_full + 8 * stage);
-        } else if (lane < a_atoms + b_atoms) {
+        } else if (lane < a_atoms + b_pieces) {
           const int at = lane - a_atoms;
           const uint8_t* isrc = p.stash + (size_t)tile * kStashTileBytes + (size_t)(u.in_atom + at) * kAtomBytes + j * kWgSlabBytes;
           bulk_g2s(dstB + at * kWgSlabBytes, isrc, kWgSlabBytes, bar_full + 8 * stage);
@@ -436,42 +446,55 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {   // ---- MMA issuer: D[out, in] += dpre^T[out, k] . in[k, in],  k = sample
-        const uint32_t idesc = make_idesc(128, u.n_in, 1, 1);
-        mbar_wait(bar_acc_empty, seg_phase ^ 1);     // previous segment's accumulators flushed
-        tcgen05_fence_after_sync();
-        uint32_t accumulate = 0;
-        for (int64_t sl = 0; sl < nslabs; ++sl) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tcgen05_fence_after_sync();
-          const uint32_t aA = sbase + stage * kWgStageBytes, aB = aA + 4 * kWgSlabBytes;
-          for (int k = 0; k < kWgSlabRows / 16; ++k) {
-            const uint64_t b_desc = make_smem_desc(aB + k * 2048, kWgSlabBytes, 1024);
-            for (int h = 0; h < u.m_out / 128; ++h) {
-              const uint64_t a_desc = make_smem_desc(aA + h * 2 * kWgSlabBytes + k * 2048, kWgSlabBytes, 1024);
-              if (!(p.debug & 1)) umma_bf16(tmem_base + (uint32_t)h * 256u, a_desc, b_desc, idesc, accumulate);
-            }
-            accumulate = 1;
-          }
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      // ---- MMA issuer (whole warp, uniform control flow: tc_common.cuh elect_one): D[out, in] += dpre^T[out, k] . in[k, in],  k = sample
+      const uint32_t idesc = make_idesc(128, u.n_in, 1, 1);
+      const uint32_t tmem_u = uniform_u32(tmem_base);
+      const int halves = u.m_out / 128;
+      mbar_wait(bar_acc_empty, seg_phase ^ 1);     // previous segment's accumulators flushed
+      tcgen05_fence_after_sync();
+      uint32_t accumulate = 0;
+      for (int64_t sl = 0; sl < nslabs; ++sl) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        uint32_t aB = sbase + stage * kWgStageBytes + 4 * kWgSlabBytes;
+        if (u.b_fp8) {
+          const uint32_t cb = nconv & 1u;
+          mbar_wait(bar_conv + 8 * cb, (nconv >> 1) & 1u);      // the converter warps have widened this slab
+          aB = sbase + WG_B16 + cb * (4 * kWgSlabBytes);
         }
-        if (nslabs > 0) umma_commit(bar_acc_full);
-      } else {
-        for (int64_t sl = 0; sl < nslabs; ++sl) if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        tcgen05_fence_after_sync();
+        const uint64_t a_desc = make_smem_desc(sbase + stage * kWgStageBytes, kWgSlabBytes, 1024);
+        const uint64_t b_desc = make_smem_desc(aB, kWgSlabBytes, 1024);
+        if (!(p.debug & 1) && elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kWgSlabRows / 16; ++k) {
+            // 16 samples = 2 KB inside every 64-feature block; the second 128 output rows are two blocks (16 KB) further
+            umma_bf16(tmem_u, a_desc + (uint64_t)(128 * k), b_desc + (uint64_t)(128 * k), idesc, k ? 1u : accumulate);
+            if (halves == 2) umma_bf16(tmem_u + 256u, a_desc + (uint64_t)(1024 + 128 * k), b_desc + (uint64_t)(128 * k), idesc, k ? 1u : accumulate);
+          }
+        }
+        accumulate = 1;
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * stage);
+          if (u.b_fp8) umma_commit(bar_b16free + 8 * (nconv & 1u));
+        }
+        if (u.b_fp8) ++nconv;
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
+      if (nslabs > 0 && elect_one()) umma_commit(bar_acc_full);
     } else {
-      // ---- column sums (bias gradient) from the dpre slabs, then the accumulator flush
-      // thread = (row group rg of 8 samples) x (16-byte chunk j = 8 output features): 8 x LDS.128 per slab, all
-      // issued before the first use, so the slab is released (empty barrier) after ~100 instructions
+      // ---- converter + column sums (bias gradient) from the dpre slabs, then the accumulator flush
       const int tid = threadIdx.x - 64;           // 0..127
       const int q = warp & 3;
       const int j = tid & 31, rg = tid >> 5;
       float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const bool do_bias = u.b_off >= 0 && 8 * j < u.m_out;
+      // widening: lane = (row rr of an 8-row block, 16-byte chunk jl of a 64-byte run); warp w, iteration i -> combination w * 8 + i
+      // of (atom hh, upper/lower 64 bytes jh, row block rb).  Stores cover all 8 chunk positions of two rows per quarter warp.
+      const int rr = lane >> 2, jl = lane & 3, cw = warp - 2;
       for (int64_t sl = 0; sl < nslabs; ++sl) {
         mbar_wait(bar_full + 8 * stage, phase);
         if (do_bias && !(p.debug & 2)) {
+          // thread = (row group rg of 8 samples) x (16-byte chunk j = 8 output features): 8 x LDS.128 per 32 rows
           const uint32_t abase = sbase + stage * kWgStageBytes + (j >> 3) * kWgSlabBytes;
 #pragma unroll
           for (int sub = 0; sub < kWgSlabRows / 32; ++sub) {
@@ -489,6 +512,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
               bs[6] += __uint_as_float(w[i].w << 16); bs[7] += __uint_as_float(w[i].w & 0xffff0000u);
             }
           }
+        }
+        if (u.b_fp8) {
+          const uint32_t cb = nconv & 1u;
+          mbar_wait(bar_b16free + 8 * cb, ((nconv >> 1) & 1u) ^ 1u);   // the MMAs of the slab before last have read this buffer
+          const uint32_t raw = sbase + stage * kWgStageBytes + 4 * kWgSlabBytes;
+          const uint32_t dst = sbase + WG_B16 + cb * (4 * kWgSlabBytes);
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int combo = cw * 8 + i;
+            const int hh = combo & 1, jh = (combo >> 1) & 1, rb = combo >> 2;
+            const uint32_t r = (uint32_t)(rb * 8 + rr);
+            const uint4 v = lds128u(raw + (uint32_t)hh * kWgSlabBytes + r * 128u + ((uint32_t)((jh * 4 + jl) ^ rr) << 4));
+            uint32_t o[8];
+            e4m3x4_to_bf16x4(v.x, o[0], o[1]); e4m3x4_to_bf16x4(v.y, o[2], o[3]);
+            e4m3x4_to_bf16x4(v.z, o[4], o[5]); e4m3x4_to_bf16x4(v.w, o[6], o[7]);
+            // features 64 hh + 16 jl + 128 jh ... + 15: 64-feature block hh + 2 jh, chunks 2 jl and 2 jl + 1 of row r
+            const uint32_t row_a = dst + (uint32_t)(hh + 2 * jh) * kWgSlabBytes + r * 128u;
+            sts128(row_a + ((uint32_t)((2 * jl) ^ rr) << 4), o[0], o[1], o[2], o[3]);
+            sts128(row_a + ((uint32_t)((2 * jl + 1) ^ rr) << 4), o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(bar_conv + 8 * cb);
+          ++nconv;
         }
         mbar_arrive(bar_empty + 8 * stage);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
@@ -510,12 +556,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
             tmem_ld_wait();
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
+            for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)   // one full 128-byte line per thread and batch, no atomics
-            prow[cb * 8 + j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int jj = 0; jj < 8; ++jj)   // one full 128-byte line per thread and batch, no atomics
+            prow[cb * 8 + jj] = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                            __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
         }
       }
       tcgen05_fence_before_sync();
@@ -549,10 +595,10 @@ __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const WgradParams
 // =====================================================================================================
 // rgb / sigma heads: dWr[3,128] += d_rgb^T hv,  dbr,  dWa[256] += d_sigma h7,  dba
 // =====================================================================================================
-// 8 warps per block, warp w owns rows 16w..16w+15 of a tile; lane l reads the 16-byte chunk (8 features) l of the 256-wide
-// h7 row (atom l / 8, chunk l % 8) and, for l < 16, chunk l of the 128-wide hv row: every load instruction of a warp
-// covers whole 128-byte lines of the swizzled stash atoms.  Partials live in registers across the block's tiles and are
-// combined through shared memory once, then 643 atomics per block.
+// 8 warps per block, warp w owns rows 16w..16w+15 of a tile.  h7 is the E4M3 stash image (two 128-byte rows per sample): lanes
+// 0..15 read one 16-byte chunk (16 features) each; hv is bf16 (one 16-byte chunk = 8 features per lane, lanes 0..15): every load
+// instruction of a warp covers whole 128-byte lines.  Partials live in registers across the block's tiles and are combined
+// through shared memory once, then 643 atomics per block.
 __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* __restrict__ stash,
                                                               const float* __restrict__ d_raw, int64_t m,
                                                               int64_t tiles, float* __restrict__ g_wr,
@@ -561,9 +607,12 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
   __shared__ float4 s_d[kTileM];
   __shared__ float s_red[8][32][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float wa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float wa[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) wa[e] = 0.f;
   float wr[3][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   float sb[4] = {0, 0, 0, 0};
+  const int l16 = lane & 15;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
     if (tid < kTileM) {
@@ -572,27 +621,31 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
     }
     __syncthreads();
     const uint8_t* st = stash + (size_t)tile * kStashTileBytes;
-    const uint8_t* h7 = st + (size_t)(SA_H0 + 28 + (lane >> 3)) * kAtomBytes;
-    const uint8_t* hv = st + (size_t)(SA_HV + ((lane & 15) >> 3)) * kAtomBytes;
+    const uint8_t* h7 = st + (size_t)stash_x_atom(7, l16 >> 3) * kAtomBytes;     // lane -> (half, chunk l16 & 7)
+    const uint8_t* hv = st + (size_t)(SA_HV + (l16 >> 3)) * kAtomBytes;
+    if (lane < 16) {
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {       // 8 rows in flight per lane: 12 x 16 B loads, ~100 registers
-      uint4 q7[8], qv[8];
+      for (int half = 0; half < 2; ++half) {       // 8 rows in flight per lane
+        uint4 q7[8], qv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t rr = (uint32_t)(warp * 16 + half * 8 + i);
-        q7[i] = __ldg(reinterpret_cast<const uint4*>(h7 + sw128_off(rr, (uint32_t)(lane & 7))));
-        if (lane < 16) qv[i] = __ldg(reinterpret_cast<const uint4*>(hv + sw128_off(rr, (uint32_t)(lane & 7))));
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 d = s_d[warp * 16 + half * 8 + i];
-        const uint32_t w7[4] = {q7[i].x, q7[i].y, q7[i].z, q7[i].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          wa[2 * e] = fmaf(d.w, __uint_as_float(w7[e] << 16), wa[2 * e]);
-          wa[2 * e + 1] = fmaf(d.w, __uint_as_float(w7[e] & 0xffff0000u), wa[2 * e + 1]);
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = (uint32_t)(warp * 16 + half * 8 + i);
+          q7[i] = __ldg(reinterpret_cast<const uint4*>(h7 + sw128_off(rr, (uint32_t)(lane & 7))));
+          qv[i] = __ldg(reinterpret_cast<const uint4*>(hv + sw128_off(rr, (uint32_t)(lane & 7))));
         }
-        if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 d = s_d[warp * 16 + half * 8 + i];
+          const uint32_t w7[4] = {q7[i].x, q7[i].y, q7[i].z, q7[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t lo, hi;
+            e4m3x4_to_f16x4(w7[e], lo, hi);
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+            wa[4 * e + 0] = fmaf(d.w, f01.x, wa[4 * e + 0]); wa[4 * e + 1] = fmaf(d.w, f01.y, wa[4 * e + 1]);
+            wa[4 * e + 2] = fmaf(d.w, f23.x, wa[4 * e + 2]); wa[4 * e + 3] = fmaf(d.w, f23.y, wa[4 * e + 3]);
+          }
           const uint32_t wv[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -601,13 +654,13 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
             wr[1][2 * e] = fmaf(d.y, h0, wr[1][2 * e]); wr[1][2 * e + 1] = fmaf(d.y, h1, wr[1][2 * e + 1]);
             wr[2][2 * e] = fmaf(d.z, h0, wr[2][2 * e]); wr[2][2 * e + 1] = fmaf(d.z, h1, wr[2][2 * e + 1]);
           }
+          if (lane == 15) { sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
         }
-        if (lane == 31) { sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
       }
     }
   }
-  // block reduction over the 8 warps, one quantity at a time through the same shared buffer
-  auto reduce8 = [&](const float (&v)[8], float* dst, int n_lanes) {
+  // block reduction over the 8 warps, one quantity at a time through the same shared buffer; lane l < n_lanes owns dst[off(l) + e]
+  auto reduce8 = [&](const float* v, float* dst, int n_lanes, auto off) {
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_red[warp][lane][e] = v[e];
@@ -618,14 +671,16 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
         float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) acc += s_red[w][lane][e];
-        atomicAdd(dst + 8 * lane + e, acc);
+        atomicAdd(dst + off(lane) + e, acc);
       }
     }
   };
-  reduce8(wa, g_wa, 32);                         // d alpha_linear.weight [256]
-  reduce8(wr[0], g_wr, 16);                      // d rgb_linear.weight [3][128]
-  reduce8(wr[1], g_wr + kWV, 16);
-  reduce8(wr[2], g_wr + 2 * kWV, 16);
+  // d alpha_linear.weight [256]: lane (half, chunk) holds features stash_x_feature(half, chunk) .. + 15
+  reduce8(wa, g_wa, 16, [](int l) { return stash_x_feature(l >> 3, l & 7); });
+  reduce8(wa + 8, g_wa, 16, [](int l) { return stash_x_feature(l >> 3, l & 7) + 8; });
+  reduce8(wr[0], g_wr, 16, [](int l) { return 8 * l; });                      // d rgb_linear.weight [3][128]
+  reduce8(wr[1], g_wr + kWV, 16, [](int l) { return 8 * l; });
+  reduce8(wr[2], g_wr + 2 * kWV, 16, [](int l) { return 8 * l; });
   {
     const float v[8] = {sb[0], sb[1], sb[2], sb[3], 0.f, 0.f, 0.f, 0.f};
     __syncthreads();
@@ -634,7 +689,7 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
     __syncthreads();
     if (tid < 4) {
       float acc = 0.f;
-      for (int w = 0; w < 8; ++w) acc += s_red[w][31][tid];
+      for (int w = 0; w < 8; ++w) acc += s_red[w][15][tid];
       atomicAdd(tid < 3 ? g_br + tid : g_ba, acc);
     }
   }

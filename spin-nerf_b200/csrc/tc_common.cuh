@@ -270,6 +270,65 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
   return d;
 }
 
+// four floats -> four E4M3 bytes (f0 in the lowest byte), round to nearest, saturating; RELU variant clamps negatives to 0
+__device__ __forceinline__ uint32_t pack_e4m3x4(float f0, float f1, float f2, float f3) {
+  uint32_t d;
+  asm("{\n\t"
+      ".reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t"
+      "}"
+      : "=r"(d)
+      : "f"(f0), "f"(f1), "f"(f2), "f"(f3));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_e4m3x4(float f0, float f1, float f2, float f3) {
+  uint32_t d;
+  asm("{\n\t"
+      ".reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.relu.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.relu.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t"
+      "}"
+      : "=r"(d)
+      : "f"(f0), "f"(f1), "f"(f2), "f"(f3));
+  return d;
+}
+// four E4M3 bytes -> two f16x2 words (exact): lo = bytes 0, 1   hi = bytes 2, 3
+__device__ __forceinline__ void e4m3x4_to_f16x4(uint32_t v, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t"
+      ".reg .b16 a, b;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "cvt.rn.f16x2.e4m3x2 %0, a;\n\t"
+      "cvt.rn.f16x2.e4m3x2 %1, b;\n\t"
+      "}"
+      : "=r"(lo), "=r"(hi)
+      : "r"(v));
+}
+
+// four E4M3 bytes -> two bf16x2 words (exact: 3 mantissa bits, exponent range inside bf16's): lo = bytes 0, 1   hi = bytes 2, 3
+__device__ __forceinline__ void e4m3x4_to_bf16x4(uint32_t v, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t"
+      ".reg .b16 a, b, h0, h1, h2, h3;\n\t"
+      ".reg .b32 p, q;\n\t"
+      ".reg .f32 f0, f1, f2, f3;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "cvt.rn.f16x2.e4m3x2 p, a;\n\t"
+      "cvt.rn.f16x2.e4m3x2 q, b;\n\t"
+      "mov.b32 {h0, h1}, p;\n\t"
+      "mov.b32 {h2, h3}, q;\n\t"
+      "cvt.f32.f16 f0, h0;\n\t"
+      "cvt.f32.f16 f1, h1;\n\t"
+      "cvt.f32.f16 f2, h2;\n\t"
+      "cvt.f32.f16 f3, h3;\n\t"
+      "cvt.rn.bf16x2.f32 %0, f1, f0;\n\t"
+      "cvt.rn.bf16x2.f32 %1, f3, f2;\n\t"
+      "}"
+      : "=r"(lo), "=r"(hi)
+      : "r"(v));
+}
+
 // ---- UMMA descriptors --------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle, sm_100 version field = 1.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

@@ -384,6 +384,56 @@ def decode_tiles(buf, tile_bytes, atom0, natoms, ntiles, rows):
     return out[:rows]
 
 
+def _e4m3_table():
+    """all 256 E4M3 (fp8, 4 exponent bits bias 7, 3 mantissa bits, no infinities) values"""
+    t = np.zeros(256, np.float32)
+    for b in range(256):
+        sgn = -1.0 if b & 0x80 else 1.0
+        e, m = (b >> 3) & 15, b & 7
+        if e == 15 and m == 7:
+            v = np.nan
+        elif e == 0:
+            v = m / 8.0 * 2.0 ** -6
+        else:
+            v = (1.0 + m / 8.0) * 2.0 ** (e - 7)
+        t[b] = sgn * v
+    return t
+
+
+E4M3 = _e4m3_table()
+STASH_TILE_BYTES, DSTASH_TILE_BYTES, STASH_ATOMS = 397312, 622592, 22          # mlp_tc.cuh
+SA_ENC, SA_X0, SA_HV, SA_DENC = 0, 1, 19, 21
+
+
+def decode_x8(buf, layer, ntiles, rows):
+    """E4M3 stash image of a 256-wide layer output (layer 0..7 = h0..h7, 8 = feature) -> float32 [rows, 256]:
+    atom SA_X0 + 2*layer + half, row r = 128 bytes, chunk j' at position j' ^ (r & 7) = features 64*half + 16*(j'&3) + 128*(j'>>2) ..+15"""
+    raw = N(buf[:ntiles * STASH_TILE_BYTES]).reshape(ntiles, STASH_TILE_BYTES)
+    out = np.zeros((ntiles * 128, 256), np.float32)
+    r = np.arange(128)
+    for t in range(ntiles):
+        for half in range(2):
+            a = SA_X0 + 2 * layer + half
+            atom = raw[t, a * 16384:(a + 1) * 16384].reshape(128, 8, 16)
+            for j in range(8):
+                f0 = 64 * half + 16 * (j & 3) + 128 * (j >> 2)
+                out[t * 128:(t + 1) * 128, f0:f0 + 16] = E4M3[atom[r, j ^ (r & 7)]]
+    return out[:rows]
+
+
+def decode_masks(buf, slot, ntiles, rows, width=256):
+    """ReLU mask stash (after the atoms): slot x 128 rows x 8 words, column 32w + c at bit ((c & 1) << 4) | (c >> 1) of word w"""
+    raw = N(buf[:ntiles * STASH_TILE_BYTES]).reshape(ntiles, STASH_TILE_BYTES)
+    out = np.zeros((ntiles * 128, width), bool)
+    c = np.arange(32)
+    bit = ((c & 1) << 4) | (c >> 1)
+    for t in range(ntiles):
+        words = raw[t, STASH_ATOMS * 16384:].copy().view(np.uint32).reshape(9, 128, 8)[slot]
+        for w in range(width // 32):
+            out[t * 128:(t + 1) * 128, 32 * w:32 * w + 32] = (words[:, w:w + 1] >> bit[None, :]) & 1
+    return out[:rows]
+
+
 @pytest.mark.parametrize("m", [192, 1000])
 def test_mlp_bf16_backward(m):
     net, p = make_net(11, spn.PREC_BF16)
@@ -403,16 +453,22 @@ def test_mlp_bf16_backward(m):
     torch.cuda.synchronize()
     emu_raw, acts = mlp_forward_bf16(p, x6)
     ntiles = (m + 127) // 128
-    SB, DB = 692224, 622592
-    # forward stash == emulated activations (bf16 exact up to accumulation-order flips of the last bit)
-    h3 = decode_tiles(stash, SB, 1 + 4 * 3, 4, ntiles, m)
-    assert np.abs(h3 - acts["h3"]).max() <= 2e-2 * max(1.0, np.abs(acts["h3"]).max())
-    gpu_acts = {"xp": decode_tiles(stash, SB, 0, 1, ntiles, m)[:, :63], "xd": decode_tiles(stash, SB, 39, 1, ntiles, m)[:, :27],
-                "feat": decode_tiles(stash, SB, 33, 4, ntiles, m), "hv": decode_tiles(stash, SB, 37, 2, ntiles, m)}
+    SB, DB = STASH_TILE_BYTES, DSTASH_TILE_BYTES
+    # forward stash == emulated activations: E4M3 carries 3 mantissa bits (half an ulp = 2^-4 relative)
+    h3 = decode_x8(stash, 3, ntiles, m)
+    assert np.abs(h3 - acts["h3"]).max() <= 7e-2 * max(1.0, np.abs(acts["h3"]).max())
+    assert np.mean(np.abs(h3 - acts["h3"])) <= 3e-2 * np.mean(np.abs(acts["h3"])) + 1e-6     # E4M3: ~2.2 % mean relative rounding error
+    gpu_acts = {"xp": decode_tiles(stash, SB, SA_ENC, 1, ntiles, m)[:, :63], "xd": decode_tiles(stash, SB, SA_DENC, 1, ntiles, m)[:, :27],
+                "feat": decode_x8(stash, 8, ntiles, m), "hv": decode_tiles(stash, SB, SA_HV, 2, ntiles, m)}
     for i in range(8):
-        gpu_acts[f"h{i}"] = decode_tiles(stash, SB, 1 + 4 * i, 4, ntiles, m)
+        gpu_acts[f"h{i}"] = decode_x8(stash, i, ntiles, m)
+    # the ReLU masks the dgrad chain applies are the stashed bit masks (a small activation may round to zero in E4M3)
+    gpu_masks = {f"h{i}": decode_masks(stash, i, ntiles, m) for i in range(8)}
+    gpu_masks["hv"] = decode_masks(stash, 8, ntiles, m, 128)
+    for i in (0, 7):     # mask bits == sign of the emulated activations, up to last-bit flips around zero
+        assert np.mean(gpu_masks[f"h{i}"] != (acts[f"h{i}"] > 0)) < 2e-3
     # emulate the backward on the GPU's own stashed activations (so only the backward is under test)
-    emu_g, dpre = mlp_backward_bf16(p, gpu_acts, gpu_acts, draw)
+    emu_g, dpre = mlp_backward_bf16(p, gpu_acts, gpu_masks, draw)
     d_h7 = decode_tiles(ws, DB, 6, 4, ntiles, m); d_h0 = decode_tiles(ws, DB, 34, 4, ntiles, m)
     d_hv = decode_tiles(ws, DB, 0, 2, ntiles, m)
     off = spn._lib.param_offsets()

@@ -1,3 +1,2 @@
-timeout 400 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-timeout 200 python bench.py --steps 20 --warmup 5 --no_cpu_baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], {k:(round(v['ms_per_step'],3),round(v['achieved'])) for k,v in d['roofline']['kernels'].items()}, d['psnr_vs_ref'])"
-timeout 200 python bench.py --workload render --steps 4 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('render', d['value'], d['ms_per_step'], d['frames_per_sec'], d['roofline']['achieved'])"
+for M in 38400 75776 1048576; do echo "--- M=$M"; timeout 60 python tools/bench_mlp.py $M train 2>&1 | tail -1 | cut -c1-150; done
+timeout 400 python -m pytest tests -q -m gpu -x 2>&1 | tail -5

@@ -14,10 +14,10 @@ raw, _ = ops.mlp_forward_points(flat, packed, T.T(x6), spn.PREC_BF16, stash)
 torch.cuda.synchronize()
 emu, acts = T.mlp_forward_bf16(p, x6)
 ntiles = (m + 127) // 128
-TB = 692224
-names = [("xp", 0, 1)] + [(f"h{i}", 1 + 4 * i, 4) for i in range(8)] + [("feat", 33, 4), ("hv", 37, 2), ("xd", 39, 1)]
-for nm, a0, na in names:
-    got = T.decode_tiles(stash, TB, a0, na, ntiles, m)
+TB = T.STASH_TILE_BYTES
+names = [("xp", T.SA_ENC, 1, None)] + [(f"h{i}", None, None, i) for i in range(8)] + [("feat", None, None, 8), ("hv", T.SA_HV, 2, None), ("xd", T.SA_DENC, 1, None)]
+for nm, a0, na, layer in names:
+    got = T.decode_tiles(stash, TB, a0, na, ntiles, m) if layer is None else T.decode_x8(stash, layer, ntiles, m)
     ref = acts[nm]
     w = ref.shape[1]
     e = np.abs(got[:, :w] - ref)
