@@ -159,6 +159,8 @@ int spn_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K,
 
 /* Diagnostic: cycles (clock64, written to cycles_dev[0]) for `reps` back-to-back tcgen05.mma M=128 x N x K=16 with
  * K-major (0) or MN-major (1) shared-memory operands — the measurement behind DESIGN.md's wgrad layout choice. */
+/* Diagnostic: the weight-gradient kernel's E4M3 -> bf16 widening of the activation stash applied to n codes (device pointers). */
+int spn_tc_e4m3_decode(const uint8_t* codes_dev, uint16_t* bf16_out_dev, int n, void* stream);
 /* CTA-pair (cta_group::2, M = 256) MMA rate: ts = 1 takes the A operand from tensor memory; nacc accumulators in turn;
  * ld_warps warps per CTA generate epilogue-like tcgen05.ld / tcgen05.st traffic meanwhile.  out_dev[0] = cycles for reps MMAs. */
 int spn_tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out_dev, void* stream);

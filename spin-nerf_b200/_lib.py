@@ -72,6 +72,7 @@ _SIGS = {
     "spn_tc_set_trace": (C.c_int, [c_fp]),
     "spn_tc_tmem_ld_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "spn_tc_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "spn_tc_e4m3_decode": (C.c_int, [c_fp, c_fp, C.c_int, c_fp]),
     "spn_tc_mma_rate_pair": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "spn_tc_bulk_rate": (C.c_int, [c_fp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "spn_gather_ray_batch": (C.c_int, [C.c_int, c_fp, c_fp, c_fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -133,6 +133,9 @@ extern "C" int spn_tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long
   return tc_tmem_ld_rate(nwarps, reps, with_mma, out_dev, as_stream(stream));
 }
 
+extern "C" int spn_tc_e4m3_decode(const uint8_t* codes_dev, uint16_t* bf16_out_dev, int n, void* stream) {
+  return tc_e4m3_decode(codes_dev, bf16_out_dev, n, as_stream(stream));
+}
 extern "C" int spn_tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out_dev, void* stream) {
   return tc_mma_rate_pair(ts, n, reps, nacc, ld_warps, out_dev, as_stream(stream));
 }

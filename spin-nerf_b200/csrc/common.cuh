@@ -138,6 +138,7 @@ int tc_bulk_rate(const void* src, size_t src_bytes, int copy_bytes, int depth, i
                  long long* out, cudaStream_t st);
 int tc_tmem_ld_rate(int nwarps, int reps, int with_mma, long long* out, cudaStream_t st);
 int tc_mma_rate(int a_mn, int b_mn, int n, int reps, long long* cycles_dev, cudaStream_t st);
+int tc_e4m3_decode(const uint8_t* codes, uint16_t* out, int n, cudaStream_t st);
 int tc_mma_rate_pair(int ts, int n, int reps, int nacc, int ld_warps, long long* out, cudaStream_t st);
 int tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_t m, float* grads,

@@ -327,7 +327,8 @@ constexpr int kWgSlabBytes = kWgSlabRows * 128; // one atom's slab: 8 KB
 constexpr int kWgStageBytes = 6 * kWgSlabBytes; // A: 4 slabs (32 KB) at +0;  B as it lands: 2 E4M3 slabs or 1 bf16 slab at +32 KB
 constexpr int WG_B16 = kWgStages * kWgStageBytes;          // 2 x 32 KB: the widened (bf16) B operand, double-buffered
 constexpr int WG_BAR = WG_B16 + 2 * 4 * kWgSlabBytes;
-constexpr int kWgThreads = 192;
+constexpr int kWgConvWarps = 8;                   // warps 2..9 widen the E4M3 slabs; warps 2..5 also take the bias column sums and the flush
+constexpr int kWgThreads = 32 * (2 + kWgConvWarps);
 constexpr int kWgSmemBytes = WG_BAR + 256 + 1024;
 static_assert(kWgSmemBytes <= 232448, "wgrad shared memory budget");
 
@@ -353,17 +354,16 @@ static WgTable build_wg_table() {
   auto DH = [&](int i) { return DA_H7 + 4 * (7 - i); };
   auto X = [&](int layer) { return stash_x_atom(layer, 0); };
   int n = 0;
-  // cost ~ CTA-cycles per tile (HBM bytes of a slab plus the per-slab copy round): 64 KB slabs measured 138 in round 1
-  // (tools/trace_wgrad.py); the E4M3 input makes a wide unit's slab 48 KB
-  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 115, 0};
-  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, X(i - 1), 256, 256, W(i), kW, B(i), 120, 1};
-  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 104, 0};
-  t.u[n++] = WgUnit{DH(5), 256, X(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 120, 1};
-  t.u[n++] = WgUnit{DH(6), 256, X(5), 256, 256, W(6), kW, B(6), 120, 1};
-  t.u[n++] = WgUnit{DH(7), 256, X(6), 256, 256, W(7), kW, B(7), 120, 1};
-  t.u[n++] = WgUnit{DA_FEAT, 256, X(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 120, 1};
-  t.u[n++] = WgUnit{DA_HV, 128, X(8), 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 95, 1};
-  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 88, 0};
+  // cost = measured CTA-cycles per tile (tools/trace_wgrad.py, profiles/r02d_wgrad_cta_balance.txt), wide unit = 127
+  t.u[n++] = WgUnit{DH(0), 256, SA_ENC, 64, kEncP, W(0), kEncP, B(0), 86, 0};
+  for (int i = 1; i <= 4; ++i) t.u[n++] = WgUnit{DH(i), 256, X(i - 1), 256, 256, W(i), kW, B(i), 127, 1};
+  t.u[n++] = WgUnit{DH(5), 256, SA_ENC, 64, kEncP, W(5), kW + kEncP, -1, 75, 0};
+  t.u[n++] = WgUnit{DH(5), 256, X(4), 256, 256, W(5) + kEncP, kW + kEncP, B(5), 127, 1};
+  t.u[n++] = WgUnit{DH(6), 256, X(5), 256, 256, W(6), kW, B(6), 127, 1};
+  t.u[n++] = WgUnit{DH(7), 256, X(6), 256, 256, W(7), kW, B(7), 127, 1};
+  t.u[n++] = WgUnit{DA_FEAT, 256, X(7), 256, 256, (int)po.off[T_WF], kW, (int)po.off[T_BF], 127, 1};
+  t.u[n++] = WgUnit{DA_HV, 128, X(8), 256, 256, (int)po.off[T_WV], kW + kEncD, (int)po.off[T_BV], 113, 1};
+  t.u[n++] = WgUnit{DA_HV, 128, SA_DENC, 64, kEncD, (int)po.off[T_WV] + kW, kW + kEncD, -1, 68, 0};
   t.total_cost = 0;
   for (int i = 0; i < kWgUnits; ++i) t.total_cost += t.u[i].cost;
   return t;
@@ -394,10 +394,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + WG_BAR + 192);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + 128); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1 + kWgConvWarps); }
     mbar_init(bar_acc_full, 1);
     mbar_init(bar_acc_empty, 128);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_conv + 8 * b, 128); mbar_init(bar_b16free + 8 * b, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_conv + 8 * b, kWgConvWarps); mbar_init(bar_b16free + 8 * b, 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
@@ -482,15 +482,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
       }
       if (nslabs > 0 && elect_one()) umma_commit(bar_acc_full);
     } else {
-      // ---- converter + column sums (bias gradient) from the dpre slabs, then the accumulator flush
-      const int tid = threadIdx.x - 64;           // 0..127
+      // ---- converter warps (2..9) + column sums (bias gradient, warps 2..5) from the dpre slabs, then the accumulator flush (warps 2..5)
+      const int tid = threadIdx.x - 64;           // 0..255
       const int q = warp & 3;
-      const int j = tid & 31, rg = tid >> 5;
+      const int cw = warp - 2;                    // 0..7
+      const int j = tid & 31, rg = (tid >> 5) & 3;
       float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const bool do_bias = u.b_off >= 0 && 8 * j < u.m_out;
-      // widening: lane = (row rr of an 8-row block, 16-byte chunk jl of a 64-byte run); warp w, iteration i -> combination w * 8 + i
+      const bool do_bias = cw < 4 && u.b_off >= 0 && 8 * j < u.m_out;
+      // widening: lane = (row rr of an 8-row block, 16-byte chunk jl of a 64-byte run); warp cw, iteration i -> combination cw * 4 + i
       // of (atom hh, upper/lower 64 bytes jh, row block rb).  Stores cover all 8 chunk positions of two rows per quarter warp.
-      const int rr = lane >> 2, jl = lane & 3, cw = warp - 2;
+      const int rr = lane >> 2, jl = lane & 3;
       for (int64_t sl = 0; sl < nslabs; ++sl) {
         mbar_wait(bar_full + 8 * stage, phase);
         if (do_bias && !(p.debug & 2)) {
@@ -518,9 +519,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
           mbar_wait(bar_b16free + 8 * cb, ((nconv >> 1) & 1u) ^ 1u);   // the MMAs of the slab before last have read this buffer
           const uint32_t raw = sbase + stage * kWgStageBytes + 4 * kWgSlabBytes;
           const uint32_t dst = sbase + WG_B16 + cb * (4 * kWgSlabBytes);
-#pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int combo = cw * 8 + i;
+#pragma unroll
+          for (int i = 0; i < 32 / kWgConvWarps; ++i) {
+            const int combo = cw * (32 / kWgConvWarps) + i;
             const int hh = combo & 1, jh = (combo >> 1) & 1, rb = combo >> 2;
             const uint32_t r = (uint32_t)(rb * 8 + rr);
             const uint4 v = lds128u(raw + (uint32_t)hh * kWgSlabBytes + r * 128u + ((uint32_t)((jh * 4 + jl) ^ rr) << 4));
@@ -533,12 +534,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradPar
             sts128(row_a + ((uint32_t)((2 * jl + 1) ^ rr) << 4), o[4], o[5], o[6], o[7]);
           }
           fence_proxy_async_smem();
-          mbar_arrive(bar_conv + 8 * cb);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_conv + 8 * cb);
           ++nconv;
         }
-        mbar_arrive(bar_empty + 8 * stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
+      if (cw >= 4) { seg_phase ^= 1; continue; }      // the flush below is the first four warps' (one per TMEM lane quarter)
       if (do_bias) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(p.grads + u.b_off + 8 * j + e, bs[e]);
@@ -695,6 +699,24 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
   }
 }
 
+// ---- diagnostic: the weight-gradient kernel's E4M3 -> bf16 widening, four codes per thread (tests: all 256 codes) ----
+__global__ void e4m3_decode_kernel(const uint8_t* __restrict__ codes, uint16_t* __restrict__ out, int n) {
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  uint32_t v = 0;
+  for (int e = 0; e < 4 && i + e < n; ++e) v |= (uint32_t)codes[i + e] << (8 * e);
+  uint32_t lo, hi;
+  e4m3x4_to_bf16x4(v, lo, hi);
+  const uint16_t r[4] = {(uint16_t)(lo & 0xffff), (uint16_t)(lo >> 16), (uint16_t)(hi & 0xffff), (uint16_t)(hi >> 16)};
+  for (int e = 0; e < 4 && i + e < n; ++e) out[i + e] = r[e];
+}
+int tc_e4m3_decode(const uint8_t* codes, uint16_t* out, int n, cudaStream_t st) {
+  SPN_CHECK_ARG(codes && out && n > 0, "spn_tc_e4m3_decode: bad arguments");
+  e4m3_decode_kernel<<<(n / 4 + 128) / 128, 128, 0, st>>>(codes, out, n);
+  SPN_LAUNCH_CHECK("e4m3_decode_kernel");
+  return SPN_OK;
+}
+
 // =====================================================================================================
 int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_t m, float* grads, void* ws,
                cudaStream_t st) {
@@ -729,7 +751,7 @@ int mlp_tc_bwd(const void* packed, const void* stash, const float* d_raw, int64_
   // run longest (cost / CTAs), which minimises the slowest CTA; a unit never gets more CTAs than tiles.
   int target = sm_count();
   {
-    const int64_t enough = (int64_t)wg_tab.total_cost * tiles / (2 * 138);   // ~2 tiles of a big unit per CTA at least
+    const int64_t enough = (int64_t)wg_tab.total_cost * tiles / (2 * 127);   // ~2 tiles of a big unit per CTA at least
     if (enough < target) target = (int)enough;
     if (target < kWgUnits) target = kWgUnits;
   }

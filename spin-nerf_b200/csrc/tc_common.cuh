@@ -307,26 +307,21 @@ __device__ __forceinline__ void e4m3x4_to_f16x4(uint32_t v, uint32_t& lo, uint32
       : "r"(v));
 }
 
-// four E4M3 bytes -> two bf16x2 words (exact: 3 mantissa bits, exponent range inside bf16's): lo = bytes 0, 1   hi = bytes 2, 3
+// two E4M3 bytes -> bf16x2, exact for every finite code including the subnormals, in five full-rate instructions (the cvt
+// chain e4m3x2 -> f16x2 -> f32 -> bf16x2 runs on the quarter-rate conversion unit and made the weight-gradient kernel
+// conversion-bound).  `sel` picks the two bytes: 0x1404 = bytes 0, 1   0x3424 = bytes 2, 3.  Each byte s eeee mmm is placed as
+// the bf16 pattern s 0000eeee mmm0000 — the number 2^(e-127) (1 + m/8), or the bf16 SUBNORMAL (m/8) 2^-126 when e = 0 — and
+// multiplied by 2^120 (E4M3 bias 7): 2^(e-7) (1 + m/8) resp. (m/8) 2^-6.  bf16 fma has no flush-to-zero mode (checked for all
+// 256 codes by tests/test_gpu_parity.py::test_e4m3_decode_all_codes).
+__device__ __forceinline__ uint32_t e4m3x2_to_bf16x2(uint32_t v, uint32_t sel) {
+  const uint32_t x = __byte_perm(v, 0u, sel);            // halves = byte << 8
+  uint32_t y = (x & 0x80008000u) | ((x & 0x7f007f00u) >> 4);
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(y) : "r"(y), "r"(0x7B807B80u), "r"(0x80008000u));
+  return y;
+}
 __device__ __forceinline__ void e4m3x4_to_bf16x4(uint32_t v, uint32_t& lo, uint32_t& hi) {
-  asm("{\n\t"
-      ".reg .b16 a, b, h0, h1, h2, h3;\n\t"
-      ".reg .b32 p, q;\n\t"
-      ".reg .f32 f0, f1, f2, f3;\n\t"
-      "mov.b32 {a, b}, %2;\n\t"
-      "cvt.rn.f16x2.e4m3x2 p, a;\n\t"
-      "cvt.rn.f16x2.e4m3x2 q, b;\n\t"
-      "mov.b32 {h0, h1}, p;\n\t"
-      "mov.b32 {h2, h3}, q;\n\t"
-      "cvt.f32.f16 f0, h0;\n\t"
-      "cvt.f32.f16 f1, h1;\n\t"
-      "cvt.f32.f16 f2, h2;\n\t"
-      "cvt.f32.f16 f3, h3;\n\t"
-      "cvt.rn.bf16x2.f32 %0, f1, f0;\n\t"
-      "cvt.rn.bf16x2.f32 %1, f3, f2;\n\t"
-      "}"
-      : "=r"(lo), "=r"(hi)
-      : "r"(v));
+  lo = e4m3x2_to_bf16x2(v, 0x1404u);
+  hi = e4m3x2_to_bf16x2(v, 0x3424u);
 }
 
 // ---- UMMA descriptors --------------------------------------------------------------------------

@@ -434,6 +434,17 @@ def decode_masks(buf, slot, ntiles, rows, width=256):
     return out[:rows]
 
 
+def test_e4m3_decode_all_codes():
+    """the weight-gradient kernel's five-instruction E4M3 -> bf16 widening is exact for every finite code, subnormals included"""
+    codes = torch.arange(256, dtype=torch.uint8, device=DEV)
+    out = torch.zeros(256, dtype=torch.int16, device=DEV)
+    spn._lib.check(spn._lib.lib().spn_tc_e4m3_decode(spn._lib.ptr(codes), spn._lib.ptr(out), 256, spn._lib.stream()), "e4m3 decode")
+    torch.cuda.synchronize()
+    got = (N(out).view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+    finite = ~np.isnan(E4M3)
+    assert np.array_equal(got[finite], E4M3[finite]), np.nonzero(got[finite] != E4M3[finite])
+
+
 @pytest.mark.parametrize("m", [192, 1000])
 def test_mlp_bf16_backward(m):
     net, p = make_net(11, spn.PREC_BF16)
