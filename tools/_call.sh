@@ -1,3 +1,1 @@
-timeout 120 python tools/trace_wgrad.py > gpurun_out/r02d_wgrad_cta_balance.txt 2>&1
-timeout 200 python bench.py --steps 20 --warmup 5 --no_cpu_baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], {k:(round(v['ms_per_step'],3),round(v['achieved'])) for k,v in d['roofline']['kernels'].items()}, d['final_loss'])"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 250 --csv --log-file gpurun_out/r02d_launches.csv python bench.py --steps 8 --warmup 3 --no_cpu_baseline --deadline 0 > /dev/null 2>&1
+SPN_TRACE_BLOCK=1 timeout 120 python tools/trace_fwd_ts.py 1048576 train > gpurun_out/r02d_trace_ts_train_peer.txt 2>&1; tail -1 gpurun_out/r02d_trace_ts_train_peer.txt

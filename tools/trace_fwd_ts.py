@@ -38,6 +38,6 @@ for it in range(3):
             dd = lambda a, b: (r2[b] - r2[a]) if r2[a] >= 0 and r2[b] >= 0 else -1
             print(f"{it:5d} {s:4d} {tl:4d} | " + " ".join(f"{x:8d}" for x in rel) +
                   f" | {d(0, 2):8d} {d(2, 4):8d}   {d(1, 3):8d} {d(3, 5):8d}   {d(5, 7):8d}"
-                  f" | half a: ld {dd(4, 8)} free {dd(8, 9)} math {dd(9, 6)} fence {dd(6, 10)} | half b: st+ld {dd(5, 11)} free {dd(11, 12)} math {dd(12, 13)} tail {dd(13, 7)}")
+                  f" | half a: ld+free {dd(4, 9)} math {dd(9, 6)} | half b: st+ld+free {dd(5, 12)} math {dd(12, 13)} tail {dd(13, 7)}")
 starts = [int(t[i, 0, 0, 0]) for i in range(3)]
 print("cycles per pair-round:", [starts[i + 1] - starts[i] for i in range(2)])
