@@ -168,27 +168,93 @@ def gpu_reference_port(spn, dev, pool, rgb_pool, disp_pool, n_rand, steps=6, war
                     "torch.optim.Adam) on the same GPU and workload; device-timed", "final_loss": float(loss.detach())}
 
 
-def psnr_vs_reference_port(spn, dev, nets, pool, n_rays=512):
-    """The second half of BASELINE.json's metric ("PSNR vs ref"): this library's render (the benchmark's arithmetic mode) against
-    the reference's fp32 formulation (oracle/torch_port.py, TF32 off) on identical rays and the networks as the timed steps left
-    them, deterministic sampling (render_kwargs_test).  A checker leg: a failure costs only this key."""
+def psnr_vs_reference_port(spn, dev, prec, n_rays=1024):
+    """The second half of BASELINE.json's metric ("PSNR vs ref") on a TRAINED scene: the analytic scene the unmodified reference
+    was trained on for tests/golden/convergence.npz (tests/golden/make_convergence_golden.py: 4 views of a textured plane, 300
+    steps, 8.9 -> 30.1 dB) is trained here with the benchmark's arithmetic (same initial weights, same ray batches), then
+    (a) the training PSNR reached is put beside the reference's, and (b) this library's render of held-out rays with the
+    trained weights is compared with the reference's fp32 formulation (oracle/torch_port.py, TF32 off) on the same weights.
+    A checker leg: a failure costs only this key."""
+    import importlib.util
     import torch
     from oracle import torch_port as TP
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    gpath = os.path.join(ROOT, "tests", "golden", "make_convergence_golden.py")
+    spec = importlib.util.spec_from_file_location("make_convergence_golden", gpath)
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "convergence.npz"))
     torch.backends.cuda.matmul.allow_tf32 = False
+    ro, rd, rgb_t, disp_t, idx = gen.problem()
+    nets = []
+    for p in gen.params():
+        net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+        net = net.to(dev); net.precision = prec
+        nets.append(net)
+    tr = trainer_mod.Trainer(nets[0], nets[1], lr=gen.LR, lrate_decay=gen.DECAY, N_samples=64, N_importance=64, lindisp=True,
+                             white_bkgd=True, perturb=0.0, raw_noise_std=0.0, near=gen.NEAR, far=gen.FAR)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pool = T(np.stack([ro, rd], 0)); rgb_pool, disp_pool = T(rgb_t), T(disp_t)
+    psnrs = []
+    for it in range(gen.K):
+        _, ps = tr.step_from_pool(pool, rgb_pool, disp_pool, torch.from_numpy(idx[it]).to(dev))
+        psnrs.append(ps)
+    trained = float(torch.stack(psnrs)[-20:].mean())
     g = torch.Generator(device=dev); g.manual_seed(7)
     ix = torch.randint(0, pool.shape[1], (n_rays,), device=dev, generator=g)
     rays = pool[:, ix].contiguous()
     with torch.no_grad():
-        rgb, disp, acc, depth, ex = spn.render(H, W, FOCAL, chunk=32768, rays=rays, use_viewdirs=True, ndc=False, near=NEAR, far=FAR,
-                                               network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=64,
-                                               N_importance=64, lindisp=True, white_bkgd=True, perturb=0., raw_noise_std=0.)
+        rgb, disp, acc, depth, ex = spn.render(gen.H, gen.W, gen.FOCAL, chunk=32768, rays=rays, use_viewdirs=True, ndc=False,
+                                               near=gen.NEAR, far=gen.FAR, network_query_fn=None, network_fn=nets[0],
+                                               network_fine=nets[1], N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                                               perturb=0., raw_noise_std=0.)
         pc, pf = ({k: v.detach().clone().float() for k, v in n.state_dict().items()} for n in nets)
-        ref = TP.render_rays(rays[0], rays[1], NEAR, FAR, pc, pf, lindisp=True, white_bkgd=True)
+        ref = TP.render_rays(rays[0], rays[1], gen.NEAR, gen.FAR, pc, pf, lindisp=True, white_bkgd=True)
         mse = float(torch.mean((rgb - ref["rgb_map"]) ** 2))
         mse0 = float(torch.mean((ex["rgb0"] - ref["rgb0"]) ** 2))
+        mse_t = float(torch.mean((rgb - rgb_pool[ix]) ** 2)); mse_rt = float(torch.mean((ref["rgb_map"] - rgb_pool[ix]) ** 2))
     db = lambda m: float(-10.0 * np.log10(max(m, 1e-20)))
     return {"rgb_db": db(mse), "rgb0_db": db(mse0), "rays": n_rays,
-            "checker": "oracle/torch_port.py: fp32 PyTorch render of the same rays with the same (trained) weights, TF32 off"}
+            "trained_psnr_db": trained, "reference_trained_psnr_db": float(gold["psnr"][-20:].mean()), "train_steps": int(gen.K),
+            "render_vs_target_db": db(mse_t), "reference_render_vs_target_db": db(mse_rt),
+            "scene": "analytic 4-view scene of tests/golden/make_convergence_golden.py, trained 300 steps with the benchmark's arithmetic",
+            "checker": "oracle/torch_port.py: fp32 PyTorch render of the same rays with the same trained weights, TF32 off; "
+                       "reference_trained_psnr_db from the unmodified reference's own 300-step run (tests/golden/convergence.npz)"}
+
+
+def hbm_write_gbs(dev):
+    """pure-write HBM bandwidth measured live (torch memset of 2 GiB, best of 5): what bounds the stash writes of the training
+    forward / dgrad kernels; MEASURED_PEAKS.json's hbm_gbs is a COPY (half reads, half writes) and overstates it"""
+    import torch
+    x = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); x.zero_(); e1.record(); torch.cuda.synchronize()
+        best = max(best, x.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del x
+    return best
+
+
+def other_workloads(timeout=150):
+    """BASELINE configs[2] and configs[4] at N = 1, each as its own short `bench.py --workload ...` run (fresh process, same JSON
+    contract), so that the default line carries every single-GPU configuration; configs[3] (strong scaling) needs N > 1."""
+    out = {}
+    for name, extra in (("train_lpips", ["--steps", "6", "--warmup", "3"]), ("render", ["--steps", "3", "--warmup", "3"])):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--deadline", str(timeout)] + extra,
+                               capture_output=True, text=True, timeout=timeout + 30, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0")))
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if not line:
+                raise RuntimeError(f"no result line (rc {r.returncode}): {r.stderr.strip()[-240:]}")
+            d = json.loads(line[-1])
+            out[name] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "frames_per_sec", "e2e")}
+            out[name]["workload"] = d["config"]["workload"]
+            if d.get("roofline"):
+                out[name]["mlp_kernels"] = d["roofline"].get("kernels")
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def run_reference(args):
@@ -438,6 +504,7 @@ def main():
     ap.add_argument("--n_rand_global", type=int, default=8192)
     ap.add_argument("--cpu_rays", type=int, default=1024, help="rays per render call in the CPU sample (default: the GPU arm's N_rand, same config)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_other_workloads", action="store_true", help="skip the short configs[2] / configs[4] runs appended to the N = 1 line")
     ap.add_argument("--workload", default="train", choices=["train", "train_lpips", "render"],
                     help="train = BASELINE configs[1] (the headline line, default); train_lpips = configs[2] (N_rand=4096 + 4 LPIPS "
                          "patches of 47x63 per step and GPU); render = configs[4] (full 1008x756 frames through render_path, one "
@@ -572,15 +639,17 @@ def main():
     def host_batches():
         return next(it)        # pinned host tensors: step_graphed copies them H2D into its static inputs
 
+    graph_e2e = os.environ.get("SPN_GRAPH_E2E", "1") != "0"     # N > 1: three graphs with the two eager all-reduces between them
+
     def e2e_steps(k):
         evs = []
         for _ in range(k):
             flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if world == 1:
-                loss, psnr = tr.step_graphed(*host_batches())     # H2D copies + one CUDA-graph replay of the whole step
-            else:   # multi-GPU: eager launches (the step contains an NCCL all-reduce; its graph capture is not validated)
+            if graph_e2e:
+                loss, psnr = tr.step_graphed(*host_batches())     # H2D copies + CUDA-graph replay of the whole step
+            else:   # SPN_GRAPH_E2E=0: eager launches
                 loss, psnr = tr.step(*[t.to(dev, non_blocking=True) for t in host_batches()])
             _ = float(loss)                      # D2H of the step's result (synchronises)
             e1.record()
@@ -622,16 +691,26 @@ def main():
         if n_l and ms_l > 0:
             kern[name] = {"launches_per_step": n_l / args.steps, "ms_per_step": ms_l / args.steps,
                           "tflops": evals_per_rank_step * flop * args.steps / (ms_l * 1e-3) / 1e12}
-    # per-kernel roofline: forward / dgrad are bound by the tensor pipe, wgrad by HBM (it streams every stash and dstash
-    # tile once: 76 atoms of 16 KB per 128-sample tile = 9.73 KB per MLP evaluation)
-    hbm_peak = float(peaks.get("hbm_gbs", 6400.0))
-    wg_bytes_per_eval = 76 * 16384 / 128.0
+    # per-kernel roofline: algorithmic FLOPs and algorithmic HBM bytes per MLP evaluation, each against its
+    # measured peak; the kernel's bound is the larger of the two floors.  Bytes: forward writes the activation stash once
+    # (397 312 B per 128-sample tile: 18 E4M3 atoms + 4 bf16 atoms + masks), dgrad reads the masks and writes the dstash
+    # (38 bf16 atoms), wgrad reads every stash / dstash atom it needs once (20 + 38 atoms of 16 KB).
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_eval = {"mlp_fwd": 397312 / 128.0, "mlp_dgrad": (38 * 16384 + 9 * 128 * 32) / 128.0, "mlp_wgrad": 58 * 16384 / 128.0}
+    try:
+        wr_bw = hbm_write_gbs(dev)
+    except Exception:
+        wr_bw = None
     for name, k in kern.items():
-        if name == "mlp_wgrad":
-            gbs = evals_per_rank_step * wg_bytes_per_eval / (k["ms_per_step"] * 1e-3) / 1e9
-            k.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak)
+        gbs = evals_per_rank_step * bytes_per_eval[name] / (k["ms_per_step"] * 1e-3) / 1e9
+        t_frac, h_frac = k["tflops"] / peak, gbs / hbm_peak
+        k.update(tensor_frac=t_frac, hbm_gbs=gbs, hbm_frac=h_frac)
+        if h_frac >= t_frac:
+            k.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=h_frac)
         else:
-            k.update(bound="tensor", achieved=k["tflops"], peak=peak, unit="TFLOP/s", frac=k["tflops"] / peak)
+            k.update(bound="tensor", achieved=k["tflops"], peak=peak, unit="TFLOP/s", frac=t_frac)
+        if name != "mlp_wgrad" and wr_bw:      # these two only WRITE: a pure-write stream reaches ~60 % of the copy figure on this part
+            k.update(frac_of_measured_write_bw=gbs / wr_bw)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     traffic, traffic_src = None, None
     try:
@@ -645,15 +724,17 @@ def main():
         d = kern[dom]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)") if d["bound"] == "hbm" else peak_src,
-                    "algorithmic_units": "wgrad: 76 x 16 KB stash/dstash atoms per 128-sample tile; fwd/dgrad: 1 186 816 / 1 115 392 FLOP per MLP evaluation",
+                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs (copy: read + write)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)") if d["bound"] == "hbm" else peak_src,
+                    "hbm_write_gbs_measured_live": wr_bw,
+                    "algorithmic_units": "per MLP evaluation: fwd 1 186 816 FLOP / 3 104 B written, dgrad 1 115 392 FLOP / 5 152 B, "
+                                         "wgrad 1 186 816 FLOP / 7 424 B read (58 atoms of 16 KB per 128-sample tile)",
                     "kernels": kern,
                     "step_mlp_flop_frac_of_peak": evals_per_rank_step * (FLOP_FWD + FLOP_BWD) * args.steps / (step_ms * 1e-3) / 1e12 / peak}
     psnr = None
     if world == 1:
         phase("PSNR of the render against the fp32 reference formulation")
         try:
-            psnr = psnr_vs_reference_port(spn, dev, nets, pool)
+            psnr = psnr_vs_reference_port(spn, dev, prec)
         except Exception as e:
             psnr = {"error": f"{type(e).__name__}: {e}"[:300]}
     gpu_port = None
@@ -685,7 +766,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "roofline": roofline, "cpu_baseline": cpu, "gpu_reference_port": gpu_port, "psnr_vs_ref": psnr, "n_rand_per_sec": value / RENDERS_PER_STEP,
-            "wall_s_timed_region": wall, "final_loss": float(loss)}
+            "wall_s_timed_region": wall, "final_loss": float(loss),
+            "stash": "activations E4M3, gradients bf16 (DESIGN.md section 3)"}
+    if world == 1 and not args.no_other_workloads:
+        phase("other workloads (BASELINE configs[2], configs[4]) as short separate runs")
+        del tr, pool, rgb_pool, disp_pool, flush
+        torch.cuda.empty_cache()
+        line["other_workloads"] = other_workloads()
     print(json.dumps(line))
 
 

@@ -48,6 +48,15 @@ def allreduce_sum_(flat_grads, group=None):
     return 1.0 / world
 
 
+def allreduce_sum_async(flat, group=None):
+    """In-place SUM all-reduce issued asynchronously: the collective waits for the work already queued on the current stream
+    (the backward pass that produced `flat`) and runs on the backend's own stream while later launches of the current stream
+    compute.  Returns the work handle (`.wait()` orders the current stream behind the collective) or None without a group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
 def broadcast_parameters(nets, src=0, group=None):
     """Replicas must start identical ("initial weight broadcast (or identical seeds)"): one broadcast of
     each network's flat parameter vector from rank `src`.  No-op without a process group."""

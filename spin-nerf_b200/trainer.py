@@ -11,7 +11,7 @@ import torch
 from . import _lib as L
 from . import ops
 from . import peer
-from .dist import RaySharder, allreduce_sum_
+from .dist import RaySharder, allreduce_sum_, allreduce_sum_async
 from .render import chunk_backward, chunk_forward
 
 
@@ -75,6 +75,8 @@ class Trainer:
             self.gen = torch.Generator(device=dev)
             self.gen.manual_seed(int(seed))
         self._graph = None
+        self._segments = None                   # multi-GPU CUDA-graph mode: [graph to the fine backward, coarse backward, Adam]
+        self._pending = []
 
     # ---------------------------------------------------------------------------------------
     def _global_rows(self, sizes_global):
@@ -198,12 +200,39 @@ class Trainer:
             g["depth_map"] = g_depth
         self.grad_all.zero_()
         gc, gf = self.grads
-        chunk_backward(cfg, k, self.net_c, self.net_f, g, gc, gf,
-                       self._scratch(cfg), self._ws(cfg), detach_range=(n1, n1 + n2))
-        if apply:
-            self.apply_gradients()
+        self._pending = []
+        split = self.sharder.world > 1 and apply and self.peer is None and cfg.n_importance > 0
+        if split:
+            # The fine network's backward runs first and is independent of the coarse one (the resampled depths are detached,
+            # run_nerf.py:700): its gradient all-reduce is issued as soon as it is complete and travels over NVLink (NCCL's
+            # own stream) while the coarse backward computes.
+            fine = {kk: v for kk, v in g.items() if kk in ("rgb_map", "disp_map", "depth_map", "acc_map", "weights")}
+            coarse = {kk: v for kk, v in g.items() if kk in ("rgb0", "disp0", "acc0")}
+            chunk_backward(cfg, k, self.net_c, self.net_f, fine, gc, gf, self._scratch(cfg), self._ws(cfg),
+                           detach_range=(n1, n1 + n2))
+            self._coarse_args = (cfg, k, coarse, (n1, n1 + n2))
+            if self._segments is None:                # eager; in segmented-graph mode the caller runs the rest (step_graphed)
+                self._after_fine_backward()
+        else:
+            chunk_backward(cfg, k, self.net_c, self.net_f, g, gc, gf,
+                           self._scratch(cfg), self._ws(cfg), detach_range=(n1, n1 + n2))
+            if apply:
+                self.apply_gradients()
         res = out[:2].clone()          # `out` is a pooled buffer: hand back copies of (loss, psnr)
         return (res[0] if depth_term is None else res[0] + depth_term), res[1]
+
+    def _after_fine_backward(self):
+        """multi-GPU tail of the step: all-reduce(fine) || coarse backward -> all-reduce(coarse) -> Adam"""
+        gc, gf = self.grads
+        self._pending.append(allreduce_sum_async(gf, self.pg))
+        self._coarse_backward()
+        self._pending.append(allreduce_sum_async(gc, self.pg))
+        self.apply_gradients()
+
+    def _coarse_backward(self):
+        cfg, k, coarse, dr = self._coarse_args
+        gc, gf = self.grads
+        chunk_backward(cfg, k, self.net_c, self.net_f, coarse, gc, gf, self._scratch(cfg), self._ws(cfg), detach_range=dr)
 
     # ---------------------------------------------------------------------------------------
     # perceptual-loss branch (run_nerf.py:1523-1561, `--lpips`; SURVEY.md section 8 f2)
@@ -314,7 +343,15 @@ class Trainer:
                                      self.global_step)
             self.net_c.mark_params_changed(); self.net_f.mark_params_changed()
             return
-        scale = allreduce_sum_([self.grad_all], self.pg) if self.sharder.world > 1 else 1.0
+        pending = getattr(self, "_pending", None)
+        if pending:                                   # the two per-network all-reduces were issued behind their backward passes
+            for w in pending:
+                if w is not None:
+                    w.wait()                          # stream-side wait: the current stream continues after the collective
+            self._pending = []
+            scale = 1.0 / self.sharder.world
+        else:
+            scale = allreduce_sum_([self.grad_all], self.pg) if self.sharder.world > 1 else 1.0
         self.global_step += 1
         if self.adam_state is not None:
             L.check(L.lib().spn_adam_tick(L.ptr(self.adam_state), self.lr0, 0.1, float(self.lrate_decay * 1000),
@@ -380,15 +417,21 @@ class Trainer:
 
     # ---------------------------------------------------------------------------------------
     def step_graphed(self, rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp):
-        """`step` replayed as ONE CUDA graph (the whole step is ~45 small and 6 large launches; replaying it removes the
-        launch latency a caller that reads the loss back every step would otherwise expose).  Inputs may live on the
-        host (pinned) or the device: they are copied into static device buffers, then the graph is replayed.  The
-        first call runs eagerly (allocates every pooled buffer), the second captures, later ones replay; shapes must
-        not change.  Returns (loss, psnr) as views of static buffers (valid until the next call)."""
+        """`step` replayed as CUDA graphs (the whole step is ~45 small and 6 large launches; replaying it removes the launch
+        latency a caller that reads the loss back every step would otherwise expose).  Inputs may live on the host (pinned)
+        or the device: they are copied into static device buffers, then the graph is replayed.  The first call runs
+        eagerly (allocates every pooled buffer), the second captures, later ones replay; shapes must not change.  Returns
+        (loss, psnr) as views of static buffers (valid until the next call).
+
+        One GPU: ONE graph.  Several GPUs: THREE graphs with the two gradient all-reduces between them — [forward, losses,
+        fine backward] -> all-reduce(fine) on NCCL's stream || [coarse backward] -> all-reduce(coarse) -> [Adam] — because a
+        CUDA-graph capture that contains the NCCL collectives hung on this stack (8 GPUs in round 1, 2 GPUs in round 2,
+        TORCH_NCCL_ASYNC_ERROR_HANDLING=0 notwithstanding): the collectives stay eager, everything else is replayed."""
         ins = (rays_clf, target_clf, rays_s, target_s, rays_inp, depth_inp)
-        if self.sharder.world > 1:
-            raise NotImplementedError("Trainer.step_graphed: graph capture of the step's NCCL all-reduce is not validated; "
-                                      "use Trainer.step / step_from_pool on multi-GPU runs")
+        multi = self.sharder.world > 1
+        if multi and self.peer is not None:
+            raise NotImplementedError("Trainer.step_graphed: the peer-memory gradient exchange is not graph-captured; "
+                                      "use Trainer.step / step_from_pool")
         if self._graph is None:
             self._static_in = [torch.empty(t.shape, dtype=torch.float32, device=self.device) for t in ins]
             if self.adam_state is None:
@@ -403,13 +446,52 @@ class Trainer:
             return out
         if self._graph == "capture":
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
             n0 = L.lib().spn_launch_count(0)
-            with torch.cuda.graph(graph):
-                self._static_out = self.step(*self._static_in)
+            if not multi:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._static_out = self.step(*self._static_in)
+                self._graph = graph
+            else:
+                g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                self._segments = "capturing"
+                with torch.cuda.graph(g1):
+                    self._static_out = self.step(*self._static_in)     # stops behind the fine backward (self._segments is set)
+                pool = g1.pool()
+                with torch.cuda.graph(g2, pool=pool):
+                    self._coarse_backward()
+                self._pending = []
+                with torch.cuda.graph(g3, pool=pool):
+                    self._graph_adam(1.0 / self.sharder.world)
+                self._segments = (g1, g2, g3)
+                self._graph = "segments"
             self.graph_launches = int(L.lib().spn_launch_count(0) - n0)   # our kernels per replay
-            self._graph = graph
             self.global_step -= 1                      # capture only recorded the step, it did not run
-        self._graph.replay()
+        if multi:
+            g1, g2, g3 = self._segments
+            gc, gf = self.grads
+            g1.replay()
+            w1 = allreduce_sum_async(gf, self.pg)
+            g2.replay()
+            w2 = allreduce_sum_async(gc, self.pg)
+            for w in (w1, w2):
+                if w is not None:
+                    w.wait()
+            g3.replay()
+        else:
+            self._graph.replay()
         self.global_step += 1
         return self._static_out
+
+    def _graph_adam(self, scale):
+        """the optimiser tail with a fixed gradient scale (segmented-graph mode: the all-reduces ran outside the graphs)"""
+        self.global_step += 1
+        L.check(L.lib().spn_adam_tick(L.ptr(self.adam_state), self.lr0, 0.1, float(self.lrate_decay * 1000),
+                                      self.betas[0], self.betas[1], L.stream()), "spn_adam_tick")
+        for net, g, m, v in zip((self.net_c, self.net_f), self.grads, self.m, self.v):
+            if net is None:
+                continue
+            L.check(L.lib().spn_adam_step_dev(L.ptr(net.flat_params()), L.ptr(g), L.ptr(m), L.ptr(v), g.numel(),
+                                              L.ptr(self.adam_state), self.betas[0], self.betas[1], self.eps,
+                                              float(scale), L.stream()), "spn_adam_step_dev")
+            net.mark_params_changed()

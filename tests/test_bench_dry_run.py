@@ -29,7 +29,7 @@ def test_headline_arm_line_has_the_contract_keys():
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["kind"] == "port"
     assert "error" not in line["gpu_reference_port"] and line["gpu_reference_port"]["value"] > 0
-    assert "error" not in line["psnr_vs_ref"] and line["psnr_vs_ref"]["rays"] == 512 and "rgb_db" in line["psnr_vs_ref"]
+    assert "error" not in line["psnr_vs_ref"] and line["psnr_vs_ref"]["rays"] == 1024 and "rgb_db" in line["psnr_vs_ref"] and "trained_psnr_db" in line["psnr_vs_ref"]
     assert "e2e done" in err and "timed steps" in err                      # the phase breadcrumbs
 
 

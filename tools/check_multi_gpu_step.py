@@ -1,0 +1,87 @@
+"""Multi-GPU check (torchrun, N >= 2): the ray-sharded train step in its three forms must walk the same trajectory —
+  (a) Trainer.step (eager; all-reduce of the fine gradients overlapped with the coarse backward),
+  (b) Trainer.step_graphed (three CUDA graphs with the two all-reduces between them),
+  (c) the single-process step on the whole batch (world = 1 sharder), run redundantly on every rank.
+Deterministic sampling (perturb = 0, raw_noise_std = 0); differences are summation order only.
+
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/check_multi_gpu_step.py
+"""
+import importlib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+spn = importlib.import_module("spin-nerf_b200")
+trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+    dist.init_process_group("nccl", device_id=dev)
+    H, W, f = 24, 32, 28.8
+    rng = np.random.default_rng(5)
+    c2w = torch.tensor([[1, 0, 0, 0.1], [0, 1, 0, -0.2], [0, 0, 1, 0.0]], dtype=torch.float32, device=dev)
+    ro, rd = spn.ops.get_rays(H, W, f, c2w)
+    pool = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    n = 64 * world
+    steps = 6
+    idx = torch.from_numpy(rng.integers(0, H * W, (steps, 3, n))).to(dev)
+    tg = torch.from_numpy(rng.random((H * W, 3), dtype=np.float32)).to(dev)
+    td = torch.from_numpy(rng.random((H * W,), dtype=np.float32)).to(dev)
+
+    def make(sharder):
+        nets = []
+        for seed in (1, 2):
+            net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+            net = net.seeded_init_(seed).to(dev); net.precision = spn.PREC_BF16
+            nets.append(net)
+        return nets, trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
+                                         perturb=0.0, raw_noise_std=0.0, near=1.2, far=8.0, ndc=False, hwf=(H, W, f), sharder=sharder)
+
+    def batch(i):
+        a, b, c = idx[i]
+        return (pool[:, a].contiguous(), tg[a], pool[:, b].contiguous(), tg[b], pool[:, c].contiguous(), td[c])
+
+    runs = {}
+    for name, sharder in (("eager", trainer_mod.RaySharder(rank, world)), ("graphed", trainer_mod.RaySharder(rank, world)),
+                          ("single", trainer_mod.RaySharder(0, 1))):
+        nets, tr = make(sharder)
+        losses = []
+        for i in range(steps):
+            loss, _ = (tr.step_graphed if name == "graphed" else tr.step)(*batch(i))
+            losses.append(float(loss))
+        torch.cuda.synchronize()
+        runs[name] = (torch.cat([nets[0].flat_params(), nets[1].flat_params()]).clone(), losses)
+    ref, _ = runs["single"]
+    moved = float((ref - torch.cat([make(trainer_mod.RaySharder(0, 1))[0][i].flat_params() for i in (0, 1)])).abs().max())
+    ok = True
+    for name in ("eager", "graphed"):
+        p, losses = runs[name]
+        d = float((p - ref).abs().max())
+        # replicas must agree bit for bit across ranks (same reduced gradient everywhere)
+        q = p.clone(); dist.broadcast(q, src=0)
+        same = bool(torch.equal(p, q))
+        if rank == 0:
+            print(f"{name:8s}: max |param - single-process| = {d:.3e} (parameters moved by up to {moved:.3e}); replicas identical: {same}; "
+                  f"local loss {losses[0]:.5f} -> {losses[-1]:.5f}")
+        ok = ok and same and d <= 2e-2 * moved + 1e-6
+    d2 = float((runs["eager"][0] - runs["graphed"][0]).abs().max())
+    if rank == 0:
+        print(f"graphed vs eager: max |diff| = {d2:.3e}")
+    ok = ok and d2 <= 2e-2 * moved + 1e-6
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_STEP_OK" if ok else "MULTI_GPU_STEP_MISMATCH")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,10 @@ run strong  100 --scaling strong --n_rand_global 8192 --steps 20 --warmup 5 --no
 run weak    100 --steps 20 --warmup 5 --no_cpu_baseline
 run render  100 --workload render --steps 3 --warmup 3
 run lpips   100 --workload train_lpips --steps 10 --warmup 3
+echo "=== check_multi_gpu_step"
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29539 \
+    tools/check_multi_gpu_step.py > "$OUT/${TAG}_n${N}_step_check.log" 2>&1
+echo "    rc=$?"; tail -n 5 "$OUT/${TAG}_n${N}_step_check.log"
 if [ -f tools/check_peer_allreduce.py ] && [ "${SPN_CHECK_PEER:-0}" = "1" ]; then
   echo "=== peer_allreduce"
   timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29540 \
