@@ -24,12 +24,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  // per device: a process may drive several GPUs (one cached value would size every grid after the first device it saw)
+  static std::atomic<int> cached[64];
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  const int c = cached[dev].load(std::memory_order_relaxed);
+  if (c > 0) return c;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

@@ -109,7 +109,6 @@ class RenderChunk(torch.autograd.Function):
     def forward(ctx, opts, rays, net_c, net_f, t_rand, u, noise0, noise1, *params):
         train = opts["train"]       # decided by the caller: grad mode is off inside Function.forward
         cfg, keep = chunk_forward(opts, rays, net_c, net_f, t_rand, u, noise0, noise1, train)
-        ctx.state = (cfg, keep, net_c, net_f, train)
         names = ["rgb_map", "disp_map", "acc_map", "depth_map", "weights", "z_vals", "raw"]
         if opts["N_importance"] > 0:
             names += ["rgb0", "disp0", "acc0", "z_std"]
@@ -117,14 +116,21 @@ class RenderChunk(torch.autograd.Function):
             names += ["alpha", "alpha0"]
         ctx.names = names
         outs = tuple(keep[k] for k in names)
+        # The Function's own outputs go through save_for_backward: kept as plain attributes they would close the cycle
+        # output -> grad_fn -> ctx -> output, which Python's collector cannot see through the C++ node — a forward whose backward
+        # never runs would then leak the whole chunk's activation stash.  Only non-output state stays on ctx.
+        ctx.save_for_backward(*outs)
+        ctx.state = (cfg, {k: v for k, v in keep.items() if k not in names}, net_c, net_f, train)
         ctx.mark_non_differentiable(*[keep[k] for k in names if k not in _DIFF])
         return outs
 
     @staticmethod
     def backward(ctx, *gouts):
-        cfg, keep, net_c, net_f, train = ctx.state
+        cfg, rest, net_c, net_f, train = ctx.state
         if not train:
             raise RuntimeError("RenderChunk.backward without a training forward")
+        keep = dict(rest)
+        keep.update(zip(ctx.names, ctx.saved_tensors))
         dev = keep["rays"].device
         gc = torch.zeros(L.MLP_NPARAMS, device=dev)
         gf = torch.zeros(L.MLP_NPARAMS, device=dev) if net_f is not None else None

@@ -21,6 +21,7 @@ class BufferPool:
 
     def __init__(self, device):
         self.device, self.bufs = device, {}
+        self.frozen = False      # set once a CUDA graph has baked the buffers' addresses in: growing one would free memory the graph uses
 
     def __call__(self, name, shape, dtype):
         need = 1
@@ -28,6 +29,9 @@ class BufferPool:
             need *= int(s)
         b = self.bufs.get(name)
         if b is None or b.numel() < need or b.dtype != dtype:
+            if self.frozen:
+                raise RuntimeError(f"BufferPool: '{name}' would have to grow to {need} elements, but a captured CUDA graph replays on "
+                                   "the current buffers; use a second Trainer (or eager steps only) for larger / other work")
             b = torch.empty(max(need, 1), device=self.device, dtype=dtype)
             self.bufs[name] = b
         return b[:need].view(*shape) if need else b[:0].view(*shape)
@@ -447,8 +451,12 @@ class Trainer:
         if self._graph == "capture":
             torch.cuda.synchronize()
             n0 = L.lib().spn_launch_count(0)
+            if self.gen is not None and multi:
+                raise NotImplementedError("Trainer.step_graphed: Trainer(seed=...) with the multi-GPU segmented graphs is not supported")
             if not multi:
                 graph = torch.cuda.CUDAGraph()
+                if self.gen is not None:               # the private random stream must advance with every replay
+                    graph.register_generator_state(self.gen)
                 with torch.cuda.graph(graph):
                     self._static_out = self.step(*self._static_in)
                 self._graph = graph
@@ -466,6 +474,8 @@ class Trainer:
                 self._segments = (g1, g2, g3)
                 self._graph = "segments"
             self.graph_launches = int(L.lib().spn_launch_count(0) - n0)   # our kernels per replay
+            for pool in set(self.pools) | {self.shared}:
+                pool.frozen = True
             self.global_step -= 1                      # capture only recorded the step, it did not run
         if multi:
             g1, g2, g3 = self._segments

@@ -150,11 +150,20 @@ def test_sample_pdf_indices_bit_exact():
     s_o, i_o = O.sample_pdf_from_cdf(bins, ref_cdf, uu)
     same = np.all(N(cdf) == ref_cdf, axis=1)
     assert same.mean() > 0.5 and np.array_equal(N(inds)[same], i_o[same])
-    g2 = load_golden("searchsorted_kat")          # torch.searchsorted(right=True) KAT
+    s_own, i_own = O.sample_pdf_from_cdf(bins, N(cdf), uu)          # every row: exact given the GPU's own cdf
+    assert np.array_equal(N(inds), i_own) and np.array_equal(N(s), s_own)
+    # torch.searchsorted(right=True) KAT (cdf [0,.2,.2,.7,1], u [0,.2,.7,.99,1,1.1] -> [1,3,4,4,5,5]),
+    # unconditionally: the KAT cdf goes straight through the library's search (numpy side='right' = torch right=True)
+    g2 = load_golden("searchsorted_kat")
+    got = ops.searchsorted(T(g2["cdf"].astype(np.float32)), T(g2["u"].astype(np.float32).reshape(1, -1)), side='right')
+    assert N(got).reshape(-1).tolist() == np.asarray(g2["inds"]).reshape(-1).tolist()
+    # and through sample_pdf's own search when its cdf reproduces the KAT's bit for bit
     cdf_k = g2["cdf"][0]
     wk = np.diff(cdf_k).astype(np.float32)        # build weights that reproduce the KAT cdf
     _, inds_k, cdf_g = ops.sample_pdf(T(np.zeros((1, 5), np.float32)), T(wk[None] - np.float32(1e-5)), 6, u=T(g2["u"]),
                                       return_inds=True, return_cdf=True)
+    i_k = O.sample_pdf_from_cdf(np.zeros((1, 5), np.float32), N(cdf_g), np.asarray(g2["u"], np.float32).reshape(1, -1))[1]
+    assert np.array_equal(N(inds_k), i_k)
     if np.array_equal(N(cdf_g)[0], cdf_k):
         assert N(inds_k).tolist() == g2["inds"].tolist()
 
@@ -170,7 +179,11 @@ def test_merge_and_resample():
     zm, zstd, zs, inds = ops.resample(T(a), T(w), 64, T(u), want_samples=True, want_inds=True)
     mid = np.float32(0.5) * (a[:, 1:] + a[:, :-1])
     s_o, i_o = O.sample_pdf(mid, w[:, 1:-1], 64, det=False, u=u)
-    assert (N(inds) == i_o).mean() > 0.999
+    assert (N(inds) == i_o).mean() > 0.999                     # vs the oracle's own cdf (may differ by an ulp per row) ...
+    # ... and EXACT given the GPU's cdf: sample_pdf's kernel on the same mids / weights returns the cdf the fused kernel builds
+    _, i_g, cdf_g = ops.sample_pdf(T(mid), T(w[:, 1:-1].copy()), 64, u=T(u), return_inds=True, return_cdf=True)
+    s_x, i_x = O.sample_pdf_from_cdf(mid, N(cdf_g), u)
+    assert np.array_equal(N(inds), i_x) and np.array_equal(N(zs), s_x)
     close_mostly(zs, s_o, rtol=1e-5, atol=1e-5)
     assert np.array_equal(N(zm), np.sort(np.concatenate([a, N(zs)], -1), -1))       # sortedness + multiset
     close(zstd, N(zs).std(-1), rtol=1e-4, atol=1e-5)

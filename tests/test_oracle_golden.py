@@ -331,3 +331,29 @@ def test_torch_port_walks_the_references_training_trajectory():
             group["lr"] = gen.LR * (0.1 ** (it / (gen.DECAY * 1000)))
         assert abs(float(loss) - float(gold["loss"][it])) <= 1e-4 * float(gold["loss"][it]), (it, float(loss))
         assert abs(float(psnr) - float(gold["psnr"][it])) <= 1e-3
+
+
+def test_torch_port_full_size_step_matches_reference():
+    """BASELINE configs[1] size (3 x 1024 rays, coarse + fine): the PyTorch restatement that bench.py times as the CPU arm
+    reproduces the unmodified reference's maps and step loss (tests/golden/make_fullsize_golden.py)."""
+    import torch
+    from conftest import load_golden
+    from oracle import torch_port as TP
+    g = load_golden("fullsize_step")
+    H, W, f, near, far, n_rand, seed_c, seed_f = [float(x) for x in g["cfg"]]
+    ps = []
+    for seed in (int(seed_c), int(seed_f)):
+        p = O.init_params(seed)
+        p["alpha_linear.bias"] = p["alpha_linear.bias"] + np.float32(1.0)
+        ps.append(TP.make_params(p, "cpu"))
+    torch.set_num_threads(8)
+    rays = torch.from_numpy(g["rays"])
+    with torch.no_grad():
+        out = TP.render_rays(rays[0, 0], rays[0, 1], near, far, ps[0], ps[1], lindisp=True, white_bkgd=True)
+    for k, rk in (("rgb_map", "rgb"), ("rgb0", "rgb0"), ("acc_map", "acc")):
+        assert np.abs(out[k].numpy() - g["clf__" + rk]).max() <= 2e-4, k
+    batches = [(rays[0], torch.from_numpy(g["target_clf"])), (rays[1], torch.from_numpy(g["target_s"])),
+               (rays[2], torch.from_numpy(g["depth_inp"]))]
+    with torch.no_grad():
+        loss, _ = TP.spin_step_loss(batches, ps[0], ps[1], near, far, perturb=False, raw_noise_std=0.0)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * float(g["loss"])

@@ -338,3 +338,124 @@ def test_training_reaches_the_references_psnr(prec_name):
     print(f"{prec_name}: PSNR over the last 20 of {gen.K} steps: ours {ours:.2f} dB, reference {ref:.2f} dB")
     assert abs(ours - ref) <= psnr_tol, (ours, ref)
     assert ours > float(gold["psnr"][:20].mean()) + 15.0          # and it did train (reference: +21 dB)
+
+
+# ---- BASELINE configs[1] at FULL size against the unmodified reference (tests/golden/make_fullsize_golden.py) -----------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
+def test_full_size_train_step_matches_reference(prec_name):
+    """One train step of 3 x 1024 rays (coarse + fine, 589 824 MLP evaluations) — the size bench.py times — against the
+    unmodified reference's three render() calls, losses and autograd gradients (tests/golden/fullsize_step.npz).
+    fp32 mode: maps abs 3e-4 (disp rel 1e-3), loss rel 2e-4, sum|g| rel 5e-3 per tensor, sub-sampled gradient entries.
+    bf16 mode (E4M3 activation stash): PSNR of every rendered map vs the reference > 35 dB, loss rel 1e-2, sum|g| rel 6e-2."""
+    from conftest import load_golden
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    g = load_golden("fullsize_step")
+    H, W, f, near, far, n_rand, seed_c, seed_f = [float(x) for x in g["cfg"]]
+    H, W, n_rand = int(H), int(W), int(n_rand)
+    prec = spn.PREC_FP32 if prec_name == "fp32" else spn.PREC_BF16
+    nets, params = [], []
+    for seed in (int(seed_c), int(seed_f)):
+        p = O.init_params(seed)
+        p["alpha_linear.bias"] = p["alpha_linear.bias"] + np.float32(1.0)
+        net = spn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+        net = net.to(DEV); net.precision = prec
+        nets.append(net); params.append(p)
+    rays = T(g["rays"])                                   # [3, 2, 1024, 3]
+    # ---- the three render() calls (forward maps)
+    kw = dict(network_query_fn=None, network_fn=nets[0], network_fine=nets[1], N_samples=64, N_importance=64, lindisp=True,
+              white_bkgd=True, perturb=0., raw_noise_std=0., use_viewdirs=True, ndc=False, near=near, far=far)
+    worst = {}
+    for ci, tag in enumerate(("clf", "s", "inp")):
+        with torch.no_grad():
+            rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=32768, rays=rays[ci], detach_weights=(tag == "s"), **kw)
+        got = dict(rgb=rgb, disp=disp, acc=acc, depth=depth, rgb0=ex["rgb0"], disp0=ex["disp0"], acc0=ex["acc0"], z_std=ex["z_std"])
+        for k, v in got.items():
+            ref = g[f"{tag}__{k}"]
+            if prec_name == "fp32":
+                if k in ("disp", "disp0"):
+                    close_mostly(v, ref, rtol=1e-3, atol=1e-6)
+                elif k == "z_std":
+                    close_mostly(v, ref, rtol=2e-3, atol=2e-4)
+                else:
+                    close_mostly(v, ref, rtol=3e-4, atol=3e-4)
+            elif k in ("rgb", "rgb0", "acc", "acc0"):
+                mse = float(np.mean((N(v) - ref) ** 2))
+                worst[f"{tag}.{k}"] = -10 * np.log10(max(mse, 1e-20))
+        if prec_name == "fp32":
+            close_mostly(ex["weights"][::16], g[f"{tag}__weights_sub"], rtol=0, atol=3e-4)
+            close_mostly(ex["z_vals"][::16], g[f"{tag}__z_vals_sub"], rtol=5e-5, atol=1e-5)
+    if worst:
+        assert min(worst.values()) > 35.0, worst
+    # ---- the step: losses + backward into the flat gradient vectors (no optimiser step)
+    tr = trainer_mod.Trainer(nets[0], nets[1], lr=5e-4, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.0,
+                             raw_noise_std=0.0, near=near, far=far, ndc=False, hwf=(H, W, f))
+    loss, psnr = tr.step(rays[0], T(g["target_clf"]), rays[1], T(g["target_s"]), rays[2], T(g["depth_inp"]), _apply=False)
+    torch.cuda.synchronize()
+    ltol, gtol = (2e-4, 5e-3) if prec_name == "fp32" else (1e-2, 6e-2)
+    assert abs(float(loss) - float(g["loss"])) <= ltol * float(g["loss"]), (float(loss), float(g["loss"]))
+    assert abs(float(psnr) - float(g["psnr"])) <= (0.01 if prec_name == "fp32" else 0.2)
+    off = spn._lib.param_offsets()
+    names = [k for k, _ in O.PARAM_SHAPES]
+    for tag, flat, p in (("c", tr.grads[0], params[0]), ("f", tr.grads[1], params[1])):
+        for i, k in enumerate(names):
+            G = N(flat[off[i]:off[i + 1]])
+            ref_abs = float(g[f"g_abs_{tag}__{k}"])
+            assert abs(np.abs(G).sum(dtype=np.float64) - ref_abs) <= gtol * ref_abs + 1e-7, (tag, k, np.abs(G).sum(), ref_abs)
+            sub, ref_sub = G[::997], g[f"g_sub_{tag}__{k}"]
+            scale = max(float(np.abs(ref_sub).max()), 1e-12)
+            if prec_name == "fp32":
+                close_mostly(sub, ref_sub, rtol=5e-3, atol=2e-3 * scale, max_frac=0.02, hard=1.0)
+            elif sub.size >= 16:   # sums of +- terms, each carrying bf16 / E4M3 rounding noise: entries at 10 % of the tensor's scale
+                close_mostly(sub, ref_sub, rtol=5e-2, atol=1e-1 * scale, max_frac=0.05, hard=1.0)      # (tiny tensors: sum|g| above)
+
+
+@pytest.mark.gpu
+def test_trainer_patch_chunk_matches_reference_patch_render_fp32():
+    """The LPIPS branch renders its patches as ONE fused chunk with rays generated from c2w + patch window on the device
+    (Trainer.lpips_patch_backward).  That chunk's rgb against the UNMODIFIED reference's render(c2w=..., patch=...) golden
+    (tests/golden/render_variants.npz 'c2w_patch'): same tolerance as the render parity tests."""
+    from conftest import load_golden
+    trainer_mod = importlib.import_module("spin-nerf_b200.trainer")
+    g = load_golden("render_variants")
+    H, W, f = 12, 16, 14.4
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    tr = trainer_mod.Trainer(netc, netf, N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=1.0, raw_noise_std=1.0,
+                             near=1.2, far=8.0, ndc=False, hwf=(H, W, f))
+    seen = {}
+
+    def fake_lpips(pred, target):                      # fixed input of the path: records what it is handed
+        seen["pred"] = pred.detach().clone()
+        return ((pred - target) ** 2).mean((1, 2, 3))
+    patch = (3, 5, 6, 8)
+    tgt = torch.zeros(1, 3, 6, 8, device=DEV)
+    tr.grad_all.zero_()
+    tr.lpips_patch_backward([g["pose_a"]], [patch], [tgt], fake_lpips, (H, W, f))
+    pred = (seen["pred"][0].permute(1, 2, 0) / 2 + 0.5)          # back from [-1, 1] (run_nerf.py:1552) to rgb [6, 8, 3]
+    assert tuple(pred.shape) == g["c2w_patch__rgb"].shape
+    close_mostly(pred, g["c2w_patch__rgb"], rtol=0, atol=2e-4)
+    assert float(tr.grads[1].abs().sum()) > 0           # and the patch gradient reached the fine network
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", [7, 20])
+def test_render_in_several_chunks_matches_reference_fp32(chunk):
+    """batchify_rays (run_nerf.py:74-87) with more than one chunk per call: the 48-ray golden of the unmodified reference
+    rendered in chunks of 7 / 20 rays (ragged last chunk) must equal it like the single-chunk render does."""
+    from conftest import load_golden
+    g = load_golden("render")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    netc, netf = make_net(11, spn.PREC_FP32), make_net(12, spn.PREC_FP32)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = spn.render(H, W, f, chunk=chunk, rays=T(g["rays"]), retraw=True, use_viewdirs=True, ndc=False,
+                                               near=1.2, far=8.0, network_query_fn=None, network_fn=netc, network_fine=netf,
+                                               N_samples=64, N_importance=64, lindisp=True, white_bkgd=True, perturb=0.,
+                                               raw_noise_std=0.)
+    G = lambda k: g[f"det_lindisp_white__{k}"]
+    assert tuple(rgb.shape) == G("rgb").shape and tuple(ex["weights"].shape) == G("weights").shape
+    close_mostly(rgb, G("rgb"), rtol=0, atol=2e-4); close_mostly(acc, G("acc"), rtol=0, atol=2e-4)
+    close_mostly(depth, G("depth"), rtol=2e-4, atol=2e-4); close_mostly(disp, G("disp"), rtol=5e-4, atol=0)
+    close_mostly(ex["weights"], G("weights"), rtol=0, atol=2e-4)
+    close_mostly(ex["z_vals"], G("z_vals"), rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(N(ex["rgb0"]), G("rgb0"), rtol=1e-5, atol=2e-4)

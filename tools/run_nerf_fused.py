@@ -50,6 +50,7 @@ def config_parser():
     A("--colmap_depth", action='store_true'); A("--depth_loss", action='store_true'); A("--depth_lambda", type=float, default=0.1)
     A("--lpips", action='store_true'); A("--lpips_render_factor", type=int, default=2); A("--patch_len_factor", type=int, default=8)
     A("--lpips_batch_size", type=int, default=4)
+    A("--lpips_standin", action='store_true', help="allow spin-nerf_b200/compat/lpips.py (seeded random conv stack) when the lpips package is missing")
     A("--lpips_from", type=int, default=300, help="the LPIPS branch runs on iterations > this (hard-coded 300 in run_nerf.py:1523)")
     A("--no_reload", action='store_true'); A("--ft_path", type=str, default=None)
     A("--render_only", action='store_true'); A("--render_factor", type=int, default=0)
@@ -165,11 +166,20 @@ def main(argv=None):
     dev_pools = pools.to(dev)
     dpool = None if depth_pool is None else tuple(torch.from_numpy(a).to(dev) for a in depth_pool)
     lpips_fn = None
-    if args.lpips:                       # the pip package when installed, else the fixed-weights stand-in (values unpinned)
+    if args.lpips:
+        # LPIPS-VGG is a fixed input of this path (the pip package `lpips`, run_nerf.py:36,970-974).  Without it the run would
+        # optimise a DIFFERENT perceptual loss, so the seeded stand-in network is only used when asked for explicitly.
         try:
             lpips_mod = importlib.import_module("lpips")
         except ImportError:
+            if not args.lpips_standin:
+                raise RuntimeError("--lpips needs the `lpips` package (LPIPS-VGG weights). It is not installed; pass --lpips_standin "
+                                   "to run the branch with spin-nerf_b200/compat/lpips.py, a seeded random conv stack that exercises the "
+                                   "same code path but is NOT the reference's perceptual loss.")
             lpips_mod = importlib.import_module("spin-nerf_b200.compat.lpips")
+            if rank == 0:
+                print("WARNING: --lpips_standin: the perceptual term is a seeded random conv stack, not LPIPS-VGG "
+                      "(recorded in args.txt)", flush=True)
         lpips_fn = lpips_mod.LPIPS(net='vgg').to(dev)
     poses_t = torch.from_numpy(np.ascontiguousarray(poses[:, :3, :4])).float()
     t0, rays_done = time.perf_counter(), 0
@@ -221,6 +231,8 @@ def main(argv=None):
             os.makedirs(out, exist_ok=True)
             spn.render_path(poses[i_test], list(hwf), args.chunk, test_kw, gt_imgs=images[i_test], savedir=out,
                             render_factor=args.render_factor)
+        if tr.peer is not None and (i % args.i_weights == 0 or (i % args.i_testset == 0 and len(i_test) > 0)):
+            torch.distributed.barrier()        # the peer-memory exchange polls device-side: nobody may enter the next step minutes early
         if i % args.i_print == 0 and rank == 0:
             print(f"[TRAIN] Iter: {i} Loss: {float(loss)}  PSNR: {float(psnr)}  "
                   f"({rays_done / (time.perf_counter() - t0) / 1e3:.0f} k rays/s wall clock)")
