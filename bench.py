@@ -207,7 +207,11 @@ def psnr_vs_reference_port(spn, dev, prec, n_rays=1024):
         rgb, disp, acc, depth, ex = spn.render(gen.H, gen.W, gen.FOCAL, chunk=32768, rays=rays, use_viewdirs=True, ndc=False,
                                                near=gen.NEAR, far=gen.FAR, network_query_fn=None, network_fn=nets[0],
                                                network_fine=nets[1], N_samples=64, N_importance=64, lindisp=True, white_bkgd=True,
-                                               perturb=0., raw_noise_std=0.)
+                                               perturb=0., raw_noise_std=0., need_alpha=True)
+        # what early ray termination could skip in the fine pass of a no-grad render (north_star): samples whose transmittance
+        # has already dropped below a threshold (run_nerf_helpers.py:384: T = exclusive cumprod of 1 - alpha + 1e-10)
+        Tr = torch.cumprod(torch.cat([torch.ones_like(ex["alpha"][:, :1]), 1.0 - ex["alpha"] + 1e-10], -1), -1)[:, :-1]
+        ert = {f"T<{t:g}": float((Tr < t).float().mean()) for t in (1e-2, 1e-3, 1e-4)}
         pc, pf = ({k: v.detach().clone().float() for k, v in n.state_dict().items()} for n in nets)
         ref = TP.render_rays(rays[0], rays[1], gen.NEAR, gen.FAR, pc, pf, lindisp=True, white_bkgd=True)
         mse = float(torch.mean((rgb - ref["rgb_map"]) ** 2))
@@ -217,6 +221,7 @@ def psnr_vs_reference_port(spn, dev, prec, n_rays=1024):
     return {"rgb_db": db(mse), "rgb0_db": db(mse0), "rays": n_rays,
             "trained_psnr_db": trained, "reference_trained_psnr_db": float(gold["psnr"][-20:].mean()), "train_steps": int(gen.K),
             "render_vs_target_db": db(mse_t), "reference_render_vs_target_db": db(mse_rt),
+            "ert_skippable_fine_sample_frac": ert,
             "scene": "analytic 4-view scene of tests/golden/make_convergence_golden.py, trained 300 steps with the benchmark's arithmetic",
             "checker": "oracle/torch_port.py: fp32 PyTorch render of the same rays with the same trained weights, TF32 off; "
                        "reference_trained_psnr_db from the unmodified reference's own 300-step run (tests/golden/convergence.npz)"}

@@ -599,10 +599,11 @@ __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const WgradParams
 // =====================================================================================================
 // rgb / sigma heads: dWr[3,128] += d_rgb^T hv,  dbr,  dWa[256] += d_sigma h7,  dba
 // =====================================================================================================
-// 8 warps per block, warp w owns rows 16w..16w+15 of a tile.  h7 is the E4M3 stash image (two 128-byte rows per sample): lanes
-// 0..15 read one 16-byte chunk (16 features) each; hv is bf16 (one 16-byte chunk = 8 features per lane, lanes 0..15): every load
-// instruction of a warp covers whole 128-byte lines.  Partials live in registers across the block's tiles and are combined
-// through shared memory once, then 643 atomics per block.
+// 8 warps per block, warp w owns rows 16w..16w+15 of a tile.  Lanes 0..15 read h7 — the E4M3 stash image, two 128-byte rows per
+// sample, one 16-byte chunk (16 features) per lane — and accumulate d alpha_linear.weight; lanes 16..31 read hv (bf16, one
+// 16-byte chunk = 8 features per lane) and accumulate d rgb_linear.weight: every load instruction of a warp covers whole
+// 128-byte lines.  Partials live in registers across the block's tiles and are combined through shared memory once, then 643
+// atomics per block.
 __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* __restrict__ stash,
                                                               const float* __restrict__ d_raw, int64_t m,
                                                               int64_t tiles, float* __restrict__ g_wr,
@@ -611,12 +612,15 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
   __shared__ float4 s_d[kTileM];
   __shared__ float s_red[8][32][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float wa[16];
+  // acc: lanes 0..15 -> d Wa for 16 features; lanes 16..31 -> d Wr rows 0 and 1 for 8 features (row 2 in acc2)
+  float acc[16], acc2[8];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) wa[e] = 0.f;
-  float wr[3][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc2[e] = 0.f;
   float sb[4] = {0, 0, 0, 0};
   const int l16 = lane & 15;
+  const bool is_h7 = lane < 16;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
     if (tid < kTileM) {
@@ -625,66 +629,62 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
     }
     __syncthreads();
     const uint8_t* st = stash + (size_t)tile * kStashTileBytes;
-    const uint8_t* h7 = st + (size_t)stash_x_atom(7, l16 >> 3) * kAtomBytes;     // lane -> (half, chunk l16 & 7)
-    const uint8_t* hv = st + (size_t)(SA_HV + (l16 >> 3)) * kAtomBytes;
-    if (lane < 16) {
+    const uint8_t* src = st + (size_t)(is_h7 ? stash_x_atom(7, l16 >> 3) : SA_HV + (l16 >> 3)) * kAtomBytes;   // lane -> (atom, chunk l16 & 7)
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {       // 8 rows in flight per lane
-        uint4 q7[8], qv[8];
+    for (int half = 0; half < 2; ++half) {       // 8 rows in flight per lane
+      uint4 qq[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t rr = (uint32_t)(warp * 16 + half * 8 + i);
-          q7[i] = __ldg(reinterpret_cast<const uint4*>(h7 + sw128_off(rr, (uint32_t)(lane & 7))));
-          qv[i] = __ldg(reinterpret_cast<const uint4*>(hv + sw128_off(rr, (uint32_t)(lane & 7))));
-        }
+      for (int i = 0; i < 8; ++i)
+        qq[i] = __ldg(reinterpret_cast<const uint4*>(src + sw128_off((uint32_t)(warp * 16 + half * 8 + i), (uint32_t)(lane & 7))));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 d = s_d[warp * 16 + half * 8 + i];
-          const uint32_t w7[4] = {q7[i].x, q7[i].y, q7[i].z, q7[i].w};
+      for (int i = 0; i < 8; ++i) {
+        const float4 d = s_d[warp * 16 + half * 8 + i];
+        const uint32_t w4[4] = {qq[i].x, qq[i].y, qq[i].z, qq[i].w};
+        if (is_h7) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             uint32_t lo, hi;
-            e4m3x4_to_f16x4(w7[e], lo, hi);
-            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&lo));
-            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-            wa[4 * e + 0] = fmaf(d.w, f01.x, wa[4 * e + 0]); wa[4 * e + 1] = fmaf(d.w, f01.y, wa[4 * e + 1]);
-            wa[4 * e + 2] = fmaf(d.w, f23.x, wa[4 * e + 2]); wa[4 * e + 3] = fmaf(d.w, f23.y, wa[4 * e + 3]);
+            e4m3x4_to_bf16x4(w4[e], lo, hi);
+            acc[4 * e + 0] = fmaf(d.w, __uint_as_float(lo << 16), acc[4 * e + 0]);
+            acc[4 * e + 1] = fmaf(d.w, __uint_as_float(lo & 0xffff0000u), acc[4 * e + 1]);
+            acc[4 * e + 2] = fmaf(d.w, __uint_as_float(hi << 16), acc[4 * e + 2]);
+            acc[4 * e + 3] = fmaf(d.w, __uint_as_float(hi & 0xffff0000u), acc[4 * e + 3]);
           }
-          const uint32_t wv[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+        } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float h0 = __uint_as_float(wv[e] << 16), h1 = __uint_as_float(wv[e] & 0xffff0000u);
-            wr[0][2 * e] = fmaf(d.x, h0, wr[0][2 * e]); wr[0][2 * e + 1] = fmaf(d.x, h1, wr[0][2 * e + 1]);
-            wr[1][2 * e] = fmaf(d.y, h0, wr[1][2 * e]); wr[1][2 * e + 1] = fmaf(d.y, h1, wr[1][2 * e + 1]);
-            wr[2][2 * e] = fmaf(d.z, h0, wr[2][2 * e]); wr[2][2 * e + 1] = fmaf(d.z, h1, wr[2][2 * e + 1]);
+            const float h0 = __uint_as_float(w4[e] << 16), h1 = __uint_as_float(w4[e] & 0xffff0000u);
+            acc[2 * e] = fmaf(d.x, h0, acc[2 * e]); acc[2 * e + 1] = fmaf(d.x, h1, acc[2 * e + 1]);
+            acc[8 + 2 * e] = fmaf(d.y, h0, acc[8 + 2 * e]); acc[8 + 2 * e + 1] = fmaf(d.y, h1, acc[8 + 2 * e + 1]);
+            acc2[2 * e] = fmaf(d.z, h0, acc2[2 * e]); acc2[2 * e + 1] = fmaf(d.z, h1, acc2[2 * e + 1]);
           }
-          if (lane == 15) { sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
         }
+        if (lane == 15) { sb[0] += d.x; sb[1] += d.y; sb[2] += d.z; sb[3] += d.w; }
       }
     }
   }
-  // block reduction over the 8 warps, one quantity at a time through the same shared buffer; lane l < n_lanes owns dst[off(l) + e]
-  auto reduce8 = [&](const float* v, float* dst, int n_lanes, auto off) {
+  // block reduction over the 8 warps, one quantity at a time through the same shared buffer; lanes [l0, l0 + 16) own dst[off(l) + e]
+  auto reduce8 = [&](const float* v, float* dst, int l0, auto off) {
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_red[warp][lane][e] = v[e];
     __syncthreads();
-    if (warp == 0 && lane < n_lanes) {
+    if (warp == 0 && lane >= l0 && lane < l0 + 16) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float acc = 0.f;
+        float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) acc += s_red[w][lane][e];
-        atomicAdd(dst + off(lane) + e, acc);
+        for (int w = 0; w < 8; ++w) a += s_red[w][lane][e];
+        atomicAdd(dst + off(lane - l0) + e, a);
       }
     }
   };
   // d alpha_linear.weight [256]: lane (half, chunk) holds features stash_x_feature(half, chunk) .. + 15
-  reduce8(wa, g_wa, 16, [](int l) { return stash_x_feature(l >> 3, l & 7); });
-  reduce8(wa + 8, g_wa, 16, [](int l) { return stash_x_feature(l >> 3, l & 7) + 8; });
-  reduce8(wr[0], g_wr, 16, [](int l) { return 8 * l; });                      // d rgb_linear.weight [3][128]
-  reduce8(wr[1], g_wr + kWV, 16, [](int l) { return 8 * l; });
-  reduce8(wr[2], g_wr + 2 * kWV, 16, [](int l) { return 8 * l; });
+  reduce8(acc, g_wa, 0, [](int l) { return stash_x_feature(l >> 3, l & 7); });
+  reduce8(acc + 8, g_wa, 0, [](int l) { return stash_x_feature(l >> 3, l & 7) + 8; });
+  reduce8(acc, g_wr, 16, [](int l) { return 8 * l; });                        // d rgb_linear.weight [3][128]
+  reduce8(acc + 8, g_wr + kWV, 16, [](int l) { return 8 * l; });
+  reduce8(acc2, g_wr + 2 * kWV, 16, [](int l) { return 8 * l; });
   {
     const float v[8] = {sb[0], sb[1], sb[2], sb[3], 0.f, 0.f, 0.f, 0.f};
     __syncthreads();
@@ -692,9 +692,9 @@ __global__ void __launch_bounds__(256, 2) mlp_heads_wgrad_kernel(const uint8_t* 
     for (int e = 0; e < 8; ++e) s_red[warp][lane][e] = v[e];
     __syncthreads();
     if (tid < 4) {
-      float acc = 0.f;
-      for (int w = 0; w < 8; ++w) acc += s_red[w][15][tid];
-      atomicAdd(tid < 3 ? g_br + tid : g_ba, acc);
+      float a = 0.f;
+      for (int w = 0; w < 8; ++w) a += s_red[w][15][tid];
+      atomicAdd(tid < 3 ? g_br + tid : g_ba, a);
     }
   }
 }
