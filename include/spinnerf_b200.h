@@ -14,6 +14,8 @@
  *     (thread-local).  Nothing throws, nothing allocates device memory, nothing syncs —
  *     except the *_host entry points, which own their H2D/D2H copies and synchronise.
  *   - fp32 row-major everywhere; int64 for sample_pdf indices (torch.searchsorted dtype).
+ *   - re-entrant per stream for the compute entry points.  The DIAGNOSTIC switches (spn_profile_enable / _read,
+ *     spn_launch_count, spn_tc_set_trace) are process-wide and unsynchronised: one measuring thread at a time.
  */
 #ifndef SPINNERF_B200_H
 #define SPINNERF_B200_H
@@ -274,8 +276,9 @@ int spn_render_rays_bwd(const spn_render_cfg* cfg, const spn_render_io* io,
 
 /* ---- end-to-end, HOST buffers (pinned or pageable): H2D, render, D2H inside ---------------- */
 /* Renders n rays given as a host ray matrix [n,ncols]; writes host rgb[n,3], disp[n], acc[n],
- * depth[n].  params_*_host are flat fp32 parameter vectors.  Synchronises.  This is the call
- * bench.py's `e2e` leg times. */
+ * depth[n].  params_*_host are flat fp32 parameter vectors.  Synchronises.  (bench.py's `e2e` leg times the train
+ * step — host batches -> Trainer.step_graphed -> loss read back — not this render-only call; the render workload's
+ * e2e goes through render_path_sharded.) */
 int spn_render_host(const spn_render_cfg* cfg, const float* rays_host,
                     const float* params_coarse_host, const float* params_fine_host,
                     float* rgb_host, float* disp_host, float* acc_host, float* depth_host);
