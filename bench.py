@@ -644,7 +644,8 @@ def main():
     def host_batches():
         return next(it)        # pinned host tensors: step_graphed copies them H2D into its static inputs
 
-    graph_e2e = os.environ.get("SPN_GRAPH_E2E", "1") != "0"     # N > 1: three graphs with the two eager all-reduces between them
+    # N > 1: three graphs with the two eager all-reduces between them; the opt-in peer-memory exchange is not graph-captured
+    graph_e2e = os.environ.get("SPN_GRAPH_E2E", "1") != "0" and tr.peer is None
 
     def e2e_steps(k):
         evs = []
@@ -772,7 +773,9 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "roofline": roofline, "cpu_baseline": cpu, "gpu_reference_port": gpu_port, "psnr_vs_ref": psnr, "n_rand_per_sec": value / RENDERS_PER_STEP,
             "wall_s_timed_region": wall, "final_loss": float(loss),
-            "stash": "activations E4M3, gradients bf16 (DESIGN.md section 3)"}
+            "stash": "activations E4M3, gradients bf16 (DESIGN.md section 3)",
+            "grad_exchange": ("peer-memory reduce-scatter / all-gather fused with Adam (SPN_P2P_ALLREDUCE=1)" if tr.peer is not None
+                              else "NCCL all-reduce per network, the fine one overlapped with the coarse backward") if world > 1 else None}
     if world == 1 and not args.no_other_workloads:
         phase("other workloads (BASELINE configs[2], configs[4]) as short separate runs")
         del tr, pool, rgb_pool, disp_pool, flush

@@ -16,6 +16,7 @@ run() { # name, timeout_s, bench args...
 }
 run strong  100 --scaling strong --n_rand_global 8192 --steps 20 --warmup 5 --no_cpu_baseline
 run weak    100 --steps 20 --warmup 5 --no_cpu_baseline
+SPN_P2P_ALLREDUCE=1 run weak_peer 100 --steps 20 --warmup 5 --no_cpu_baseline
 run render  100 --workload render --steps 3 --warmup 3
 run lpips   100 --workload train_lpips --steps 10 --warmup 3
 echo "=== check_multi_gpu_step"
