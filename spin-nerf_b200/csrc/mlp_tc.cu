@@ -409,11 +409,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == (warp >= 2 ? p.trace_block : 0);
 
   if (warp == kProdWarp) {
-    if (lane < 2 * kTsSlots) {
+    if (lane < kTsSlots) {
       // ================= weight producer: this CTA's half of every chunk, groups of two chunks per ring slot =================
       // The group sequence of a round is padded to 24 (c_g_nch: three empty groups), so every group sits in a ring slot that is
       // known at compile time (the MMA issuer addresses the ring with immediates) and slot s is used once per revolution.
-      const int slot = lane & 3, sub = lane >> 2;                  // lane (slot, sub) copies chunk `sub` of the groups in `slot`
+      // ONE lane per slot takes part in EVERY phase of its slot's barriers (waits for the release, arms the group, issues its
+      // copies), and the issuer waits for every group's full barrier — also an empty group's — before it releases the slot: a
+      // slot's two barriers then alternate strictly.  Round 2's first version had a second lane per slot (idle for one-chunk
+      // and empty groups) and released empty groups unseen; a lane that was not scheduled for the ~2 us between two
+      // consecutive releases of its slot then waited for a parity that had already come round again: one deadlock per
+      // ~1000 train steps (profiles/r02h_summary.md).
+      const int slot = lane;
       for (int it = 0; it < my_rounds; ++it) {
         const uint8_t* src = p.packed;
         for (int g = 0; g < kTsGroups; ++g) {
@@ -421,14 +427,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
           const uint32_t half = (uint32_t)c_g_half[g];
           if ((g & 3) == slot) {
             const uint32_t rev = (uint32_t)(it * (kTsGroups / 4) + (g >> 2));
-            mbar_wait(bar_empty + 8 * slot, (rev & 1u) ^ 1u);      // both lanes of the slot wait for every release
-            if (sub == 0) {
-              if (nch) mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)nch * half);
-              else mbar_arrive(bar_full + 8 * slot);               // empty group: the barrier still advances one phase per revolution
+            mbar_wait(bar_empty + 8 * slot, (rev & 1u) ^ 1u);
+            if (nch) {
+              mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)nch * half);
+              for (int sub = 0; sub < nch; ++sub)
+                bulk_g2s(sbase + TS_RING + slot * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)sub * 2 * half + (size_t)rank * half,
+                         half, bar_full + 8 * slot);
+            } else {
+              mbar_arrive(bar_full + 8 * slot);                    // empty group: same handshake, no bytes
             }
-            if (sub < nch)
-              bulk_g2s(sbase + TS_RING + slot * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)sub * 2 * half + (size_t)rank * half, half,
-                       bar_full + 8 * slot);
           }
           src += (size_t)nch * 2 * half;
         }
@@ -518,7 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
             }
-            if (last) { empty_commit(0); empty_commit(1); }
+            if (last) { full_wait(1, rev); empty_commit(0); empty_commit(1); }       // slot 1: the empty group behind layer 0
           } else {
             // four 64-wide K chunks from the slot's activations in TMEM: two ring slots of two chunks
             if (elect_one()) {
@@ -541,7 +548,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), bg + (uint64_t)(2 * k), idesc, 1u);
               }
-              if (last) { empty_commit(0); empty_commit(1); }
+              if (last) { full_wait(1, rev + 1); empty_commit(0); empty_commit(1); }   // slot 1: the empty group behind the skip layer
             } else if (kind == LK_VIEWS) {                   // + gamma(dir) part (K = 32): ring slot 2
               if (first) full_wait(2, rev);
               const uint64_t bg = ring_desc + (uint64_t)(2048 * 2);
@@ -549,7 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
 #pragma unroll
                 for (int k = 0; k < 2; ++k) umma_bf16_2cta(d_tmem, a_gam + (uint64_t)(2 * k), bg + (uint64_t)(2 * k), idesc, 1u);
               }
-              if (last) { empty_commit(2); empty_commit(3); }
+              if (last) { full_wait(3, rev); empty_commit(2); empty_commit(3); }       // slot 3: the empty group that ends the round
             }
           }
           if (elect_one()) umma_commit_2cta(bar_accfull + 8 * acc, 3);

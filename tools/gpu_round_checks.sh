@@ -29,7 +29,7 @@ run bench_sustained 300 python bench.py --gpus 1 --steps 2000 --warmup 5 --no_cp
 run bench_strong1  300 python bench.py --gpus 1 --scaling strong --n_rand_global 8192 --steps 20 --warmup 5 --no_cpu_baseline
 run ncu_launches   420 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 250 --csv \
                        --log-file "$OUT/${TAG}_launches.csv" python bench.py --steps 8 --warmup 3 --no_cpu_baseline --deadline 0
-run ncu_full       600 ncu --set full --clock-control none --import-source on -k 'regex:mlp_(fwd|dgrad|wgrad)_kernel' -s 18 -c 6 \
+run ncu_full       600 ncu --set full --clock-control none --import-source on -k 'regex:mlp_(fwd_ts|dgrad|wgrad)_kernel' -s 18 -c 6 \
                        -o "$OUT/${TAG}_mlp" -f python bench.py --steps 8 --warmup 3 --no_cpu_baseline --deadline 0
 run san_memcheck   600 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()"
 run san_racecheck  900 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()"
