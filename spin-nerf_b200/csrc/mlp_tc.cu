@@ -383,7 +383,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   const float* cst = reinterpret_cast<const float*>(p.packed + kFwdBytes + kBwdBytes);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsSlots; ++s) { mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_full + 8 * s, rank == 0 ? 2 : 1); }
+    // full: both producer lanes of the slot (+ the peer's relay on the leader)
+    for (int s = 0; s < kTsSlots; ++s) { mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_full + 8 * s, rank == 0 ? 3 : 2); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_accfull + 8 * t, 1);
       mbar_init(bar_accfree + 8 * t, 2 * kFwdEpiWarps);
@@ -409,17 +410,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == (warp >= 2 ? p.trace_block : 0);
 
   if (warp == kProdWarp) {
-    if (lane < kTsSlots) {
+    if (lane < 2 * kTsSlots) {
       // ================= weight producer: this CTA's half of every chunk, groups of two chunks per ring slot =================
       // The group sequence of a round is padded to 24 (c_g_nch: three empty groups), so every group sits in a ring slot that is
       // known at compile time (the MMA issuer addresses the ring with immediates) and slot s is used once per revolution.
-      // ONE lane per slot takes part in EVERY phase of its slot's barriers (waits for the release, arms the group, issues its
-      // copies), and the issuer waits for every group's full barrier — also an empty group's — before it releases the slot: a
-      // slot's two barriers then alternate strictly.  Round 2's first version had a second lane per slot (idle for one-chunk
-      // and empty groups) and released empty groups unseen; a lane that was not scheduled for the ~2 us between two
-      // consecutive releases of its slot then waited for a parity that had already come round again: one deadlock per
-      // ~1000 train steps (profiles/r02h_summary.md).
-      const int slot = lane;
+      // Two lanes per slot (a thread retires one cp.async.bulk per ~700 cycles): lane (slot, 0) arms the group's byte count and
+      // copies chunk 0, lane (slot, 1) copies chunk 1.  BOTH take part in EVERY phase of the slot's two barriers — both wait
+      // for the release, both arrive on the full barrier, also for one-chunk and empty groups — and the issuer waits for every
+      // group's full barrier, also an empty group's, before it releases the slot: the two barriers then alternate strictly.
+      // Round 2's first version let lane (slot, 1) sit out one-chunk / empty groups and released empty groups unseen; a lane
+      // that was not scheduled for the ~2 us between two consecutive releases of its slot then waited for a parity that had
+      // already come round again: one deadlock per ~1000 train steps (profiles/r02h_summary.md).
+      const int slot = lane & 3, sub = lane >> 2;
       for (int it = 0; it < my_rounds; ++it) {
         const uint8_t* src = p.packed;
         for (int g = 0; g < kTsGroups; ++g) {
@@ -428,14 +430,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
           if ((g & 3) == slot) {
             const uint32_t rev = (uint32_t)(it * (kTsGroups / 4) + (g >> 2));
             mbar_wait(bar_empty + 8 * slot, (rev & 1u) ^ 1u);
-            if (nch) {
-              mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)nch * half);
-              for (int sub = 0; sub < nch; ++sub)
-                bulk_g2s(sbase + TS_RING + slot * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)sub * 2 * half + (size_t)rank * half,
-                         half, bar_full + 8 * slot);
-            } else {
-              mbar_arrive(bar_full + 8 * slot);                    // empty group: same handshake, no bytes
-            }
+            if (sub == 0 && nch) mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)nch * half);
+            else mbar_arrive(bar_full + 8 * slot);
+            if (sub < nch)
+              bulk_g2s(sbase + TS_RING + slot * kSlotBytes + sub * (kSlotBytes / 2), src + (size_t)sub * 2 * half + (size_t)rank * half, half,
+                       bar_full + 8 * slot);
           }
           src += (size_t)nch * 2 * half;
         }

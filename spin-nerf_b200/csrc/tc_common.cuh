@@ -41,32 +41,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug must not hang the GPU box (that would cost a gpurun strike) — after
 // ~2^26 failed probes (seconds) the kernel traps and the launch reports an error instead.
-// On a timeout (wall clock: 2 s without progress) every waiting warp reports what it is blocked on — one line per warp — and the
-// kernel traps two seconds later, so that all lines make it out: together they are the wait-for graph of the deadlock.
-__device__ __forceinline__ unsigned long long globaltimer_ns_tc() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_timeout_report(const char* what, uint32_t bar, uint32_t parity, uint32_t& spins,
-                                                    unsigned long long& t0, bool& reported) {
-  if ((spins & 0x3ffu) != 0) return;
-  const unsigned long long now = globaltimer_ns_tc();
-  if (t0 == 0) { t0 = now; return; }
-  if (!reported && now - t0 > 2000000000ull) {
-    reported = true;
-    if ((threadIdx.x & 31) == __ffs(__activemask()) - 1)
-      printf("spinnerf_b200: %s timed out (block %d thread %d bar +0x%x parity %u)\n", what, (int)blockIdx.x, (int)threadIdx.x,
-             bar & 0x3ffu, parity);
-  }
-  if (now - t0 > 4000000000ull) __trap();
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  bool reported = false;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 16)) mbar_timeout_report("mbarrier wait", bar, parity, spins, t0, reported);
+    if (++spins > (1u << 26)) {
+      printf("spinnerf_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 
@@ -120,8 +102,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 // wait on a local mbarrier whose arrivals may come from the peer CTA, bounded like mbar_wait
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  unsigned long long t0 = 0;
-  bool reported = false;
   while (true) {
     uint32_t ok;
     asm volatile(
@@ -134,7 +114,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    if (++spins > (1u << 16)) mbar_timeout_report("cluster mbarrier wait", bar, parity, spins, t0, reported);
+    if (++spins > (1u << 26)) {
+      printf("spinnerf_b200: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 
