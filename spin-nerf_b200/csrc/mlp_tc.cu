@@ -420,7 +420,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) mlp
       // group's full barrier, also an empty group's, before it releases the slot: the two barriers then alternate strictly.
       // Round 2's first version let lane (slot, 1) sit out one-chunk / empty groups and released empty groups unseen; a lane
       // that was not scheduled for the ~2 us between two consecutive releases of its slot then waited for a parity that had
-      // already come round again: one deadlock per ~1000 train steps (profiles/r02h_summary.md).
+      // already come round again: one deadlock per ~1000 train steps (profiles/r02_summary.md).
       const int slot = lane & 3, sub = lane >> 2;
       for (int it = 0; it < my_rounds; ++it) {
         const uint8_t* src = p.packed;
