@@ -104,7 +104,7 @@ class Sim:
         assert self.done == set(self.threads), "threads did not finish: " + str(set(self.threads) - self.done)
 
 
-def simulate(chunks, rounds, seed, fwd_phase_formula, lane_skips_wait_bug=False):
+def simulate(chunks, rounds, seed, fwd_phase_formula, lane_skips_wait_bug=False, stall_prob=0.0):
     """chunks: per-step chunk counts; fwd_phase_formula: True -> group barrier index s % 4 with phase it*(n/4) + s//4
     (round 1's forward kernel), False -> running step counter gs: index gs % 4, phase gs // 4 (mlp_dgrad_kernel)."""
     sim = Sim(seed)
@@ -138,6 +138,8 @@ def simulate(chunks, rounds, seed, fwd_phase_formula, lane_skips_wait_bug=False)
                     if stage == slot_of_lane:
                         in_group = min(2, nch - 2 * g)
                         bi, ph = gidx(it, s)
+                        if rng.random() < stall_prob:
+                            yield ("sleep", rng.uniform(3000, 12000))        # the lane is descheduled for a few microseconds
                         # both lanes of the slot wait for EVERY release (phase ^ 1 parity, release number rev - 1)
                         if not (lane_skips_wait_bug and sub >= in_group):
                             yield ("wait", me["empty"][stage], (rev & 1) ^ 1, rev - 1)
@@ -163,6 +165,8 @@ def simulate(chunks, rounds, seed, fwd_phase_formula, lane_skips_wait_bug=False)
             for s in range(n_steps):
                 bi, ph = gidx(it, s)
                 for g in range(2):
+                    if rng.random() < stall_prob:
+                        yield ("sleep", rng.uniform(3000, 12000))
                     yield ("wait", peer["full"][g][bi], ph & 1, ph)
                     sim.at(rng.uniform(100, 900), lambda b=leader["full"][g][bi]: b.arrive())
 
@@ -229,6 +233,12 @@ def test_three_slot_ring_with_odd_chunk_counts(seed):
 @pytest.mark.parametrize("seed", range(8))
 def test_dgrad_pair_protocol(seed):
     assert simulate(DG_CHUNKS, rounds=9, seed=100 + seed, fwd_phase_formula=False) > 0
+
+
+def test_dgrad_pair_protocol_under_heavy_stalls():
+    for seed in range(4):
+        assert simulate(DG_CHUNKS, rounds=7, seed=200 + seed, fwd_phase_formula=False, stall_prob=0.25) > 0
+        assert simulate(R1_FWD_CHUNKS, rounds=5, seed=300 + seed, fwd_phase_formula=True, stall_prob=0.25) > 0
 
 
 def test_model_flags_the_revolution_skipping_producer():
