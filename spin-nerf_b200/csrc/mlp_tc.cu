@@ -130,13 +130,18 @@ int mlp_tc_pack(const float* params, void* packed, cudaStream_t st) {
 // ---- kernel geometry: see mlp_tc.cuh ---------------------------------------------------------------
 constexpr int kNumSteps = 12;
 
-// step tables (forward).  A step = one accumulation pass on the tensor cores followed by an epilogue action; the TS kernel
-// runs a layer = one or two steps (c_l_step0 / c_l_parts below) and takes the epilogue, bias row and mask slot of the last one.
+// step tables (forward).  A step = one accumulation pass on the tensor cores followed by an epilogue action.
 enum EpiAction : int { EPI_RELU = 0, EPI_WRITE_ENC = 1, EPI_LINEAR = 2, EPI_WRITE_DENC = 3, EPI_FINAL = 4, EPI_RELU_ALPHA = 5 };
+__constant__ int c_step_chunks[kNumSteps] = {1, 4, 4, 4, 4, 4, 1, 4, 4, 4, 4, 1};
+__constant__ int c_step_n[kNumSteps] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 128, 128};
+__constant__ int c_step_acc[kNumSteps] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+__constant__ int c_step_ksteps[kNumSteps] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2};
 __constant__ int c_step_epi[kNumSteps] = {EPI_RELU, EPI_RELU, EPI_RELU, EPI_RELU, EPI_RELU, EPI_WRITE_ENC, EPI_RELU,
                                           EPI_RELU, EPI_RELU_ALPHA, EPI_LINEAR, EPI_WRITE_DENC, EPI_FINAL};
 __constant__ int c_step_bias[kNumSteps] = {C_B + 0, C_B + 256, C_B + 512, C_B + 768, C_B + 1024, 0, C_B + 1280,
                                            C_B + 1536, C_B + 1792, C_BF, 0, C_BV};
+// stash slot written after the step's epilogue (-1: none).  Slots are 16 KB atoms inside the per-tile stash.
+__constant__ int c_step_stash_atom[kNumSteps] = {1, 5, 9, 13, 17, -1, 21, 25, 29, 33, -1, 37};
 __constant__ int c_step_mask_slot[kNumSteps] = {0, 1, 2, 3, 4, -1, 5, 6, 7, -1, -1, 8};
 
 size_t mlp_tc_stash_bytes(int64_t m) {
