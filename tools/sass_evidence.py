@@ -27,7 +27,7 @@ def main():
     if not os.path.exists(LIB):
         sys.exit(f"{LIB} not built: python -c 'import __graft_entry__ as g; g.build()'")
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
-    counts, cur, arch = collections.OrderedDict(), None, set()
+    counts, cur, arch, mix = collections.OrderedDict(), None, set(), {}
     for line in sass.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
@@ -38,6 +38,9 @@ def main():
         if cur is None or not re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             continue
         counts[cur]["instructions"] += 1
+        op = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        if op:
+            mix.setdefault(cur, collections.Counter())[op.group(1)] += 1
         for name, pat in PATTERNS:
             if re.search(pat, line):
                 counts[cur][name] += 1
@@ -63,6 +66,9 @@ def main():
             row = ", ".join(f"{n} {c[n]}" for n, _ in PATTERNS if c[n])
             if row:
                 print(f"    {row}")
+            if c["UTCHMMA"] and "mlp_" in short:        # static instruction mix of the three MLP kernels (all roles of the kernel together)
+                top = mix[k].most_common(14)
+                print("    mix: " + ", ".join(f"{n} {v}" for n, v in top))
 
 
 if __name__ == "__main__":
